@@ -1,0 +1,138 @@
+/*
+ * spkemb.h -- C ABI of libspkemb.so: the B200 (sm_100a) speaker-embedding hot path.
+ *
+ * The reference (CODEJIN/Speaker_Embedding_Torch) has no FFI: its hot path is the Python
+ * import `from Modules import GE2E, GE2E_Loss` (Train.py:9, Inference.py:14, Trace.py:4) and
+ * `from distributed import ...` (Train.py:15).  The entry points below are what a binding for
+ * that path calls; `speaker_embedding_torch_b200/_native.py` is the ctypes binding and
+ * `speaker_embedding_torch_b200/Modules.py` the drop-in module layer.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device buffer (inputs, outputs, workspaces, gradients)
+ *     is owned by the caller; the library allocates no device memory and keeps no pointers;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no host sync);
+ *   - return 0 on success, a negative errno-style code otherwise (SPK_EINVAL bad shape/alignment,
+ *     SPK_ENOMEM workspace too small, SPK_EIO CUDA error); text via spk_last_error() (thread-local);
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with SPK_EIO.
+ */
+#ifndef SPKEMB_H_
+#define SPKEMB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPK_ABI_VERSION 1
+#define SPK_EINVAL (-22)
+#define SPK_ENOMEM (-12)
+#define SPK_EIO (-5)
+#define SPK_MAX_LAYERS 8
+
+int spk_abi_version(void);
+const char* spk_last_error(void);
+
+/* Encoder hyper-parameters: the `GE2E:` block + Sound.Mel_Dim of Hyper_Parameters.yaml:3,10-18
+ * (read by GE2E.__init__, Modules.py:10-44).  This build supports mel_dim 80, emb 256, heads 4,
+ * ffn 1024 (= 4 * emb, hard-wired at Modules.py:29), 1..8 layers, max_pos >= T. */
+typedef struct spk_encoder_config {
+  int32_t mel_dim, emb, heads, ffn, layers, max_pos;
+  float pe_dropout;  /* GE2E.Positional_Encoding.Dropout_Rate */
+  float dropout;     /* GE2E.Transformer.Dropout_Rate */
+} spk_encoder_config;
+
+/* fp32 device pointers in the reference's state_dict layout.  The same
+ * struct describes the gradients (pe is ignored there; it is a buffer). */
+typedef struct spk_layer_params {
+  float* in_proj_w;  /* [3*emb, emb]  rows Wq | Wk | Wv */
+  float* in_proj_b;  /* [3*emb] */
+  float* out_proj_w; /* [emb, emb] */
+  float* out_proj_b; /* [emb] */
+  float* linear1_w;  /* [ffn, emb] */
+  float* linear1_b;  /* [ffn] */
+  float* linear2_w;  /* [emb, ffn] */
+  float* linear2_b;  /* [emb] */
+  float* norm1_w;    /* [emb] */
+  float* norm1_b;
+  float* norm2_w;
+  float* norm2_b;
+} spk_layer_params;
+
+typedef struct spk_encoder_params {
+  float* prenet_w;   /* [emb, mel_dim(,1)] */
+  float* prenet_b;   /* [emb] */
+  float* pe_alpha;   /* [1] */
+  float* pe;         /* [1, emb, max_pos] buffer */
+  spk_layer_params layer[SPK_MAX_LAYERS];
+  float* norm_w;     /* final LayerNorm [emb] */
+  float* norm_b;
+  float* proj_w;     /* [emb, emb(,1)] */
+  float* proj_b;     /* [emb] */
+} spk_encoder_params;
+
+/* precision: 1 = bf16 operands (inference), 2 = split-bf16 (hi+lo, 3 MMAs; training parity).
+ * keep_stash: 1 when spk_encoder_backward will follow (activations of every layer are kept). */
+size_t spk_encoder_workspace_bytes(const spk_encoder_config* cfg, int batch, int frames, int samples,
+                                   int precision, int keep_stash);
+
+/* GE2E.forward (Modules.py:46-59): mel [batch, mel_dim, frames] fp32 -> dvec [batch/samples, emb] fp32.
+ * training != 0 applies the 13 dropout sites with masks that are a pure function of `seed`. */
+int spk_encoder_forward(const spk_encoder_config* cfg, const spk_encoder_params* weights, const float* mel,
+                        int batch, int frames, int samples, int precision, int training, uint64_t seed,
+                        float* dvec, void* workspace, size_t workspace_bytes, int keep_stash, void* stream);
+
+/* Backward of the call above (same cfg/shape/precision/training/seed/workspace).  Accumulates
+ * (+=) into `grads`, which the caller zero-initialises; replaces autograd through Modules.py:46-59. */
+int spk_encoder_backward(const spk_encoder_config* cfg, const spk_encoder_params* weights,
+                         const spk_encoder_params* grads, const float* d_dvec, int batch, int frames,
+                         int samples, int precision, int training, uint64_t seed, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* GE2E_Loss.forward + backward (Modules.py:121-156) as one fused kernel.
+ * emb [speakers*per_speaker, dim] fp32, speaker-major rows; weight/bias: device pointers to the
+ * 0-dim parameters (logits = weight * cos - bias).  d_emb == NULL -> loss only. */
+size_t spk_ge2e_workspace_bytes(int speakers, int per_speaker);
+int spk_ge2e_loss(const float* emb, int speakers, int per_speaker, int dim, const float* weight,
+                  const float* bias, float* loss, float* d_emb, float* d_weight, float* d_bias,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused optimiser over a list of tensors (replaces Radam.py:25-90 / torch AdamW + the
+ * clip_grad_norm_ site Train.py:154-159).  One launch computes the global grad norm, one applies
+ * clip + update.  kind: 0 = RAdam (Radam.py), 1 = AdamW.  step is 1-based. */
+typedef struct spk_optim_tensors {
+  int32_t count;
+  float* param[64];
+  float* grad[64];
+  float* exp_avg[64];
+  float* exp_avg_sq[64];
+  int64_t numel[64];
+} spk_optim_tensors;
+int spk_optim_step(const spk_optim_tensors* tensors, int kind, int64_t step, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float max_grad_norm, float grad_scale,
+                   float* norm_scratch /* [2] fp32 */, void* stream);
+
+/* Diagnostic / benchmark entry: one tensor-core GEMM on split-bf16 operands,
+ * D[M,N] = A * B^T (+ bias, ReLU), used by the GEMM parity tests and the roofline bench. */
+typedef struct spk_gemm_desc {
+  const void* a; int64_t a_plane_stride, a_rows, a_cols, a_ld, a_sb0, a_sb1; int32_t a_mn;
+  const void* b; int64_t b_plane_stride, b_rows, b_cols, b_ld, b_sb0, b_sb1; int32_t b_mn;
+  int32_t planes, m, n, k, nb0, nb1, ksplit, block_n;
+  uint32_t flags;      /* bit0 bias, bit1 relu, bit8 fp32 out, bit9 fp32 atomic out */
+  float alpha;
+  const float* bias;
+  void* out; int64_t out_plane_stride, out_ld, out_sb0, out_sb1; int32_t out_planes;
+} spk_gemm_desc;
+int spk_gemm(const spk_gemm_desc* desc, void* stream);
+
+/* fp32 [n] -> split-bf16 planes (hi at dst, lo at dst + plane_stride elements). */
+int spk_split_pack(const float* src, void* dst, int64_t plane_stride, int planes, int64_t n, void* stream);
+
+/* Watchdog code of the last device-side pipeline timeout (0 = none); debugging aid. */
+int spk_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPKEMB_H_ */

@@ -1,0 +1,95 @@
+// extern "C" surface of libspkemb.so (declared in include/spkemb.h).  No C++ exception crosses it.
+#include "../../include/spkemb.h"
+#include "encoder.h"
+#include "ge2e.h"
+#include "gemm.h"
+#include "optim.h"
+#include "rowops.h"
+
+using namespace spk;
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int spk_abi_version(void) { return SPK_ABI_VERSION; }
+const char* spk_last_error(void) { return last_error_buf(); }
+
+size_t spk_encoder_workspace_bytes(const spk_encoder_config* cfg, int batch, int frames, int samples, int precision,
+                                   int keep_stash) {
+  if (!cfg) { set_error("null config"); return 0; }
+  return encoder_workspace_bytes(*cfg, batch, frames, samples, precision, keep_stash);
+}
+
+int spk_encoder_forward(const spk_encoder_config* cfg, const spk_encoder_params* weights, const float* mel, int batch,
+                        int frames, int samples, int precision, int training, uint64_t seed, float* dvec,
+                        void* workspace, size_t workspace_bytes, int keep_stash, void* stream) {
+  SPK_CHECK(cfg && weights && mel && dvec && workspace, "spk_encoder_forward: null argument");
+  return encoder_forward(*cfg, *weights, mel, batch, frames, samples, precision, training, seed, dvec, workspace,
+                         workspace_bytes, keep_stash, as_stream(stream));
+}
+
+int spk_encoder_backward(const spk_encoder_config* cfg, const spk_encoder_params* weights,
+                         const spk_encoder_params* grads, const float* d_dvec, int batch, int frames, int samples,
+                         int precision, int training, uint64_t seed, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  SPK_CHECK(cfg && weights && grads && d_dvec && workspace, "spk_encoder_backward: null argument");
+  return encoder_backward(*cfg, *weights, *grads, d_dvec, batch, frames, samples, precision, training, seed, workspace,
+                          workspace_bytes, as_stream(stream));
+}
+
+size_t spk_ge2e_workspace_bytes(int speakers, int per_speaker) { return ge2e_workspace_bytes(speakers, per_speaker); }
+
+int spk_ge2e_loss(const float* emb, int speakers, int per_speaker, int dim, const float* weight, const float* bias,
+                  float* loss, float* d_emb, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  SPK_CHECK(emb && weight && bias && loss && workspace, "spk_ge2e_loss: null argument");
+  SPK_CHECK(d_emb == nullptr || (d_weight && d_bias), "spk_ge2e_loss: d_weight/d_bias required with d_emb");
+  return ge2e_fused(emb, speakers, per_speaker, dim, weight, bias, loss, d_emb, d_weight, d_bias, workspace,
+                    workspace_bytes, as_stream(stream));
+}
+
+int spk_optim_step(const spk_optim_tensors* tensors, int kind, int64_t step, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, float max_grad_norm, float grad_scale, float* norm_scratch,
+                   void* stream) {
+  SPK_CHECK(tensors && norm_scratch, "spk_optim_step: null argument");
+  return optim_step(*tensors, kind, step, lr, beta1, beta2, eps, weight_decay, max_grad_norm, grad_scale, norm_scratch,
+                    as_stream(stream));
+}
+
+int spk_gemm(const spk_gemm_desc* d, void* stream) {
+  SPK_CHECK(d != nullptr, "spk_gemm: null descriptor");
+  GemmProblem g;
+  g.A.base = d->a; g.A.plane_stride = d->a_plane_stride; g.A.rows = d->a_rows; g.A.cols = d->a_cols; g.A.ld = d->a_ld;
+  g.A.sb0 = d->a_sb0; g.A.sb1 = d->a_sb1; g.a_mn = d->a_mn != 0;
+  g.B.base = d->b; g.B.plane_stride = d->b_plane_stride; g.B.rows = d->b_rows; g.B.cols = d->b_cols; g.B.ld = d->b_ld;
+  g.B.sb0 = d->b_sb0; g.B.sb1 = d->b_sb1; g.b_mn = d->b_mn != 0;
+  g.planes = d->planes; g.M = d->m; g.N = d->n; g.K = d->k; g.nb0 = d->nb0 < 1 ? 1 : d->nb0; g.nb1 = d->nb1 < 1 ? 1 : d->nb1;
+  g.ksplit = d->ksplit < 1 ? 1 : d->ksplit; g.block_n = d->block_n;
+  g.epi.flags = d->flags & (EPI_BIAS | EPI_RELU | EPI_OUT_F32 | EPI_OUT_ATOMIC);
+  g.epi.alpha = d->alpha; g.epi.bias = d->bias;
+  g.epi.out = d->out; g.epi.out_plane_stride = d->out_plane_stride; g.epi.out_ld = d->out_ld;
+  g.epi.out_sb0 = d->out_sb0; g.epi.out_sb1 = d->out_sb1; g.epi.out_planes = d->out_planes < 1 ? 1 : d->out_planes;
+  return gemm_run(g, as_stream(stream));
+}
+
+int spk_split_pack(const float* src, void* dst, int64_t plane_stride, int planes, int64_t n, void* stream) {
+  SPK_CHECK(src && dst && n >= 0 && (planes == 1 || planes == 2), "spk_split_pack: bad argument");
+  PackTable tab;
+  tab.count = 1;
+  tab.seg[0].src = src; tab.seg[0].dst_off = 0; tab.seg[0].n = n;
+  return pack_weights(tab, dst, plane_stride, planes, as_stream(stream));
+}
+
+int spk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  SPK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SPK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+}  // extern "C"

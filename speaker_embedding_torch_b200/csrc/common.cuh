@@ -1,0 +1,167 @@
+// Shared host/device helpers: error reporting, split-bf16 tensors, Philox dropout masks.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace spk {
+
+// ----------------------------------------------------------------------------- errors
+// Thread-local last-error text, exposed through spk_last_error() (api.cu).
+char* last_error_buf();
+void set_error(const char* fmt, ...);
+
+#define SPK_EINVAL (-22)
+#define SPK_ENOMEM (-12)
+#define SPK_EIO (-5)
+
+#define SPK_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      spk::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return SPK_EIO;                                                                       \
+    }                                                                                       \
+  } while (0)
+
+#define SPK_CHECK(cond, ...)       \
+  do {                             \
+    if (!(cond)) {                 \
+      spk::set_error(__VA_ARGS__); \
+      return SPK_EINVAL;           \
+    }                              \
+  } while (0)
+
+#define SPK_TRY(expr)        \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+// ----------------------------------------------------------------------------- split-bf16 tensors
+// Every activation / gradient that feeds a tensor-core GEMM is stored as one or two bf16
+// "planes": x ~= hi (planes = 1, inference) or x ~= hi + lo (planes = 2, training; ~16
+// mantissa bits).  A GEMM over two-plane operands issues Ah*Bh + Ah*Bl + Al*Bh, which
+// reproduces fp32 products to ~2^-16 (needed for grad parity <= 1e-3).
+// Plane p of a tensor with `plane_stride` elements starts at base + p * plane_stride.
+
+__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16lo_to_f(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi_to_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// Load 8 consecutive elements (16 B per plane, must be 16-B aligned) of a split tensor as fp32.
+__device__ __forceinline__ void load8_split(const __nv_bfloat16* base, size_t plane_stride, int planes, size_t off,
+                                            float (&v)[8]) {
+  uint4 h = *reinterpret_cast<const uint4*>(base + off);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = bf16lo_to_f(hw[i]);
+    v[2 * i + 1] = bf16hi_to_f(hw[i]);
+  }
+  if (planes > 1) {
+    uint4 l = *reinterpret_cast<const uint4*>(base + plane_stride + off);
+    const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] += bf16lo_to_f(lw[i]);
+      v[2 * i + 1] += bf16hi_to_f(lw[i]);
+    }
+  }
+}
+// Store 8 consecutive fp32 values as split planes (16-B aligned).
+__device__ __forceinline__ void store8_split(__nv_bfloat16* base, size_t plane_stride, int planes, size_t off,
+                                             const float (&v)[8]) {
+  uint32_t hw[4];
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    hw[i] = *reinterpret_cast<uint32_t*>(&p);
+    r[2 * i] = v[2 * i] - __bfloat162float(p.x);
+    r[2 * i + 1] = v[2 * i + 1] - __bfloat162float(p.y);
+  }
+  *reinterpret_cast<uint4*>(base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  if (planes > 1) {
+    uint32_t lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lw[i] = pack_bf16x2(r[2 * i], r[2 * i + 1]);
+    *reinterpret_cast<uint4*>(base + plane_stride + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+__device__ __forceinline__ float load1_split(const __nv_bfloat16* base, size_t plane_stride, int planes, size_t off) {
+  float v = __bfloat162float(base[off]);
+  if (planes > 1) v += __bfloat162float(base[plane_stride + off]);
+  return v;
+}
+__device__ __forceinline__ void store1_split(__nv_bfloat16* base, size_t plane_stride, int planes, size_t off, float x) {
+  __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  base[off] = hi;
+  if (planes > 1) base[plane_stride + off] = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// ----------------------------------------------------------------------------- Philox4x32-10
+// Counter-based RNG for dropout: the keep-mask of element `idx` at dropout site `site` is a pure
+// function of (seed, site, idx), so backward regenerates it instead of storing 13 masks.
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+// Keep-scale (0 or 1/(1-p)) for 4 consecutive elements idx4*4 .. idx4*4+3.
+__device__ __forceinline__ void dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx4, uint32_t thresh,
+                                               float inv_keep, float (&s)[4]) {
+  Philox4 r = philox4x32_10(static_cast<uint32_t>(idx4), static_cast<uint32_t>(idx4 >> 32), site, 0x5eedu,
+                            static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  s[0] = r.x >= thresh ? inv_keep : 0.f;
+  s[1] = r.y >= thresh ? inv_keep : 0.f;
+  s[2] = r.z >= thresh ? inv_keep : 0.f;
+  s[3] = r.w >= thresh ? inv_keep : 0.f;
+}
+
+struct DropCfg {
+  uint64_t seed;
+  uint32_t thresh;   // drop iff rand32 < thresh ; 0 disables
+  float inv_keep;    // 1 / (1 - p)
+};
+inline DropCfg make_drop(uint64_t seed, float p, bool training) {
+  DropCfg d;
+  d.seed = seed;
+  if (!training || p <= 0.f) { d.thresh = 0; d.inv_keep = 1.f; return d; }
+  double t = static_cast<double>(p) * 4294967296.0;
+  d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+  d.inv_keep = 1.f / (1.f - p);
+  return d;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace spk

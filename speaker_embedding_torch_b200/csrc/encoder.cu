@@ -1,0 +1,578 @@
+// Encoder orchestration: GE2E.forward / its backward as a fixed sequence of kernel launches over a
+// caller-owned workspace.  Mirrors /root/reference/Modules.py:46-59 (forward order) and the
+// post-LN torch.nn.TransformerEncoderLayer built at Modules.py:25-36; math: SURVEY.md Appendix B.
+//
+// Data layout in HBM (all token-major, tokens = slices * frames):
+//   split tensors  [planes][rows][cols] bf16   activations and gradients that feed tensor-core GEMMs
+//   fp32           LayerNorm statistics, head vectors, parameters and parameter gradients
+// Dense contractions run in gemm_tc.cu (tcgen05/TMEM/TMA); everything else is a coalesced row kernel.
+#include "encoder.h"
+#include "gemm.h"
+#include "rowops.h"
+
+namespace spk {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Split {
+  size_t off = 0;      // byte offset into the workspace
+  int64_t ps = 0;      // plane stride, elements
+};
+
+struct LayerBufs {
+  Split qkv, p, pd, att, z1, h1, f, z2, hout;
+  size_t st1 = 0, st2 = 0;
+};
+
+struct Plan {
+  int B, T, S, P, Tp, H, D, F, C, L;
+  int64_t Mt, BH;
+  bool keep;
+  Split wpack;
+  int64_t w_pre, w_in[SPK_MAX_LAYERS], w_out[SPK_MAX_LAYERS], w_l1[SPK_MAX_LAYERS], w_l2[SPK_MAX_LAYERS];
+  Split x0, h0, scr;
+  size_t pe_t;
+  LayerBufs Lb[SPK_MAX_LAYERS];
+  size_t hn, hst, emean, epre, de;
+  Split dh_a, dh_b, dz, dzd, df, datt, dqkv;
+  size_t total;
+};
+
+static Split take_split(size_t& cur, int64_t elems, int planes) {
+  Split s;
+  s.off = cur;
+  s.ps = static_cast<int64_t>(align_up(static_cast<size_t>(elems), 128));
+  cur = align_up(cur + static_cast<size_t>(s.ps) * planes * 2, 1024);
+  return s;
+}
+static size_t take_f32(size_t& cur, int64_t elems) {
+  size_t o = cur;
+  cur = align_up(cur + static_cast<size_t>(elems) * 4, 1024);
+  return o;
+}
+
+static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bool keep, Plan& pl) {
+  SPK_CHECK(c.mel_dim == 80 && c.emb == 256 && c.heads == 4 && c.ffn == 1024,
+            "encoder: this build supports Mel_Dim 80, Embedding_Size 256, Head 4 (got %d/%d/%d/%d)", c.mel_dim, c.emb,
+            c.heads, c.ffn);
+  SPK_CHECK(c.layers >= 1 && c.layers <= SPK_MAX_LAYERS, "encoder: Num_Layers %d out of range", c.layers);
+  SPK_CHECK(B >= 1 && T >= 1 && T <= c.max_pos && T <= 1024, "encoder: frames %d outside [1, %d]", T,
+            c.max_pos < 1024 ? c.max_pos : 1024);
+  SPK_CHECK(S >= 1 && B % S == 0, "encoder: batch %d is not a multiple of samples %d", B, S);
+  SPK_CHECK(P == 1 || P == 2, "encoder: precision must be 1 (bf16) or 2 (split-bf16)");
+  pl.B = B; pl.T = T; pl.S = S; pl.P = P; pl.Tp = (T + 7) / 8 * 8;
+  pl.H = c.heads; pl.D = c.emb; pl.F = c.ffn; pl.C = c.mel_dim; pl.L = c.layers;
+  pl.Mt = static_cast<int64_t>(B) * T;
+  pl.BH = static_cast<int64_t>(B) * pl.H;
+  pl.keep = keep;
+  const int64_t D = pl.D, F = pl.F, Mt = pl.Mt;
+  size_t cur = 0;
+  // packed weights
+  int64_t w = 0;
+  pl.w_pre = w; w += D * pl.C;
+  for (int l = 0; l < pl.L; ++l) {
+    pl.w_in[l] = w; w += 3 * D * D;
+    pl.w_out[l] = w; w += D * D;
+    pl.w_l1[l] = w; w += F * D;
+    pl.w_l2[l] = w; w += D * F;
+  }
+  pl.wpack = take_split(cur, w, P);
+  pl.x0 = take_split(cur, Mt * pl.C, P);
+  pl.h0 = take_split(cur, Mt * D, P);
+  pl.pe_t = take_f32(cur, static_cast<int64_t>(T) * D);
+  pl.scr = take_split(cur, pl.BH * T * pl.Tp, P);
+  const bool drop = keep;   // P_drop is only distinct in training; allocate with the stash
+  for (int l = 0; l < pl.L; ++l) {
+    if (l > 0 && !keep) { pl.Lb[l] = pl.Lb[0]; continue; }
+    LayerBufs& b = pl.Lb[l];
+    b.qkv = take_split(cur, Mt * 3 * D, P);
+    b.p = take_split(cur, pl.BH * T * pl.Tp, P);
+    b.pd = drop ? take_split(cur, pl.BH * T * pl.Tp, P) : b.p;
+    b.att = take_split(cur, Mt * D, P);
+    b.z1 = take_split(cur, Mt * D, P);
+    b.st1 = take_f32(cur, Mt * 2);
+    b.h1 = take_split(cur, Mt * D, P);
+    b.f = take_split(cur, Mt * F, P);
+    b.z2 = take_split(cur, Mt * D, P);
+    b.st2 = take_f32(cur, Mt * 2);
+    b.hout = keep ? take_split(cur, Mt * D, P) : pl.h0;
+  }
+  const int64_t Bo = B / S;
+  pl.hn = take_f32(cur, static_cast<int64_t>(B) * D);
+  pl.hst = take_f32(cur, static_cast<int64_t>(B) * 2);
+  pl.emean = take_f32(cur, Bo * D);
+  pl.epre = take_f32(cur, Bo * D);
+  pl.de = take_f32(cur, Bo * D);
+  if (keep) {
+    pl.dh_a = take_split(cur, Mt * D, P);
+    pl.dh_b = take_split(cur, Mt * D, P);
+    pl.dz = take_split(cur, Mt * D, P);
+    pl.dzd = take_split(cur, Mt * D, P);
+    pl.df = take_split(cur, Mt * F, P);
+    pl.datt = take_split(cur, Mt * D, P);
+    pl.dqkv = take_split(cur, Mt * 3 * D, P);
+  }
+  pl.total = cur + 1024;
+  return 0;
+}
+
+size_t encoder_workspace_bytes(const spk_encoder_config& c, int B, int T, int S, int P, int keep) {
+  Plan pl;
+  if (make_plan(c, B, T, S, P, keep != 0, pl) != 0) return 0;
+  return pl.total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// d-vector head (Modules.py:54-57): final LayerNorm of the t = 0 token of every slice, mean over the
+// `samples` slices of an utterance, 256x256 projection (fp32), L2 normalisation.
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ h, int64_t ps, int planes,
+                                                       int T, int S, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ wp,
+                                                       const float* __restrict__ bp, float* __restrict__ hn,
+                                                       float2* __restrict__ hst, float* __restrict__ emean,
+                                                       float* __restrict__ epre, float* __restrict__ dvec) {
+  __shared__ float red[8];
+  __shared__ float em[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t u = blockIdx.x;
+  auto bsum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    return s;
+  };
+  float acc = 0.f;
+  const float g = __ldg(gamma + tid), b = __ldg(beta + tid);
+  for (int s = 0; s < S; ++s) {
+    const int64_t slice = u * S + s;
+    const float x = load1_split(h, ps, planes, slice * T * 256 + tid);   // token t = 0
+    const float mean = bsum(x) * (1.f / 256.f);
+    const float xc = x - mean;
+    const float rstd = rsqrtf(bsum(xc * xc) * (1.f / 256.f) + 1e-5f);
+    const float y = xc * rstd * g + b;
+    hn[slice * 256 + tid] = y;
+    if (tid == 0) hst[slice] = make_float2(mean, rstd);
+    acc += y;
+  }
+  acc *= 1.f / static_cast<float>(S);
+  emean[u * 256 + tid] = acc;
+  em[tid] = acc;
+  __syncthreads();
+  // projection: warp w computes outputs w*32 .. w*32+31, lanes split the 256-long dot product
+  __shared__ float eo[256];
+  for (int j = 0; j < 32; ++j) {
+    const int n = warp * 32 + j;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + n * 256 + lane * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + n * 256 + lane * 8 + 4));
+    const float* e8 = em + lane * 8;
+    float d = w0.x * e8[0] + w0.y * e8[1] + w0.z * e8[2] + w0.w * e8[3] + w1.x * e8[4] + w1.y * e8[5] +
+              w1.z * e8[6] + w1.w * e8[7];
+    d = warp_sum(d);
+    if (lane == 0) eo[n] = d + __ldg(bp + n);
+  }
+  __syncthreads();
+  const float e = eo[tid];
+  epre[u * 256 + tid] = e;
+  const float nrm = fmaxf(sqrtf(bsum(e * e)), 1e-12f);
+  dvec[u * 256 + tid] = e / nrm;
+}
+
+// Backward of the head for one utterance: d_dvec -> de (pre-normalisation), d_emean, final-LN backward
+// into the t = 0 rows of dH (pre-zeroed), dgamma/dbeta of the final LayerNorm.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ g_dvec, const float* __restrict__ epre,
+                                                       const float* __restrict__ wp, const __nv_bfloat16* __restrict__ h,
+                                                       int64_t h_ps, int planes, const float2* __restrict__ hst,
+                                                       const float* __restrict__ gamma, int T, int S,
+                                                       float* __restrict__ de_out, __nv_bfloat16* __restrict__ dh,
+                                                       int64_t dh_ps, float* __restrict__ dgamma,
+                                                       float* __restrict__ dbeta) {
+  __shared__ float red[8];
+  __shared__ float des[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t u = blockIdx.x;
+  auto bsum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    return s;
+  };
+  const float e = epre[u * 256 + tid];
+  const float go = g_dvec[u * 256 + tid];
+  const float nrm = sqrtf(bsum(e * e));
+  float de;
+  if (nrm > 1e-12f) {            // block-uniform
+    const float d = e / nrm;
+    const float dot = bsum(go * d);
+    de = (go - dot * d) / nrm;
+  } else {
+    de = go / 1e-12f;
+  }
+  de_out[u * 256 + tid] = de;
+  des[tid] = de;
+  __syncthreads();
+  // d_emean[k] = sum_n Wp[n][k] * de[n]   (thread k; coalesced over k)
+  float dm = 0.f;
+#pragma unroll 8
+  for (int n = 0; n < 256; ++n) dm = fmaf(__ldg(wp + n * 256 + tid), des[n], dm);
+  dm *= 1.f / static_cast<float>(S);       // gradient of every slice's LayerNorm output
+  const float gam = __ldg(gamma + tid);
+  float ag = 0.f, ab = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const int64_t slice = u * S + s;
+    const int64_t off = slice * T * 256 + tid;
+    const float2 ms = hst[slice];
+    const float xh = (load1_split(h, h_ps, planes, off) - ms.x) * ms.y;
+    ag += dm * xh;
+    ab += dm;
+    const float gd = dm * gam;
+    const float m1 = bsum(gd) * (1.f / 256.f);
+    const float m2 = bsum(gd * xh) * (1.f / 256.f);
+    store1_split(dh, dh_ps, planes, off, ms.y * (gd - m1 - xh * m2));
+  }
+  atomicAdd(dgamma + tid, ag);
+  atomicAdd(dbeta + tid, ab);
+}
+
+// dWp[n][k] += sum_u de[u][n] * emean[u][k] ; dbp[n] += sum_u de[u][n]     (block n, thread k)
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ de, const float* __restrict__ emean,
+                                                         int64_t U, float* __restrict__ dwp, float* __restrict__ dbp) {
+  const int n = blockIdx.x, k = threadIdx.x;
+  float acc = 0.f, accb = 0.f;
+  for (int64_t u = 0; u < U; ++u) {
+    const float d = __ldg(de + u * 256 + n);
+    acc = fmaf(d, __ldg(emean + u * 256 + k), acc);
+    accb += d;
+  }
+  dwp[n * 256 + k] += acc;
+  if (k == 0) dbp[n] += accb;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Ctx {
+  const Plan& pl;
+  char* ws;
+  cudaStream_t st;
+  int P;
+  __nv_bfloat16* ptr(const Split& s, int64_t elem_off = 0) const {
+    return reinterpret_cast<__nv_bfloat16*>(ws + s.off) + elem_off;
+  }
+  float* f32(size_t off) const { return reinterpret_cast<float*>(ws + off); }
+  SplitMat mat(const Split& s, int64_t elem_off, int64_t rows, int64_t cols, int64_t ld, int64_t sb0 = 0,
+               int64_t sb1 = 0) const {
+    SplitMat m;
+    m.base = ptr(s, elem_off);
+    m.plane_stride = s.ps;
+    m.rows = rows; m.cols = cols; m.ld = ld; m.sb0 = sb0; m.sb1 = sb1;
+    return m;
+  }
+  void out(GemmEpilogue& e, const Split& s, int64_t elem_off, int64_t ld, int64_t sb0 = 0, int64_t sb1 = 0) const {
+    e.out = ptr(s, elem_off);
+    e.out_plane_stride = s.ps; e.out_ld = ld; e.out_sb0 = sb0; e.out_sb1 = sb1; e.out_planes = P;
+  }
+  void res(GemmEpilogue& e, const Split& s, int64_t ld) const {
+    e.res = ptr(s);
+    e.res_plane_stride = s.ps; e.res_ld = ld; e.res_planes = P;
+  }
+};
+
+int wgrad_ksplit(int64_t K, int M, int N) {
+  const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
+  const int kb = static_cast<int>((K + 63) / 64);
+  int ks = (2 * device_sm_count() + tiles - 1) / tiles;
+  if (ks > kb) ks = kb;
+  return ks < 1 ? 1 : ks;
+}
+
+// dW[M_out, N_in] += dY^T[M_out, tokens] * X[tokens, N_in]   (both operands read MN-major, split-K, fp32 atomics)
+int wgrad(const Ctx& c, const Split& dy, int64_t dy_cols, const Split& x, int64_t x_cols, float* dw) {
+  GemmProblem g;
+  g.A = c.mat(dy, 0, c.pl.Mt, dy_cols, dy_cols);
+  g.B = c.mat(x, 0, c.pl.Mt, x_cols, x_cols);
+  g.a_mn = true; g.b_mn = true; g.planes = c.P;
+  g.M = static_cast<int>(dy_cols); g.N = static_cast<int>(x_cols); g.K = static_cast<int>(c.pl.Mt);
+  g.ksplit = wgrad_ksplit(c.pl.Mt, g.M, g.N);
+  g.epi.flags = EPI_OUT_ATOMIC;
+  g.epi.out = dw; g.epi.out_ld = x_cols;
+  return gemm_run(g, c.st);
+}
+
+}  // namespace
+
+static void fill_pack_table(const Plan& pl, const spk_encoder_params& w, PackTable& tab) {
+  int n = 0;
+  auto add = [&](const float* src, int64_t off, int64_t cnt) { tab.seg[n].src = src; tab.seg[n].dst_off = off; tab.seg[n].n = cnt; ++n; };
+  const int64_t D = pl.D, F = pl.F;
+  add(w.prenet_w, pl.w_pre, D * pl.C);
+  for (int l = 0; l < pl.L; ++l) {
+    add(w.layer[l].in_proj_w, pl.w_in[l], 3 * D * D);
+    add(w.layer[l].out_proj_w, pl.w_out[l], D * D);
+    add(w.layer[l].linear1_w, pl.w_l1[l], F * D);
+    add(w.layer[l].linear2_w, pl.w_l2[l], D * F);
+  }
+  tab.count = n;
+}
+
+int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, const float* mel, int B, int T, int S,
+                    int P, int training, uint64_t seed, float* dvec, void* ws_v, size_t ws_bytes, int keep,
+                    cudaStream_t st) {
+  Plan pl;
+  SPK_TRY(make_plan(cfg, B, T, S, P, keep != 0, pl));
+  if (ws_bytes < pl.total) { set_error("encoder: workspace too small (%zu < %zu)", ws_bytes, pl.total); return SPK_ENOMEM; }
+  SPK_CHECK((reinterpret_cast<uintptr_t>(ws_v) & 255) == 0, "encoder: workspace must be 256-byte aligned");
+  SPK_CHECK(!training || keep, "encoder: training forward needs keep_stash (dropout P buffers live in the stash)");
+  Ctx c{pl, reinterpret_cast<char*>(ws_v), st, P};
+  const int64_t Mt = pl.Mt, D = pl.D, F = pl.F;
+  const int Tp = pl.Tp, H = pl.H;
+  const DropCfg drop_pe = make_drop(seed, cfg.pe_dropout, training != 0);
+  const DropCfg drop = make_drop(seed, cfg.dropout, training != 0);
+
+  PackTable tab;
+  fill_pack_table(pl, w, tab);
+  SPK_TRY(pack_weights(tab, c.ptr(pl.wpack), pl.wpack.ps, P, st));
+  SPK_TRY(mel_pack(mel, c.ptr(pl.x0), pl.x0.ps, P, B, pl.C, T, st));
+  SPK_TRY(pe_transpose(w.pe, c.f32(pl.pe_t), pl.D, cfg.max_pos, T, st));
+
+  {  // prenet k=1 conv + ReLU + alpha * PE (+ dropout)        Modules.py:50-52,98-105
+    GemmProblem g;
+    g.A = c.mat(pl.x0, 0, Mt, pl.C, pl.C);
+    g.B = c.mat(pl.wpack, pl.w_pre, D, pl.C, pl.C);
+    g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = pl.C;
+    g.epi.flags = EPI_BIAS | EPI_RELU | EPI_PE | (drop_pe.thresh ? EPI_DROPOUT : 0);
+    g.epi.bias = w.prenet_b; g.epi.pe_t = c.f32(pl.pe_t); g.epi.pe_alpha = w.pe_alpha; g.epi.pe_T = T;
+    g.epi.drop = drop_pe; g.epi.drop_site = 0;
+    c.out(g.epi, pl.h0, 0, D);
+    SPK_TRY(gemm_run(g, st));
+  }
+  for (int l = 0; l < pl.L; ++l) {
+    const LayerBufs& b = pl.Lb[l];
+    const Split& hin = (l == 0) ? pl.h0 : pl.Lb[l - 1].hout;
+    const spk_layer_params& lw = w.layer[l];
+    {  // in-proj
+      GemmProblem g;
+      g.A = c.mat(hin, 0, Mt, D, D);
+      g.B = c.mat(pl.wpack, pl.w_in[l], 3 * D, D, D);
+      g.planes = P; g.M = (int)Mt; g.N = (int)(3 * D); g.K = (int)D;
+      g.epi.flags = EPI_BIAS; g.epi.bias = lw.in_proj_b;
+      c.out(g.epi, b.qkv, 0, 3 * D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    {  // S = Q K^T / sqrt(dh), per (slice, head)
+      GemmProblem g;
+      g.A = c.mat(b.qkv, 0, T, 64, 3 * D, 64, (int64_t)T * 3 * D);
+      g.B = c.mat(b.qkv, D, T, 64, 3 * D, 64, (int64_t)T * 3 * D);
+      g.planes = P; g.M = T; g.N = Tp; g.K = 64; g.nb0 = H; g.nb1 = B;
+      g.epi.alpha = 0.125f;
+      c.out(g.epi, pl.scr, 0, Tp, (int64_t)T * Tp, (int64_t)H * T * Tp);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(softmax_fwd(c.ptr(pl.scr), pl.scr.ps, P, c.ptr(b.p), c.ptr(b.pd), drop, 1 + 4 * l, pl.BH * T, T, Tp, st));
+    {  // O = P V, heads written back interleaved into [tokens, 256]
+      GemmProblem g;
+      g.A = c.mat(drop.thresh ? b.pd : b.p, 0, T, T, Tp, (int64_t)T * Tp, (int64_t)H * T * Tp);
+      g.B = c.mat(b.qkv, 2 * D, T, 64, 3 * D, 64, (int64_t)T * 3 * D);
+      g.b_mn = true;
+      g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
+      c.out(g.epi, b.att, 0, D, 64, (int64_t)T * D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    {  // out-proj + dropout1 + residual
+      GemmProblem g;
+      g.A = c.mat(b.att, 0, Mt, D, D);
+      g.B = c.mat(pl.wpack, pl.w_out[l], D, D, D);
+      g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)D;
+      g.epi.flags = EPI_BIAS | EPI_RES | (drop.thresh ? EPI_DROPOUT : 0);
+      g.epi.bias = lw.out_proj_b; g.epi.drop = drop; g.epi.drop_site = 2 + 4 * l;
+      c.res(g.epi, hin, D);
+      c.out(g.epi, b.z1, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(ln_fwd(c.ptr(b.z1), b.z1.ps, P, 1, lw.norm1_w, lw.norm1_b, c.ptr(b.h1), b.h1.ps, P, c.f32(b.st1), Mt, st));
+    {  // linear1 + ReLU + dropout
+      GemmProblem g;
+      g.A = c.mat(b.h1, 0, Mt, D, D);
+      g.B = c.mat(pl.wpack, pl.w_l1[l], F, D, D);
+      g.planes = P; g.M = (int)Mt; g.N = (int)F; g.K = (int)D;
+      g.epi.flags = EPI_BIAS | EPI_RELU | (drop.thresh ? EPI_DROPOUT : 0);
+      g.epi.bias = lw.linear1_b; g.epi.drop = drop; g.epi.drop_site = 3 + 4 * l;
+      c.out(g.epi, b.f, 0, F);
+      SPK_TRY(gemm_run(g, st));
+    }
+    {  // linear2 + dropout2 + residual
+      GemmProblem g;
+      g.A = c.mat(b.f, 0, Mt, F, F);
+      g.B = c.mat(pl.wpack, pl.w_l2[l], D, F, F);
+      g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)F;
+      g.epi.flags = EPI_BIAS | EPI_RES | (drop.thresh ? EPI_DROPOUT : 0);
+      g.epi.bias = lw.linear2_b; g.epi.drop = drop; g.epi.drop_site = 4 + 4 * l;
+      c.res(g.epi, b.h1, D);
+      c.out(g.epi, b.z2, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(ln_fwd(c.ptr(b.z2), b.z2.ps, P, 1, lw.norm2_w, lw.norm2_b, c.ptr(b.hout), b.hout.ps, P, c.f32(b.st2), Mt, st));
+  }
+  const Split& hl = pl.Lb[pl.L - 1].hout;
+  head_fwd_kernel<<<B / S, 256, 0, st>>>(c.ptr(hl), hl.ps, P, T, S, w.norm_w, w.norm_b, w.proj_w, w.proj_b,
+                                         c.f32(pl.hn), reinterpret_cast<float2*>(c.f32(pl.hst)), c.f32(pl.emean),
+                                         c.f32(pl.epre), dvec);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w, const spk_encoder_params& gr,
+                     const float* d_dvec, int B, int T, int S, int P, int training, uint64_t seed, void* ws_v,
+                     size_t ws_bytes, cudaStream_t st) {
+  Plan pl;
+  SPK_TRY(make_plan(cfg, B, T, S, P, true, pl));
+  if (ws_bytes < pl.total) { set_error("encoder: workspace too small (%zu < %zu)", ws_bytes, pl.total); return SPK_ENOMEM; }
+  Ctx c{pl, reinterpret_cast<char*>(ws_v), st, P};
+  const int64_t Mt = pl.Mt, D = pl.D, F = pl.F;
+  const int Tp = pl.Tp, H = pl.H;
+  const DropCfg drop_pe = make_drop(seed, cfg.pe_dropout, training != 0);
+  const DropCfg drop = make_drop(seed, cfg.dropout, training != 0);
+
+  // ---- head
+  const Split& hl = pl.Lb[pl.L - 1].hout;
+  SPK_CUDA(cudaMemsetAsync(c.ptr(pl.dh_a), 0, static_cast<size_t>(pl.dh_a.ps) * P * 2, st));
+  head_bwd_kernel<<<B / S, 256, 0, st>>>(d_dvec, c.f32(pl.epre), w.proj_w, c.ptr(hl), hl.ps, P,
+                                         reinterpret_cast<const float2*>(c.f32(pl.hst)), w.norm_w, T, S, c.f32(pl.de),
+                                         c.ptr(pl.dh_a), pl.dh_a.ps, gr.norm_w, gr.norm_b);
+  SPK_CUDA(cudaGetLastError());
+  head_wgrad_kernel<<<256, 256, 0, st>>>(c.f32(pl.de), c.f32(pl.emean), B / S, gr.proj_w, gr.proj_b);
+  SPK_CUDA(cudaGetLastError());
+
+  for (int l = pl.L - 1; l >= 0; --l) {
+    const LayerBufs& b = pl.Lb[l];
+    const Split& hin = (l == 0) ? pl.h0 : pl.Lb[l - 1].hout;
+    const spk_layer_params& lw = w.layer[l];
+    const spk_layer_params& lg = gr.layer[l];
+    const Split& dy_ffn = drop.thresh ? pl.dzd : pl.dz;
+    // ---- LayerNorm2 backward: dH(out) -> dZ2 (residual path) and dZ2 * mask (FFN path)
+    SPK_TRY(ln_bwd(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.ptr(b.z2), b.z2.ps, P, c.f32(b.st2), lw.norm2_w, c.ptr(pl.dz),
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 4 + 4 * l, lg.norm2_w, lg.norm2_b, Mt, st));
+    SPK_TRY(colsum(c.ptr(dy_ffn), dy_ffn.ps, P, lg.linear2_b, Mt, (int)D, st));
+    SPK_TRY(wgrad(c, dy_ffn, D, b.f, F, lg.linear2_w));
+    {  // dU = (dY2 W2) * 1[f > 0] / (1 - p)
+      GemmProblem g;
+      g.A = c.mat(dy_ffn, 0, Mt, D, D);
+      g.B = c.mat(pl.wpack, pl.w_l2[l], D, F, F);
+      g.b_mn = true;
+      g.planes = P; g.M = (int)Mt; g.N = (int)F; g.K = (int)D;
+      g.epi.flags = EPI_GATE_POS;
+      g.epi.gate = c.ptr(b.f); g.epi.gate_plane_stride = b.f.ps; g.epi.gate_ld = F; g.epi.gate_planes = P;
+      g.epi.gate_scale = drop.inv_keep;
+      c.out(g.epi, pl.df, 0, F);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(colsum(c.ptr(pl.df), pl.df.ps, P, lg.linear1_b, Mt, (int)F, st));
+    SPK_TRY(wgrad(c, pl.df, F, b.h1, D, lg.linear1_w));
+    {  // dH1 = dU W1 + dZ2
+      GemmProblem g;
+      g.A = c.mat(pl.df, 0, Mt, F, F);
+      g.B = c.mat(pl.wpack, pl.w_l1[l], F, D, D);
+      g.b_mn = true;
+      g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)F;
+      g.epi.flags = EPI_RES;
+      c.res(g.epi, pl.dz, D);
+      c.out(g.epi, pl.dh_b, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    // ---- LayerNorm1 backward
+    const Split& dy_att = drop.thresh ? pl.dzd : pl.dz;
+    SPK_TRY(ln_bwd(c.ptr(pl.dh_b), pl.dh_b.ps, P, c.ptr(b.z1), b.z1.ps, P, c.f32(b.st1), lw.norm1_w, c.ptr(pl.dz),
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 2 + 4 * l, lg.norm1_w, lg.norm1_b, Mt, st));
+    SPK_TRY(colsum(c.ptr(dy_att), dy_att.ps, P, lg.out_proj_b, Mt, (int)D, st));
+    SPK_TRY(wgrad(c, dy_att, D, b.att, D, lg.out_proj_w));
+    {  // dATT = dY1 Wo
+      GemmProblem g;
+      g.A = c.mat(dy_att, 0, Mt, D, D);
+      g.B = c.mat(pl.wpack, pl.w_out[l], D, D, D);
+      g.b_mn = true;
+      g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)D;
+      c.out(g.epi, pl.datt, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    // ---- attention backward, per (slice, head)
+    const Split& pdrop = drop.thresh ? b.pd : b.p;
+    const int64_t sP0 = (int64_t)T * Tp, sP1 = (int64_t)H * T * Tp;
+    const int64_t sQ0 = 64, sQ1 = (int64_t)T * 3 * D, sA1 = (int64_t)T * D;
+    {  // dV = P_drop^T dO
+      GemmProblem g;
+      g.A = c.mat(pdrop, 0, T, T, Tp, sP0, sP1);
+      g.B = c.mat(pl.datt, 0, T, 64, D, 64, sA1);
+      g.a_mn = true; g.b_mn = true;
+      g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
+      c.out(g.epi, pl.dqkv, 2 * D, 3 * D, sQ0, sQ1);
+      SPK_TRY(gemm_run(g, st));
+    }
+    {  // dP_drop = dO V^T
+      GemmProblem g;
+      g.A = c.mat(pl.datt, 0, T, 64, D, 64, sA1);
+      g.B = c.mat(b.qkv, 2 * D, T, 64, 3 * D, sQ0, sQ1);
+      g.planes = P; g.M = T; g.N = Tp; g.K = 64; g.nb0 = H; g.nb1 = B;
+      c.out(g.epi, pl.scr, 0, Tp, sP0, sP1);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(softmax_bwd(c.ptr(b.p), c.ptr(pl.scr), pl.scr.ps, P, c.ptr(pl.scr), drop, 1 + 4 * l, 0.125f, pl.BH * T, T,
+                        Tp, st));
+    {  // dQ = dS K
+      GemmProblem g;
+      g.A = c.mat(pl.scr, 0, T, T, Tp, sP0, sP1);
+      g.B = c.mat(b.qkv, D, T, 64, 3 * D, sQ0, sQ1);
+      g.b_mn = true;
+      g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
+      c.out(g.epi, pl.dqkv, 0, 3 * D, sQ0, sQ1);
+      SPK_TRY(gemm_run(g, st));
+    }
+    {  // dK = dS^T Q
+      GemmProblem g;
+      g.A = c.mat(pl.scr, 0, T, T, Tp, sP0, sP1);
+      g.B = c.mat(b.qkv, 0, T, 64, 3 * D, sQ0, sQ1);
+      g.a_mn = true; g.b_mn = true;
+      g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
+      c.out(g.epi, pl.dqkv, D, 3 * D, sQ0, sQ1);
+      SPK_TRY(gemm_run(g, st));
+    }
+    // ---- in-proj
+    SPK_TRY(colsum(c.ptr(pl.dqkv), pl.dqkv.ps, P, lg.in_proj_b, Mt, (int)(3 * D), st));
+    SPK_TRY(wgrad(c, pl.dqkv, 3 * D, hin, D, lg.in_proj_w));
+    {  // dH(in) = dQKV Win + dZ1
+      GemmProblem g;
+      g.A = c.mat(pl.dqkv, 0, Mt, 3 * D, 3 * D);
+      g.B = c.mat(pl.wpack, pl.w_in[l], 3 * D, D, D);
+      g.b_mn = true;
+      g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)(3 * D);
+      g.epi.flags = EPI_RES;
+      c.res(g.epi, pl.dz, D);
+      c.out(g.epi, pl.dh_a, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+  }
+  // ---- embedding: positional alpha, prenet weight / bias  (ReLU gate recomputed from x0 W^T + b)
+  SPK_TRY(pe_alpha_grad(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.f32(pl.pe_t), drop_pe, 0, gr.pe_alpha, Mt, T, st));
+  {
+    GemmProblem g;
+    g.A = c.mat(pl.x0, 0, Mt, pl.C, pl.C);
+    g.B = c.mat(pl.wpack, pl.w_pre, D, pl.C, pl.C);
+    g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = pl.C;
+    g.epi.flags = EPI_BIAS | EPI_ACC_GATES_AUX;
+    g.epi.bias = w.prenet_b; g.epi.drop = drop_pe; g.epi.drop_site = 0;
+    c.res(g.epi, pl.dh_a, D);
+    c.out(g.epi, pl.dh_b, 0, D);
+    SPK_TRY(gemm_run(g, st));
+  }
+  SPK_TRY(colsum(c.ptr(pl.dh_b), pl.dh_b.ps, P, gr.prenet_b, Mt, (int)D, st));
+  SPK_TRY(wgrad(c, pl.dh_b, D, pl.x0, pl.C, gr.prenet_w));
+  return 0;
+}
+
+}  // namespace spk

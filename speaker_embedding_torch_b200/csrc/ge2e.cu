@@ -1,0 +1,324 @@
+// Fused GE2E loss: ONE cooperative kernel computes centroids, row/centroid normalisation, the
+// N*M x N cosine-similarity matrix, w*S - b, log-softmax cross-entropy, and its gradient
+// (dE, dw, db) without ever materialising the [N*M, N] logits or the reference's two
+// [N*M, N, D] expanded operands (/root/reference/Modules.py:121-156; math: SURVEY.md App. B).
+//
+//   phase 1  (block per speaker)   c_k = mean_m E ; ehat scale 1/max(|E_i|,eps) ; chat_k ; zero dchat
+//   phase 2  (block per 16 rows)   pass A: S tile -> online (max, sum) -> lse, loss
+//                                  pass B: recompute S tile -> G = (w/NM)(softmax - onehot)
+//                                          dehat += G * Chat   (registers)
+//                                          dchat += G^T * Ehat (coalesced fp32 RED)
+//                                  dE_i  = (dehat - (dehat.ehat) ehat) / |E_i|
+//   phase 3  (block per speaker)   dE_i += (1/M) (dchat_j - (dchat_j.chat_j) chat_j) / |c_j|
+//
+// fp32 SIMT math throughout (bit-for-bit deterministic except the fp32 atomics of dchat/loss).
+// D is fixed at 256 (= Embedding_Size of the reference hyper-parameters): thread <-> column.
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "ge2e.h"
+
+namespace cg = cooperative_groups;
+
+namespace spk {
+
+constexpr int GD = 256;        // embedding size
+constexpr int TR = 16;         // rows per block tile
+constexpr int TC = 64;         // centroids per tile
+constexpr int CPAD = GD + 4;   // padded centroid row (floats), keeps 16-B alignment, breaks bank aliasing
+
+struct Ge2eSmem {
+  float e[TR][GD];         // normalised rows
+  float c[TC][CPAD];       // normalised centroids tile
+  float g[TR][TC];         // G tile, row-major (for dchat)
+  float gt[TC][TR];        // G tile, transposed (for dehat)
+  float red[8][TR];
+  float rowv[TR];
+};
+
+__device__ __forceinline__ float block_sum_256(float v, float* red8) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red8[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red8[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(256, 2)
+ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __restrict__ w_ptr,
+                  const float* __restrict__ b_ptr, float* __restrict__ loss, float* __restrict__ dE,
+                  float* __restrict__ dw, float* __restrict__ db, float* __restrict__ chat,
+                  float* __restrict__ cinv, float* __restrict__ einv, float* __restrict__ dchat, int need_grad,
+                  float eps) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Ge2eSmem& sm = *reinterpret_cast<Ge2eSmem*>(smem_raw);
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t NM = static_cast<int64_t>(N) * M;
+  const float w = __ldg(w_ptr), b = __ldg(b_ptr);
+  float* red8 = &sm.red[0][0];
+
+  // ------------------------------------------------------------------ phase 1
+  if (blockIdx.x == 0 && tid == 0) {
+    loss[0] = 0.f;
+    if (need_grad) { dw[0] = 0.f; db[0] = 0.f; }
+  }
+  for (int k = blockIdx.x; k < N; k += gridDim.x) {
+    // warp per row: row norm + partial centroid (lane owns columns lane*8 .. +7)
+    float cpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int m = warp; m < M; m += 8) {
+      const float* row = E + (static_cast<int64_t>(k) * M + m) * GD + lane * 8;
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(row));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(row + 4));
+      const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { q += v[i] * v[i]; cpart[i] += v[i]; }
+      q = warp_sum(q);
+      if (lane == 0) einv[static_cast<int64_t>(k) * M + m] = 1.f / fmaxf(sqrtf(q), eps);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm.e[warp][lane * 8 + i] = cpart[i];
+    __syncthreads();
+    float cv = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) cv += sm.e[wv][tid];
+    cv *= 1.f / static_cast<float>(M);
+    const float nrm = fmaxf(sqrtf(block_sum_256(cv * cv, red8)), eps);
+    chat[static_cast<int64_t>(k) * GD + tid] = cv / nrm;
+    if (need_grad) dchat[static_cast<int64_t>(k) * GD + tid] = 0.f;
+    if (tid == 0) cinv[k] = 1.f / nrm;
+    __syncthreads();
+  }
+  grid.sync();
+
+  // ------------------------------------------------------------------ phase 2
+  const int r_loc = tid >> 4;      // 0..15 : row within tile (S-tile compute mapping)
+  const int cgp = tid & 15;        // columns cgp, cgp+16, cgp+32, cgp+48 of the centroid tile
+  const int64_t row_tiles = (NM + TR - 1) / TR;
+  const int col_tiles = (N + TC - 1) / TC;
+  const float inv_nm = 1.f / static_cast<float>(NM);
+
+  for (int64_t rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
+    const int64_t row0 = rt * TR;
+    __syncthreads();
+    // load + normalise 16 rows: warp handles rows warp, warp+8
+    for (int r = warp; r < TR; r += 8) {
+      const int64_t gi = row0 + r;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (gi < NM) {
+        const float sc = einv[gi];
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(E + gi * GD + lane * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(E + gi * GD + lane * 8 + 4));
+        v[0] = a0.x * sc; v[1] = a0.y * sc; v[2] = a0.z * sc; v[3] = a0.w * sc;
+        v[4] = a1.x * sc; v[5] = a1.y * sc; v[6] = a1.z * sc; v[7] = a1.w * sc;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm.e[r][lane * 8 + i] = v[i];
+    }
+    const int64_t my_row = row0 + r_loc;
+    const int my_label = (my_row < NM) ? static_cast<int>(my_row / M) : -1;
+    float run_max = -INFINITY, run_sum = 0.f, z_true = 0.f;
+    float lse = 0.f;
+    float dacc[TR];
+#pragma unroll
+    for (int r = 0; r < TR; ++r) dacc[r] = 0.f;
+    float dw_part = 0.f, db_part = 0.f;
+
+    for (int pass = 0; pass < (need_grad ? 2 : 1); ++pass) {
+      for (int ct = 0; ct < col_tiles; ++ct) {
+        const int c0 = ct * TC;
+        __syncthreads();
+        // centroid tile -> smem (coalesced float4)
+        for (int i = tid; i < TC * (GD / 4); i += 256) {
+          const int cr = i / (GD / 4), c4 = i % (GD / 4);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c0 + cr < N) v = __ldg(reinterpret_cast<const float4*>(chat + static_cast<int64_t>(c0 + cr) * GD) + c4);
+          *reinterpret_cast<float4*>(&sm.c[cr][c4 * 4]) = v;
+        }
+        __syncthreads();
+        // S tile: 4 dot products of length 256 per thread
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int d = 0; d < GD; d += 4) {
+          const float4 ev = *reinterpret_cast<const float4*>(&sm.e[r_loc][d]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 cvv = *reinterpret_cast<const float4*>(&sm.c[cgp + 16 * j][d]);
+            s[j] = fmaf(ev.x, cvv.x, s[j]);
+            s[j] = fmaf(ev.y, cvv.y, s[j]);
+            s[j] = fmaf(ev.z, cvv.z, s[j]);
+            s[j] = fmaf(ev.w, cvv.w, s[j]);
+          }
+        }
+        if (pass == 0) {
+          float tmax = -INFINITY;
+          float z[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = c0 + cgp + 16 * j;
+            z[j] = (col < N) ? w * s[j] - b : -INFINITY;
+            if (col == my_label) z_true = z[j];
+            tmax = fmaxf(tmax, z[j]);
+          }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+          const float new_max = fmaxf(run_max, tmax);
+          float part = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) part += (z[j] == -INFINITY) ? 0.f : expf(z[j] - new_max);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          run_sum = run_sum * ((run_max == -INFINITY) ? 0.f : expf(run_max - new_max)) + part;
+          run_max = new_max;
+        } else {
+          // G tile
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cl = cgp + 16 * j, col = c0 + cl;
+            float gval = 0.f;
+            if (col < N && my_row < NM) {
+              const float p = expf(w * s[j] - b - lse);
+              const float pm = (p - (col == my_label ? 1.f : 0.f)) * inv_nm;
+              dw_part += pm * s[j];
+              db_part -= pm;
+              gval = w * pm;
+            }
+            sm.g[r_loc][cl] = gval;
+            sm.gt[cl][r_loc] = gval;
+          }
+          __syncthreads();
+          // dehat[r][tid] += sum_c G[r][c] * chat[c][tid]
+#pragma unroll 4
+          for (int c = 0; c < TC; ++c) {
+            const float cvl = sm.c[c][tid];
+#pragma unroll
+            for (int r4 = 0; r4 < TR; r4 += 4) {
+              const float4 gv = *reinterpret_cast<const float4*>(&sm.gt[c][r4]);
+              dacc[r4 + 0] = fmaf(gv.x, cvl, dacc[r4 + 0]);
+              dacc[r4 + 1] = fmaf(gv.y, cvl, dacc[r4 + 1]);
+              dacc[r4 + 2] = fmaf(gv.z, cvl, dacc[r4 + 2]);
+              dacc[r4 + 3] = fmaf(gv.w, cvl, dacc[r4 + 3]);
+            }
+          }
+          // dchat[c][tid] += sum_r G[r][c] * ehat[r][tid]   (16 centroids at a time to bound registers)
+#pragma unroll 1
+          for (int cb = 0; cb < TC; cb += 16) {
+            if (c0 + cb >= N) break;
+            float a2[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a2[i] = 0.f;
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {
+              const float evl = sm.e[r][tid];
+#pragma unroll
+              for (int c4 = 0; c4 < 16; c4 += 4) {
+                const float4 gv = *reinterpret_cast<const float4*>(&sm.g[r][cb + c4]);
+                a2[c4 + 0] = fmaf(gv.x, evl, a2[c4 + 0]);
+                a2[c4 + 1] = fmaf(gv.y, evl, a2[c4 + 1]);
+                a2[c4 + 2] = fmaf(gv.z, evl, a2[c4 + 2]);
+                a2[c4 + 3] = fmaf(gv.w, evl, a2[c4 + 3]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + cb + i < N) atomicAdd(dchat + static_cast<int64_t>(c0 + cb + i) * GD + tid, a2[i]);
+          }
+        }
+      }
+      if (pass == 0) {
+        lse = run_max + logf(run_sum);
+        // loss contribution: one thread per row (cgp == 0 holds the reduced values; z_true lives in one lane)
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) z_true += __shfl_xor_sync(0xffffffffu, z_true, o);
+        float lrow = (cgp == 0 && my_row < NM) ? (lse - z_true) : 0.f;
+        const float lsum = block_sum_256(lrow, red8);
+        if (tid == 0) atomicAdd(loss, lsum * inv_nm);
+      }
+    }
+
+    if (need_grad) {
+      const float dws = block_sum_256(dw_part, red8);
+      const float dbs = block_sum_256(db_part, red8);
+      if (tid == 0) { atomicAdd(dw, dws); atomicAdd(db, dbs); }
+      // project out the radial component and write the row part of dE
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        float dot = warp_sum(dacc[r] * sm.e[r][tid]);
+        if (lane == 0) sm.red[warp][r] = dot;
+      }
+      __syncthreads();
+      if (tid < TR) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += sm.red[wv][tid];
+        sm.rowv[tid] = s;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        const int64_t gi = row0 + r;
+        if (gi < NM) dE[gi * GD + tid] = (dacc[r] - sm.rowv[r] * sm.e[r][tid]) * einv[gi];
+      }
+    }
+  }
+  if (!need_grad) return;
+  grid.sync();
+
+  // ------------------------------------------------------------------ phase 3
+  for (int k = blockIdx.x; k < N; k += gridDim.x) {
+    const float dc = dchat[static_cast<int64_t>(k) * GD + tid];
+    const float ch = chat[static_cast<int64_t>(k) * GD + tid];
+    const float dot = block_sum_256(dc * ch, red8);
+    const float u = (dc - dot * ch) * cinv[k] * (1.f / static_cast<float>(M));
+    for (int m = 0; m < M; ++m) dE[(static_cast<int64_t>(k) * M + m) * GD + tid] += u;
+  }
+}
+
+size_t ge2e_workspace_bytes(int N, int M) {
+  const size_t NM = static_cast<size_t>(N) * M;
+  return (2 * static_cast<size_t>(N) * GD + N + NM) * sizeof(float) + 256;
+}
+
+int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float* b, float* loss, float* dE, float* dw,
+               float* db, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SPK_CHECK(D == GD, "ge2e: embedding size %d not supported by this build (256)", D);
+  SPK_CHECK(N >= 1 && M >= 1, "ge2e: need at least one speaker and one utterance");
+  SPK_CHECK((reinterpret_cast<uintptr_t>(E) & 15) == 0, "ge2e: embeddings must be 16-byte aligned");
+  if (ws_bytes < ge2e_workspace_bytes(N, M)) {
+    set_error("ge2e: workspace too small (%zu < %zu)", ws_bytes, ge2e_workspace_bytes(N, M));
+    return SPK_ENOMEM;
+  }
+  const int need_grad = (dE != nullptr);
+  float* chat = reinterpret_cast<float*>(ws);
+  float* dchat = chat + static_cast<size_t>(N) * GD;
+  float* cinv = dchat + static_cast<size_t>(N) * GD;
+  float* einv = cinv + N;
+
+  static int max_blocks = 0;
+  const int smem = static_cast<int>(sizeof(Ge2eSmem));
+  if (max_blocks == 0) {
+    SPK_CUDA(cudaFuncSetAttribute(ge2e_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0, dev = 0, sms = 0;
+    SPK_CUDA(cudaGetDevice(&dev));
+    SPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ge2e_fused_kernel, 256, smem));
+    SPK_CHECK(per_sm >= 1, "ge2e: kernel does not fit on an SM");
+    max_blocks = per_sm * sms;
+  }
+  const long long NM = 1LL * N * M;
+  long long want = std::max<long long>((NM + TR - 1) / TR, N);
+  const int grid = static_cast<int>(std::min<long long>(want, max_blocks));
+  float eps = 1e-8f;
+  int ng = need_grad;
+  void* args[] = {(void*)&E, (void*)&N, (void*)&M, (void*)&w, (void*)&b, (void*)&loss, (void*)&dE, (void*)&dw,
+                  (void*)&db, (void*)&chat, (void*)&cinv, (void*)&einv, (void*)&dchat, (void*)&ng, (void*)&eps};
+  SPK_CUDA(cudaLaunchCooperativeKernel((void*)ge2e_fused_kernel, dim3(grid), dim3(256), args, smem, st));
+  return 0;
+}
+
+}  // namespace spk

@@ -1,0 +1,448 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a on split-bf16 operands.
+//
+//   D[M,N] = epilogue( alpha * A[M,K] * B[N,K]^T )          (per batch, optional split-K)
+//
+// * operands are fetched by TMA (cp.async.bulk.tensor.4d, 128-byte swizzle) into a multi-stage
+//   shared-memory ring; each operand may be K-major or MN-major (transposed reads for dgrad /
+//   wgrad / P*V come from the descriptor, never from a transposed copy);
+// * one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16 in, fp32 accumulate in
+//   TMEM); with two planes it issues Ah*Bh + Ah*Bl + Al*Bh into the same accumulator;
+// * the accumulator is double-buffered in TMEM so the 4 epilogue warps (tcgen05.ld -> registers
+//   -> fused bias / ReLU / positional term / dropout / residual / gate -> global) drain tile i
+//   while the MMA warp works on tile i+1;
+// * grid = min(#tiles, #SMs); tiles are assigned round-robin (persistent CTAs).
+//
+// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
+// 4..7 = epilogue (warp w owns TMEM lanes 32*(w-4) .. +31 == accumulator rows).
+#include "gemm.h"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace spk {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;              // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in limit per CTA
+constexpr int BAR_BYTES = 256;
+
+struct GemmKernelArgs {
+  CUtensorMap a_map[2];
+  CUtensorMap b_map[2];
+  int M, N, K;
+  int tiles_m, tiles_n, nb0, nb1, ksplit, kb_total, kb_per_split;
+  int a_batched, b_batched;
+  GemmEpilogue epi;
+};
+
+template <int PLANES, int BLOCK_N>
+struct TileCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int RAW_STAGES = (SMEM_LIMIT - 1024 - BAR_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static_assert(STAGES >= 2, "need at least a double buffer");
+  static_assert(2 * BLOCK_N <= 512, "accumulator double buffer must fit TMEM");
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue for 8 consecutive columns of one accumulator row.
+__device__ __forceinline__ void epilogue8(const GemmEpilogue& e, int N, int batch_M, int64_t row_in_batch,
+                                          int64_t batch, int64_t out_boff, int64_t res_boff, int col,
+                                          const uint32_t* acc, float pe_alpha) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = e.alpha * __uint_as_float(acc[i]);
+  const uint32_t f = e.flags;
+  if (f & EPI_BIAS) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (f & EPI_RELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (f & EPI_PE) {
+    const int64_t t = row_in_batch % e.pe_T;
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(e.pe_t + t * N + col));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(e.pe_t + t * N + col + 4));
+    v[0] += pe_alpha * p0.x; v[1] += pe_alpha * p0.y; v[2] += pe_alpha * p0.z; v[3] += pe_alpha * p0.w;
+    v[4] += pe_alpha * p1.x; v[5] += pe_alpha * p1.y; v[6] += pe_alpha * p1.z; v[7] += pe_alpha * p1.w;
+  }
+  float keep[8];
+  if (f & (EPI_DROPOUT | EPI_ACC_GATES_AUX)) {
+    if (e.drop.thresh != 0) {
+      const uint64_t idx = (static_cast<uint64_t>(batch) * batch_M + row_in_batch) * N + col;
+      float s0[4], s1[4];
+      dropout_scale4(e.drop.seed, e.drop_site, idx >> 2, e.drop.thresh, e.drop.inv_keep, s0);
+      dropout_scale4(e.drop.seed, e.drop_site, (idx >> 2) + 1, e.drop.thresh, e.drop.inv_keep, s1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { keep[i] = s0[i]; keep[4 + i] = s1[i]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) keep[i] = 1.f;
+    }
+  }
+  if (f & EPI_DROPOUT) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= keep[i];
+  }
+  if (f & (EPI_RES | EPI_ACC_GATES_AUX)) {
+    float r[8];
+    load8_split(reinterpret_cast<const __nv_bfloat16*>(e.res), e.res_plane_stride, e.res_planes,
+                res_boff + row_in_batch * e.res_ld + col, r);
+    if (f & EPI_RES) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += r[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? r[i] * keep[i] : 0.f;
+    }
+  }
+  if (f & EPI_GATE_POS) {
+    float g[8];
+    load8_split(reinterpret_cast<const __nv_bfloat16*>(e.gate), e.gate_plane_stride, e.gate_planes,
+                row_in_batch * e.gate_ld + col, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = g[i] > 0.f ? v[i] * e.gate_scale : 0.f;
+  }
+  const int64_t o = out_boff + row_in_batch * e.out_ld + col;
+  if (f & EPI_OUT_ATOMIC) {
+    float* dst = reinterpret_cast<float*>(e.out) + o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(dst + i, v[i]);
+  } else if (f & EPI_OUT_F32) {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + o);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    store8_split(reinterpret_cast<__nv_bfloat16*>(e.out), e.out_plane_stride, e.out_planes, o, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
+__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ GemmKernelArgs args) {
+  using Cfg = TileCfg<PLANES, BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto sA = [&](int s, int p) { return smem_base + s * Cfg::STAGE_BYTES + p * Cfg::A_BYTES; };
+  auto sB = [&](int s, int p) { return smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES + p * Cfg::B_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+#pragma unroll
+    for (int p = 0; p < PLANES; ++p) {
+      tma_prefetch_desc(&args.a_map[p]);
+      tma_prefetch_desc(&args.b_map[p]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles_per_batch = args.ksplit * args.tiles_m * args.tiles_n;
+  const int total_tiles = args.nb0 * args.nb1 * tiles_per_batch;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tn = t % args.tiles_n; t /= args.tiles_n;
+        const int tm = t % args.tiles_m; t /= args.tiles_m;
+        const int ks = t % args.ksplit;  t /= args.ksplit;
+        const int i0 = t % args.nb0, i1 = t / args.nb0;
+        const int a0 = args.a_batched ? i0 : 0, a1 = args.a_batched ? i1 : 0;
+        const int b0 = args.b_batched ? i0 : 0, b1 = args.b_batched ? i1 : 0;
+        const int kb_begin = ks * args.kb_per_split;
+        const int kb_end = min(kb_begin + args.kb_per_split, args.kb_total);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 0x100u + stage);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int p = 0; p < PLANES; ++p) {
+            if (!A_MN) {
+              tma_load_4d(sA(stage, p), &args.a_map[p], full_bar(stage), kb * BLOCK_K, tm * BLOCK_M, a0, a1);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BLOCK_M / 64; ++c)
+                tma_load_4d(sA(stage, p) + c * (BLOCK_K * 128), &args.a_map[p], full_bar(stage),
+                            tm * BLOCK_M + c * 64, kb * BLOCK_K, a0, a1);
+            }
+            if (!B_MN) {
+              tma_load_4d(sB(stage, p), &args.b_map[p], full_bar(stage), kb * BLOCK_K, tn * BLOCK_N, b0, b1);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BLOCK_N / 64; ++c)
+                tma_load_4d(sB(stage, p) + c * (BLOCK_K * 128), &args.b_map[p], full_bar(stage),
+                            tn * BLOCK_N + c * 64, kb * BLOCK_K, b0, b1);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        int t = tile / (args.tiles_n * args.tiles_m);
+        const int ks = t % args.ksplit;
+        const int kb_begin = ks * args.kb_per_split;
+        const int kb_end = min(kb_begin + args.kb_per_split, args.kb_total);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x200u + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        uint32_t accumulate = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(full_bar(stage), phase, 0x300u + stage);
+          tc_fence_after();
+#pragma unroll
+          for (int combo = 0; combo < (PLANES == 1 ? 1 : 3); ++combo) {
+            // small terms first: Al*Bh, Ah*Bl, then Ah*Bh
+            const int pa = (PLANES == 1) ? 0 : (combo == 0 ? 1 : 0);
+            const int pb = (PLANES == 1) ? 0 : (combo == 1 ? 1 : 0);
+            const uint32_t a_base = sA(stage, pa), b_base = sB(stage, pb);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t da = A_MN ? umma_smem_desc(a_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                       : umma_smem_desc(a_base + k * (UMMA_K * 2), 16, 1024);
+              const uint64_t db = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                       : umma_smem_desc(b_base + k * (UMMA_K * 2), 16, 1024);
+              umma_bf16(d_tmem, da, db, IDESC, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(empty_bar(stage));        // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));            // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue
+    const int w = warp - 4;
+    const GemmEpilogue& e = args.epi;
+    const float pe_alpha = (e.flags & EPI_PE) ? __ldg(e.pe_alpha) : 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int t = tile;
+      const int tn = t % args.tiles_n; t /= args.tiles_n;
+      const int tm = t % args.tiles_m; t /= args.tiles_m;
+      t /= args.ksplit;
+      const int i0 = t % args.nb0, i1 = t / args.nb0;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase, 0x400u + acc);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(tm) * BLOCK_M + w * 32 + lane;
+      const bool row_ok = row < args.M;
+      const int64_t out_boff = i0 * e.out_sb0 + i1 * e.out_sb1;
+      const int64_t res_boff = i0 * e.res_sb0 + i1 * e.res_sb1;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = tn * BLOCK_N + c * 32;
+        if (col0 >= args.N) break;             // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < args.N) epilogue8(e, args.N, args.M, row, t, out_boff, res_boff, col, r + g * 8, pe_alpha);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+// 4-D map {cols, rows, nb0, nb1}; box = {64, box_rows, 1, 1}; bf16; 128-byte swizzle; OOB -> zeros.
+static int make_map(CUtensorMap* map, const SplitMat& m, int plane, int nb0, int nb1, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  SPK_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const bool batched = (m.sb0 != 0 || m.sb1 != 0);
+  char* base = reinterpret_cast<char*>(const_cast<void*>(m.base)) + static_cast<int64_t>(plane) * m.plane_stride * 2;
+  SPK_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "GEMM operand base must be 16-byte aligned");
+  SPK_CHECK((m.ld * 2) % 16 == 0, "GEMM operand row stride must be a multiple of 16 bytes (ld=%lld)", (long long)m.ld);
+  const int64_t dflt = m.rows * m.ld;
+  cuuint64_t dims[4] = {(cuuint64_t)m.cols, (cuuint64_t)m.rows, (cuuint64_t)(batched ? nb0 : 1),
+                        (cuuint64_t)(batched ? nb1 : 1)};
+  int64_t s0 = (batched && nb0 > 1) ? m.sb0 : dflt;
+  int64_t s1 = (batched && nb1 > 1) ? m.sb1 : dflt * (batched ? nb0 : 1);
+  if (s0 <= 0) s0 = dflt;
+  if (s1 <= 0) s1 = dflt;
+  SPK_CHECK((s0 * 2) % 16 == 0 && (s1 * 2) % 16 == 0, "GEMM batch strides must be multiples of 16 bytes");
+  cuuint64_t strides[3] = {(cuuint64_t)(m.ld * 2), (cuuint64_t)(s0 * 2), (cuuint64_t)(s1 * 2)};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SPK_CHECK(r == CUDA_SUCCESS,
+            "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu x %llu ld %lld box_rows %d", (int)r,
+            (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+            (unsigned long long)dims[3], (long long)m.ld, box_rows);
+  return 0;
+}
+
+template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
+static int launch(const GemmKernelArgs& args, int grid, cudaStream_t stream) {
+  using Cfg = TileCfg<PLANES, BLOCK_N>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, PLANES, BLOCK_N>;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(args);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <bool A_MN, bool B_MN, int PLANES>
+static int launch_bn(int block_n, const GemmKernelArgs& args, int grid, cudaStream_t stream) {
+  switch (block_n) {
+    case 64: return launch<A_MN, B_MN, PLANES, 64>(args, grid, stream);
+    case 128: return launch<A_MN, B_MN, PLANES, 128>(args, grid, stream);
+    case 192: return launch<A_MN, B_MN, PLANES, 192>(args, grid, stream);
+    case 256: return launch<A_MN, B_MN, PLANES, 256>(args, grid, stream);
+  }
+  set_error("unsupported block_n %d", block_n);
+  return SPK_EINVAL;
+}
+
+template <int PLANES>
+static int launch_major(bool a_mn, bool b_mn, int block_n, const GemmKernelArgs& args, int grid, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_bn<false, false, PLANES>(block_n, args, grid, stream);
+  if (!a_mn && b_mn) return launch_bn<false, true, PLANES>(block_n, args, grid, stream);
+  if (a_mn && b_mn) return launch_bn<true, true, PLANES>(block_n, args, grid, stream);
+  set_error("A MN-major with B K-major is not instantiated");
+  return SPK_EINVAL;
+}
+
+int gemm_run(const GemmProblem& p, cudaStream_t stream) {
+  SPK_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %d x %d x %d", p.M, p.N, p.K);
+  SPK_CHECK(p.planes == 1 || p.planes == 2, "gemm: planes must be 1 or 2");
+  SPK_CHECK(p.N % 8 == 0, "gemm: N (%d) must be a multiple of 8", p.N);
+  SPK_CHECK(p.epi.out != nullptr, "gemm: no output");
+  SPK_CHECK(p.ksplit == 1 || (p.epi.flags & EPI_OUT_ATOMIC), "gemm: split-K needs the atomic epilogue");
+  // the non-contraction extent of an operand may be smaller than M / N: TMA zero-fills the rest
+  if (!p.a_mn) SPK_CHECK(p.A.rows <= p.M && p.A.cols == p.K, "gemm: A is not [<=M, K]");
+  else SPK_CHECK(p.A.rows == p.K && p.A.cols <= p.M, "gemm: A is not [K, <=M]");
+  if (!p.b_mn) SPK_CHECK(p.B.rows <= p.N && p.B.cols == p.K, "gemm: B is not [<=N, K]");
+  else SPK_CHECK(p.B.rows == p.K && p.B.cols <= p.N, "gemm: B is not [K, <=N]");
+
+  int bn = p.block_n;
+  if (bn == 0) bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : (p.N <= 192 ? 192 : 256));
+
+  GemmKernelArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int pl = 0; pl < p.planes; ++pl) {
+    SPK_TRY(make_map(&a.a_map[pl], p.A, pl, p.nb0, p.nb1, p.a_mn ? BLOCK_K : BLOCK_M));
+    SPK_TRY(make_map(&a.b_map[pl], p.B, pl, p.nb0, p.nb1, p.b_mn ? BLOCK_K : bn));
+  }
+  a.M = p.M; a.N = p.N; a.K = p.K;
+  a.tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  a.tiles_n = (p.N + bn - 1) / bn;
+  a.nb0 = p.nb0; a.nb1 = p.nb1;
+  a.kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  int ks = p.ksplit < 1 ? 1 : p.ksplit;
+  if (ks > a.kb_total) ks = a.kb_total;
+  a.kb_per_split = (a.kb_total + ks - 1) / ks;
+  a.ksplit = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  a.a_batched = (p.A.sb0 != 0 || p.A.sb1 != 0);
+  a.b_batched = (p.B.sb0 != 0 || p.B.sb1 != 0);
+  a.epi = p.epi;
+  const long long total = 1LL * a.nb0 * a.nb1 * a.ksplit * a.tiles_m * a.tiles_n;
+  SPK_CHECK(total < (1LL << 30), "gemm: too many tiles");
+  const int sms = device_sm_count();
+  const int grid = static_cast<int>(total < sms ? total : sms);
+  if (p.planes == 1) return launch_major<1>(p.a_mn, p.b_mn, bn, a, grid, stream);
+  return launch_major<2>(p.a_mn, p.b_mn, bn, a, grid, stream);
+}
+
+}  // namespace spk

@@ -1,0 +1,105 @@
+// Fused multi-tensor optimiser step: global gradient norm, clip (Train.py:154-159) and RAdam
+// (Radam.py:25-90) or AdamW update in two launches over a pointer table (no per-tensor Python loop).
+#include "optim.h"
+
+namespace spk {
+
+__global__ void __launch_bounds__(256) grad_sqnorm_kernel(const __grid_constant__ spk_optim_tensors t, float gs,
+                                                          float* __restrict__ out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int i = 0; i < t.count; ++i) {
+    const float* g = t.grad[i];
+    const int64_t n = t.numel[i];
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+      const float v = g[j] * gs;
+      acc = fmaf(v, v, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(out, s);
+  }
+}
+
+struct StepScalars {
+  int kind;          // 0 RAdam, 1 AdamW
+  int rectified;     // RAdam: N_sma >= 5
+  float lr, beta1, beta2, eps, wd;
+  float step_size;   // RAdam: Radam.py:70-76 ; AdamW: 1 / (1 - beta1^t)
+  float inv_sqrt_bc2;  // AdamW: 1 / sqrt(1 - beta2^t)
+  float max_norm, gs;
+};
+
+__global__ void __launch_bounds__(256) optim_update_kernel(const __grid_constant__ spk_optim_tensors t,
+                                                           const StepScalars s, const float* __restrict__ sqnorm) {
+  float coef = s.gs;
+  if (s.max_norm > 0.f) {
+    const float total = sqrtf(*sqnorm);
+    coef *= fminf(1.f, s.max_norm / (total + 1e-6f));
+  }
+  for (int i = 0; i < t.count; ++i) {
+    float* p = t.param[i];
+    const float* g = t.grad[i];
+    float* m = t.exp_avg[i];
+    float* v = t.exp_avg_sq[i];
+    const int64_t n = t.numel[i];
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+      const float gj = g[j] * coef;
+      float pj = p[j];
+      const float vj = s.beta2 * v[j] + (1.f - s.beta2) * gj * gj;
+      const float mj = s.beta1 * m[j] + (1.f - s.beta1) * gj;
+      v[j] = vj;
+      m[j] = mj;
+      if (s.kind == 0) {
+        if (s.wd != 0.f) pj += -s.wd * s.lr * pj;
+        if (s.rectified) pj += -s.step_size * s.lr * mj / (sqrtf(vj) + s.eps);
+        else pj += -s.step_size * s.lr * mj;
+      } else {
+        pj *= 1.f - s.lr * s.wd;
+        pj -= s.lr * s.step_size * mj / (sqrtf(vj) * s.inv_sqrt_bc2 + s.eps);
+      }
+      p[j] = pj;
+    }
+  }
+}
+
+int optim_step(const spk_optim_tensors& t, int kind, int64_t step, float lr, float beta1, float beta2, float eps,
+               float wd, float max_norm, float grad_scale, float* norm_scratch, cudaStream_t st) {
+  SPK_CHECK(t.count >= 1 && t.count <= 64, "optim: tensor count %d out of range", t.count);
+  SPK_CHECK(step >= 1, "optim: step is 1-based");
+  SPK_CHECK(kind == 0 || kind == 1, "optim: kind must be 0 (RAdam) or 1 (AdamW)");
+  StepScalars s;
+  s.kind = kind; s.lr = lr; s.beta1 = beta1; s.beta2 = beta2; s.eps = eps; s.wd = wd;
+  s.max_norm = max_norm; s.gs = grad_scale;
+  const double b1t = pow((double)beta1, (double)step), b2t = pow((double)beta2, (double)step);
+  if (kind == 0) {
+    const double n_max = 2.0 / (1.0 - beta2) - 1.0;
+    const double n_sma = n_max - 2.0 * step * b2t / (1.0 - b2t);
+    s.rectified = n_sma >= 5.0;
+    if (s.rectified)
+      s.step_size = (float)(sqrt((1.0 - b2t) * (n_sma - 4.0) / (n_max - 4.0) * (n_sma - 2.0) / n_sma * n_max /
+                                 (n_max - 2.0)) / (1.0 - b1t));
+    else
+      s.step_size = (float)(1.0 / (1.0 - b1t));
+    s.inv_sqrt_bc2 = 1.f;
+  } else {
+    s.rectified = 1;
+    s.step_size = (float)(1.0 / (1.0 - b1t));
+    s.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - b2t));
+  }
+  if (max_norm > 0.f) {
+    SPK_CUDA(cudaMemsetAsync(norm_scratch, 0, sizeof(float), st));
+    grad_sqnorm_kernel<<<296, 256, 0, st>>>(t, grad_scale, norm_scratch);
+    SPK_CUDA(cudaGetLastError());
+  }
+  optim_update_kernel<<<296, 256, 0, st>>>(t, s, norm_scratch);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace spk

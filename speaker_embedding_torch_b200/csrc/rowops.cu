@@ -1,0 +1,384 @@
+// Bandwidth-bound kernels of the encoder: layout packing, LayerNorm fwd/bwd, softmax fwd/bwd,
+// column sums (bias gradients).  All are coalesced 16-byte-vector kernels with warp-shuffle
+// reductions; rows of the 256-wide model dimension are handled one warp per row (8 elements / lane).
+#include "rowops.h"
+
+namespace spk {
+
+// ------------------------------------------------------------------------------------------------
+// fp32 weights -> split-bf16 planes, all matrices in one launch.
+__global__ void pack_weights_kernel(const __grid_constant__ PackTable tab, __nv_bfloat16* dst, int64_t plane_stride,
+                                    int planes) {
+  for (int s = 0; s < tab.count; ++s) {
+    const float* src = tab.seg[s].src;
+    const int64_t n = tab.seg[s].n, off = tab.seg[s].dst_off;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      store1_split(dst, plane_stride, planes, off + i, __ldg(src + i));
+  }
+}
+int pack_weights(const PackTable& tab, void* dst, int64_t plane_stride, int planes, cudaStream_t st) {
+  pack_weights_kernel<<<296, 256, 0, st>>>(tab, reinterpret_cast<__nv_bfloat16*>(dst), plane_stride, planes);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mel [B, C, T] fp32 (frames contiguous)  ->  token-major split tensor [B*T, C]   (C % 8 == 0)
+template <int C>
+__global__ void mel_pack_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ out, int64_t plane_stride,
+                                int planes, int T) {
+  __shared__ float tile[C][33];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 32;
+  const float* src = mel + static_cast<int64_t>(b) * C * T;
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+    const int c = i >> 5, tl = i & 31;
+    tile[c][tl] = (t0 + tl < T) ? __ldg(src + static_cast<int64_t>(c) * T + t0 + tl) : 0.f;
+  }
+  __syncthreads();
+  constexpr int G = C / 8;
+  for (int i = threadIdx.x; i < G * 32; i += blockDim.x) {
+    const int tl = i / G, g = i % G;
+    if (t0 + tl >= T) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = tile[g * 8 + j][tl];
+    store8_split(out, plane_stride, planes, (static_cast<int64_t>(b) * T + t0 + tl) * C + g * 8, v);
+  }
+}
+int mel_pack(const float* mel, void* out, int64_t plane_stride, int planes, int B, int C, int T, cudaStream_t st) {
+  SPK_CHECK(C == 80, "mel_pack: Mel_Dim %d not supported by this build (80)", C);
+  dim3 grid((T + 31) / 32, B);
+  mel_pack_kernel<80><<<grid, 256, 0, st>>>(mel, reinterpret_cast<__nv_bfloat16*>(out), plane_stride, planes, T);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// pe buffer [1, D, max_pos] -> pe_t [T, D]
+__global__ void pe_transpose_kernel(const float* __restrict__ pe, float* __restrict__ pe_t, int D, int max_pos, int T) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads: 8 rows per pass
+  for (int r = ty; r < 32; r += 8) {
+    const int d = d0 + r, t = t0 + tx;
+    tile[r][tx] = (d < D && t < T) ? __ldg(pe + static_cast<int64_t>(d) * max_pos + t) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, d = d0 + tx;
+    if (t < T && d < D) pe_t[static_cast<int64_t>(t) * D + d] = tile[tx][r];
+  }
+}
+int pe_transpose(const float* pe, float* pe_t, int D, int max_pos, int T, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, (D + 31) / 32);
+  pe_transpose_kernel<<<grid, 256, 0, st>>>(pe, pe_t, D, max_pos, T);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over D = 256, one warp per row.
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ z, int64_t z_ps, int z_planes,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     __nv_bfloat16* __restrict__ y, int64_t y_ps, int y_planes,
+                                                     float2* __restrict__ stats, int64_t rows, int64_t row_stride_rows,
+                                                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float g[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { g[i] = __ldg(gamma + lane * 8 + i); b[i] = __ldg(beta + lane * 8 + i); }
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float v[8];
+    load8_split(z, z_ps, z_planes, r * row_stride_rows * 256 + lane * 8, v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.f / 256.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = v[i] * rstd * g[i] + b[i];
+    store8_split(y, y_ps, y_planes, r * 256 + lane * 8, o);
+    if (lane == 0 && stats) stats[r] = make_float2(mean, rstd);
+  }
+}
+int ln_fwd(const void* z, int64_t z_ps, int z_planes, int64_t z_row_step, const float* gamma, const float* beta,
+           void* y, int64_t y_ps, int y_planes, float* stats, int64_t rows, cudaStream_t st) {
+  const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
+  ln_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(z), z_ps, z_planes, gamma, beta,
+                                        reinterpret_cast<__nv_bfloat16*>(y), y_ps, y_planes,
+                                        reinterpret_cast<float2*>(stats), rows, z_row_step, 1e-5f);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma ; dgamma += dy * xhat ; dbeta += dy
+// Optionally also writes dz_drop = dz * keep(site) (the gradient that enters the sub-layer's GEMMs).
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_ps, int dy_planes,
+                                                     const __nv_bfloat16* __restrict__ z, int64_t z_ps, int z_planes,
+                                                     const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                     __nv_bfloat16* __restrict__ dz, int64_t dz_ps, int dz_planes,
+                                                     __nv_bfloat16* __restrict__ dz_drop, DropCfg drop, uint32_t site,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     int64_t rows) {
+  __shared__ float red[2][8][256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float g[8], ag[8], ab[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { g[i] = __ldg(gamma + lane * 8 + i); ag[i] = 0.f; ab[i] = 0.f; }
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float d[8], x[8];
+    load8_split(dy, dy_ps, dy_planes, r * 256 + lane * 8, d);
+    load8_split(z, z_ps, z_planes, r * 256 + lane * 8, x);
+    const float2 ms = stats[r];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[i] = (x[i] - ms.x) * ms.y;
+      ag[i] += d[i] * x[i];
+      ab[i] += d[i];
+      d[i] *= g[i];
+      s1 += d[i];
+      s2 += d[i] * x[i];
+    }
+    s1 = warp_sum(s1) * (1.f / 256.f);
+    s2 = warp_sum(s2) * (1.f / 256.f);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = ms.y * (d[i] - s1 - x[i] * s2);
+    store8_split(dz, dz_ps, dz_planes, r * 256 + lane * 8, o);
+    if (dz_drop != nullptr) {
+      float k0[4], k1[4];
+      const uint64_t idx = static_cast<uint64_t>(r) * 256 + lane * 8;
+      dropout_scale4(drop.seed, site, idx >> 2, drop.thresh, drop.inv_keep, k0);
+      dropout_scale4(drop.seed, site, (idx >> 2) + 1, drop.thresh, drop.inv_keep, k1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { o[i] *= k0[i]; o[4 + i] *= k1[i]; }
+      store8_split(dz_drop, dz_ps, dz_planes, r * 256 + lane * 8, o);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][wib][lane * 8 + i] = ag[i]; red[1][wib][lane * 8 + i] = ab[i]; }
+  __syncthreads();
+  float sg = 0.f, sb = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { sg += red[0][w][threadIdx.x]; sb += red[1][w][threadIdx.x]; }
+  atomicAdd(dgamma + threadIdx.x, sg);
+  atomicAdd(dbeta + threadIdx.x, sb);
+}
+int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t z_ps, int z_planes, const float* stats,
+           const float* gamma, void* dz, int64_t dz_ps, int dz_planes, void* dz_drop, DropCfg drop, uint32_t site,
+           float* dgamma, float* dbeta, int64_t rows, cudaStream_t st) {
+  const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 4));
+  ln_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ps, dy_planes,
+                                        reinterpret_cast<const __nv_bfloat16*>(z), z_ps, z_planes,
+                                        reinterpret_cast<const float2*>(stats), gamma,
+                                        reinterpret_cast<__nv_bfloat16*>(dz), dz_ps, dz_planes,
+                                        (drop.thresh != 0) ? reinterpret_cast<__nv_bfloat16*>(dz_drop) : nullptr, drop,
+                                        site, dgamma, dbeta, rows);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax over the first T of Tp columns (Tp % 8 == 0, Tp <= 1024); one warp per row.
+// Writes P (and P_drop = P * keep / (1-p) when dropout is on); pad columns are written as zeros.
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* __restrict__ s, int64_t ps, int planes,
+                                                          __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ p_drop,
+                                                          DropCfg drop, uint32_t site, int64_t rows, int T, int Tp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float v[4][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < Tp) {
+        load8_split(s, ps, planes, r * Tp + col, v[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (col + i >= T) v[c][i] = -INFINITY;
+          mx = fmaxf(mx, v[c][i]);
+        }
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < Tp) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[c][i] = __expf(v[c][i] - mx); sum += v[c][i]; }
+      }
+    }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < Tp) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] *= inv;
+        store8_split(p, ps, planes, r * Tp + col, v[c]);
+        if (p_drop != nullptr) {
+          float k0[4], k1[4];
+          const uint64_t idx = static_cast<uint64_t>(r) * Tp + col;
+          dropout_scale4(drop.seed, site, idx >> 2, drop.thresh, drop.inv_keep, k0);
+          dropout_scale4(drop.seed, site, (idx >> 2) + 1, drop.thresh, drop.inv_keep, k1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { v[c][i] *= k0[i]; v[c][4 + i] *= k1[i]; }
+          store8_split(p_drop, ps, planes, r * Tp + col, v[c]);
+        }
+      }
+    }
+  }
+}
+int softmax_fwd(const void* s, int64_t ps, int planes, void* p, void* p_drop, DropCfg drop, uint32_t site,
+                int64_t rows, int T, int Tp, cudaStream_t st) {
+  SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
+  const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
+  softmax_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(s), ps, planes,
+                                             reinterpret_cast<__nv_bfloat16*>(p),
+                                             drop.thresh != 0 ? reinterpret_cast<__nv_bfloat16*>(p_drop) : nullptr,
+                                             drop, site, rows, T, Tp);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dS = scale * P * (dP' - sum_k dP'_k P_k),  dP' = dP_drop * keep/(1-p)
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p,
+                                                          const __nv_bfloat16* __restrict__ dp, int64_t ps, int planes,
+                                                          __nv_bfloat16* __restrict__ ds, DropCfg drop, uint32_t site,
+                                                          float scale, int64_t rows, int T, int Tp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float pv[4][8], dv[4][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < Tp) {
+        load8_split(p, ps, planes, r * Tp + col, pv[c]);
+        load8_split(dp, ps, planes, r * Tp + col, dv[c]);
+        if (drop.thresh != 0) {
+          float k0[4], k1[4];
+          const uint64_t idx = static_cast<uint64_t>(r) * Tp + col;
+          dropout_scale4(drop.seed, site, idx >> 2, drop.thresh, drop.inv_keep, k0);
+          dropout_scale4(drop.seed, site, (idx >> 2) + 1, drop.thresh, drop.inv_keep, k1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { dv[c][i] *= k0[i]; dv[c][4 + i] *= k1[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (col + i >= T) { pv[c][i] = 0.f; dv[c][i] = 0.f; }
+          dot += pv[c][i] * dv[c][i];
+        }
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < Tp) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = scale * pv[c][i] * (dv[c][i] - dot);
+        store8_split(ds, ps, planes, r * Tp + col, o);
+      }
+    }
+  }
+}
+int softmax_bwd(const void* p, const void* dp, int64_t ps, int planes, void* ds, DropCfg drop, uint32_t site,
+                float scale, int64_t rows, int T, int Tp, cudaStream_t st) {
+  SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
+  const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
+  softmax_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(p),
+                                             reinterpret_cast<const __nv_bfloat16*>(dp), ps, planes,
+                                             reinterpret_cast<__nv_bfloat16*>(ds), drop, site, scale, rows, T, Tp);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[c] += sum_r x[r, c]   (bias gradients).  C % 8 == 0, C <= 1024.
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ps, int planes,
+                                                     float* __restrict__ out, int64_t rows, int C, int rows_per_block) {
+  const int groups = C / 8;
+  const int lanes_r = 256 / groups > 0 ? 256 / groups : 1;   // row lanes per block
+  const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
+  if (rl >= lanes_r) return;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, rows);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = r0 + rl; r < r1; r += lanes_r) {
+    float v[8];
+    load8_split(x, ps, planes, r * C + g * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(out + g * 8 + i, acc[i]);
+}
+int colsum(const void* x, int64_t ps, int planes, float* out, int64_t rows, int C, cudaStream_t st) {
+  SPK_CHECK(C % 8 == 0 && C / 8 <= 256, "colsum: C=%d unsupported", C);
+  const int rpb = 512;
+  const int blocks = static_cast<int>((rows + rpb - 1) / rpb);
+  colsum_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ps, planes, out, rows, C, rpb);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// d_alpha += sum over tokens/channels of dH0 * keep(site 0) * pe_t[t]
+__global__ void __launch_bounds__(256) pe_alpha_grad_kernel(const __nv_bfloat16* __restrict__ dh, int64_t ps, int planes,
+                                                            const float* __restrict__ pe_t, DropCfg drop, uint32_t site,
+                                                            float* __restrict__ dalpha, int64_t rows, int T) {
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float acc = 0.f;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float d[8];
+    load8_split(dh, ps, planes, r * 256 + lane * 8, d);
+    if (drop.thresh != 0) {
+      float k0[4], k1[4];
+      const uint64_t idx = static_cast<uint64_t>(r) * 256 + lane * 8;
+      dropout_scale4(drop.seed, site, idx >> 2, drop.thresh, drop.inv_keep, k0);
+      dropout_scale4(drop.seed, site, (idx >> 2) + 1, drop.thresh, drop.inv_keep, k1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { d[i] *= k0[i]; d[4 + i] *= k1[i]; }
+    }
+    const float* pr = pe_t + (r % T) * 256 + lane * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += d[i] * __ldg(pr + i);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) red[wib] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(dalpha, s);
+  }
+}
+int pe_alpha_grad(const void* dh, int64_t ps, int planes, const float* pe_t, DropCfg drop, uint32_t site, float* dalpha,
+                  int64_t rows, int T, cudaStream_t st) {
+  const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 4));
+  pe_alpha_grad_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dh), ps, planes, pe_t, drop, site,
+                                               dalpha, rows, T);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace spk
