@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- GE2E train steps/sec (and d-vectors/sec) on N B200s, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference [--steps K] [--warmup W]       # reference CPU path (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W      # N > 1
+
+Workload (BASELINE.json configs[1]): one GE2E training step = encoder forward + GE2E loss + backward
++ gradient clip 1.0 + RAdam (lr 2e-3, eps 1e-6) with Modified-Noam(4000), on a synthetic batch of
+64 speakers x 15 utterances x T frames x 80 mel bins, one T drawn from [140, 180] per step
+(Datasets.py:77-84), dropout on (train mode).  N > 1: every rank owns its own 64 speakers (rank-local
+loss) and the flat gradient arena is averaged with one NCCL all-reduce -> weak scaling.
+
+One JSON line is printed by rank 0.  `value` is measured with inputs resident in HBM; `e2e` includes
+the pinned-host -> device copy of every batch and a device -> host read of the loss every step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SPEAKERS, UTTS, MEL = 64, 15, 80
+T_MIN, T_MAX = 140, 180
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sus=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+def synth_mel(gen, batch, frames, device):
+    """Log-mel-like features: clamp(-5 + 2 randn, ln 1e-5, 2)  (SURVEY.md 8d)."""
+    x = torch.randn(batch, MEL, frames, generator=gen, device=device) * 2.0 - 5.0
+    return x.clamp_(float(np.log(1e-5)), 2.0)
+
+
+def dense_flops_fwd(T):
+    """Algorithmic forward FLOPs per slice (dense accounting)."""
+    return 40960.0 * T + 3 * (1572864.0 * T + 1024.0 * T * T) + 131072.0
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's CPU path (Device -1)
+
+def cpu_train_step_rate(steps, warmup, budget_s=150.0):
+    """Times the oracle's restatement of the reference train step (fwd + GE2E + bwd + clip + RAdam,
+    dropout on) on the host cores, on a bounded sample: `spk` speakers x 15 utterances x 160 frames.
+    Returns steps/s scaled to the full 64-speaker batch, and a description of the sample."""
+    from oracle import ge2e_oracle as O
+    from oracle import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = O.to_torch_state(synth.make_state(0), torch.float32, requires_grad=True)
+    params = [v for k, v in state.items() if v.requires_grad]
+    w = torch.tensor(10.0, requires_grad=True)
+    b = torch.tensor(-5.0, requires_grad=True)
+    gen = torch.Generator().manual_seed(1234)
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+
+    def one_step(spk, step):
+        mel = torch.as_tensor(synth.make_mel(step, spk * UTTS, 160))
+        for p in params:
+            p.grad = None
+        d = O.encoder_forward(state, mel, 1, dropout_p=0.1, gen=gen)
+        loss = O.ge2e_loss(d, UTTS, w, b)
+        loss.backward()
+        total = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in params)).item()
+        coef = O.clip_coef(total, 1.0)
+        lr = O.modified_noam_lr(2e-3, step, 4000)
+        with torch.no_grad():
+            for p, mi, vi in zip(params, m, v):
+                O.radam_step(p.detach().numpy(), (p.grad * coef).numpy(), mi.numpy(), vi.numpy(), step + 1, lr,
+                             eps=1e-6)
+        return float(loss)
+
+    t0 = time.perf_counter()
+    one_step(2, 0)                                   # probe (also warms the allocator / threads)
+    per_spk = (time.perf_counter() - t0) / 2.0
+    spk = int(max(2, min(SPEAKERS, budget_s / max(per_spk * (steps + warmup), 1e-9))))
+    for i in range(warmup):
+        one_step(spk, i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one_step(spk, warmup + i)
+    dt = (time.perf_counter() - t0) / steps
+    rate = 1.0 / (dt * SPEAKERS / spk)
+    sample = "%d of 64 speakers x 15 utt x 160 frames per step, %d step(s), scaled x%.1f" % (
+        spk, steps, SPEAKERS / spk)
+    return rate, dt * 1e3 * SPEAKERS / spk, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    rate, ms, cores, sample = cpu_train_step_rate(steps, warmup)
+    line = {
+        "impl": "reference", "metric": "GE2E train steps/sec (64 spk x 15 utt, fwd+bwd+clip+RAdam/Noam)",
+        "value": rate, "unit": "steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "ge2e_train_step_64x15_T140-180", "device": "cpu (reference Device -1 path)"},
+        "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch.distributed as dist
+    from speaker_embedding_torch_b200 import GE2E, GE2E_Loss, _native
+    from speaker_embedding_torch_b200.Arg_Parser import default_hyper_parameters
+    from speaker_embedding_torch_b200.Noam_Scheduler import Modified_Noam_Scheduler
+    from speaker_embedding_torch_b200.Radam import RAdam
+    from speaker_embedding_torch_b200.distributed import apply_gradient_allreduce
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (B200); there is no CPU path. "
+                           "Use --impl reference for the CPU baseline.")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = max(1, args.steps), max(3, args.warmup)
+    pk = peaks()
+
+    torch.manual_seed(0)
+    model = GE2E(default_hyper_parameters())
+    with torch.no_grad():                      # perturb every tensor so no layer / bias is degenerate
+        g0 = torch.Generator().manual_seed(1)
+        for p in model.parameters():
+            p.add_(0.1 * torch.randn(p.shape, generator=g0) * (p.abs().mean() + 0.05))
+    model = model.to(dev).train()
+    crit = GE2E_Loss().to(dev)
+    if world > 1:
+        apply_gradient_allreduce(model)
+    opt = RAdam(model.parameters(), lr=2e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=1.0)
+    sched = Modified_Noam_Scheduler(opt, base=4000)
+
+    rs = np.random.RandomState(0)
+    lengths = [int(rs.randint(T_MIN, T_MAX + 1)) for _ in range(W + 2 * K + 4)]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    batch = SPEAKERS * UTTS
+
+    def step(mel):
+        opt.zero_grad(set_to_none=True)
+        d = model(mel)
+        loss = crit(d, UTTS)
+        loss.backward()
+        opt.step()
+        sched.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident inputs: `value`
+    dev_mels = [synth_mel(gen, batch, T, dev) for T in lengths[:W + K]]
+    for i in range(W):
+        step(dev_mels[i])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for i in range(K):
+            loss = step(dev_mels[W + i])
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * K / (ms_total * 1e-3)
+    last_loss = float(loss.item())
+    del dev_mels
+
+    # ---- end to end through the public API: pinned host batch -> H2D -> step -> loss D2H
+    host = [synth_mel(gen, batch, T, dev).cpu().pin_memory() for T in lengths[W + K:W + 2 * K]]
+    barrier()
+    e0.record()
+    for i in range(K):
+        mel = host[i].to(dev, non_blocking=True)
+        lv = step(mel).item()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * K / (float(t.item()) * 1e-3)
+    h2d = int(np.mean([h.numel() * 4 for h in host]))
+    del host
+
+    # ---- per-kernel profile (events around every launch; separate pass so it does not perturb `value`)
+    line_extra = {}
+    if rank == 0:
+        _native.prof_enable(True)
+        prof_steps = 2
+        Tp = lengths[W]
+        for i in range(prof_steps):
+            step(synth_mel(gen, batch, Tp, dev))
+        torch.cuda.synchronize()
+        rep = _native.prof_report()
+        _native.prof_enable(False)
+        launches_per_step = sum(r["launches"] for r in rep.values()) // prof_steps
+        tot_ms = sum(r["ms"] for r in rep.values())
+        top = max(rep.items(), key=lambda kv: kv[1]["ms"])
+        tag, r = top
+        per_launch_ms = r["ms"] / r["launches"]
+        tflops = r["flops"] / r["launches"] / (per_launch_ms * 1e-3) / 1e12
+        gbs = r["bytes"] / r["launches"] / (per_launch_ms * 1e-3) / 1e9
+        tensor_bound = r["flops"] > 0 and (r["flops"] / pk["tf_sus"] / 1e12) > (r["bytes"] / pk["hbm"] / 1e9)
+        roof = {"kernel": tag, "bound": "tensor" if tensor_bound else "hbm",
+                "achieved": tflops if tensor_bound else gbs, "peak": pk["tf_sus"] if tensor_bound else pk["hbm"],
+                "unit": "TFLOP/s" if tensor_bound else "GB/s", "traffic": None,
+                "peak_source": pk["src"] + (" sustained bf16" if tensor_bound else " copy"),
+                "launch_ms": per_launch_ms, "share_of_step": r["ms"] / tot_ms,
+                "alg_flops_per_launch": r["flops"] / r["launches"], "alg_bytes_per_launch": r["bytes"] / r["launches"]}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        breakdown = {k: {"ms_per_step": round(v["ms"] / prof_steps, 4), "launches": v["launches"] // prof_steps,
+                         "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else 0.0,
+                         "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)}
+                     for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
+        line_extra = {"roofline": roof, "gpu_launches": launches_per_step * K, "breakdown": breakdown,
+                      "profiled_step_ms": tot_ms / prof_steps, "profiled_T": Tp}
+
+        # ---- d-vectors/sec, 160-frame slices, eval (BASELINE metric part 1)
+        model.eval()
+        mel160 = synth_mel(gen, batch, 160, dev)
+        with torch.no_grad():
+            for _ in range(3):
+                model(mel160)
+            torch.cuda.synchronize()
+            e0.record()
+            reps = 10
+            for _ in range(reps):
+                model(mel160)
+            e1.record()
+            torch.cuda.synchronize()
+        dv_ms = e0.elapsed_time(e1) / reps
+        model.train()
+        line_extra["extra"] = {"dvectors_per_sec_160f_1gpu": batch / (dv_ms * 1e-3), "infer_ms_per_960x160_batch": dv_ms,
+                               "infer_tensor_frac_of_sustained": batch * dense_flops_fwd(160) / (dv_ms * 1e-3) / 1e12 / pk["tf_sus"],
+                               "train_tensor_frac_of_sustained": 3 * batch * dense_flops_fwd(160) * value / world / 1e12 / pk["tf_sus"],
+                               "last_loss": last_loss}
+
+    barrier()
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                rate, cms, cores, sample = cpu_train_step_rate(1, 0, budget_s=25.0)
+                cpu = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+            except Exception as exc:  # the baseline must never take the GPU number down with it
+                cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+                       "sample": "failed: %r" % (exc,)}
+        line = {
+            "metric": "GE2E train steps/sec (64 spk x 15 utt, fwd+bwd+clip+RAdam/Noam)",
+            "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 hi+lo operands, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "ge2e_train_step_64x15_T140-180", "speakers_per_gpu": SPEAKERS,
+                       "utterances_per_speaker": UTTS, "frames": "one T~U[140,180] per step", "mel": MEL,
+                       "optimizer": "fused RAdam lr2e-3 eps1e-6 + Modified_Noam(4000), clip 1.0",
+                       "dropout": 0.1, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; no flush needed"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "cpu_baseline": cpu,
+        }
+        line.update(line_extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,7 +72,8 @@ typedef struct spk_encoder_params {
   float* proj_b;     /* [emb] */
 } spk_encoder_params;
 
-/* precision: 1 = bf16 operands (inference), 2 = split-bf16 (hi+lo, 3 MMAs; training parity).
+/* precision: 1 = bf16 operands (inference), 2 = split-bf16 hi+lo (3 MMAs per product), 3 = hi+mid+lo
+ * (6 MMAs, fp32-equivalent forward; the backward pass then reads two of the three planes).
  * keep_stash: 1 when spk_encoder_backward will follow (activations of every layer are kept). */
 size_t spk_encoder_workspace_bytes(const spk_encoder_config* cfg, int batch, int frames, int samples,
                                    int precision, int keep_stash);
@@ -89,6 +90,10 @@ int spk_encoder_backward(const spk_encoder_config* cfg, const spk_encoder_params
                          const spk_encoder_params* grads, const float* d_dvec, int batch, int frames,
                          int samples, int precision, int training, uint64_t seed, void* workspace,
                          size_t workspace_bytes, void* stream);
+
+/* Test aid: text table "name byte_offset plane_stride" of the workspace buffers (returns bytes written). */
+int spk_encoder_debug_layout(const spk_encoder_config* cfg, int batch, int frames, int samples, int precision,
+                             int keep_stash, char* buf, size_t cap);
 
 /* GE2E_Loss.forward + backward (Modules.py:121-156) as one fused kernel.
  * emb [speakers*per_speaker, dim] fp32, speaker-major rows; weight/bias: device pointers to the
@@ -129,8 +134,14 @@ int spk_gemm(const spk_gemm_desc* desc, void* stream);
 /* fp32 [n] -> split-bf16 planes (hi at dst, lo at dst + plane_stride elements). */
 int spk_split_pack(const float* src, void* dst, int64_t plane_stride, int planes, int64_t n, void* stream);
 
-/* Watchdog code of the last device-side pipeline timeout (0 = none); debugging aid. */
 int spk_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Launch profiler (used by bench.py for the per-kernel roofline): when enabled every launcher brackets
+ * its kernel with CUDA events on the launching stream.  spk_prof_report synchronises those events,
+ * writes one text line per kernel tag -- "tag launches total_ms algorithmic_flops algorithmic_bytes" --
+ * into buf, clears the records and returns the number of bytes written. */
+int spk_prof_enable(int on);
+int spk_prof_report(char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

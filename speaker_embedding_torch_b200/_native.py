@@ -21,7 +21,8 @@ ABI_VERSION = 1
 EXPORTS = (
     "spk_abi_version", "spk_last_error", "spk_encoder_workspace_bytes", "spk_encoder_forward",
     "spk_encoder_backward", "spk_ge2e_workspace_bytes", "spk_ge2e_loss", "spk_optim_step",
-    "spk_gemm", "spk_split_pack", "spk_device_info",
+    "spk_gemm", "spk_split_pack", "spk_device_info", "spk_prof_enable", "spk_prof_report",
+    "spk_encoder_debug_layout",
 )
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
@@ -126,6 +127,13 @@ def lib():
         L.spk_split_pack.argtypes = [vp, vp, i64, i32, i64, vp]
         L.spk_device_info.restype = i32
         L.spk_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        L.spk_prof_enable.restype = i32
+        L.spk_prof_enable.argtypes = [i32]
+        L.spk_prof_report.restype = i32
+        L.spk_prof_report.argtypes = [ctypes.c_char_p, sz]
+        L.spk_encoder_debug_layout.restype = i32
+        L.spk_encoder_debug_layout.argtypes = [ctypes.POINTER(EncoderConfig), i32, i32, i32, i32, i32,
+                                               ctypes.c_char_p, sz]
         if L.spk_abi_version() != ABI_VERSION:
             raise RuntimeError("libspkemb.so ABI %d != binding ABI %d" % (L.spk_abi_version(), ABI_VERSION))
         _lib = L
@@ -210,4 +218,42 @@ def gemm(a, b, planes, m, n, k, a_mn=False, b_mn=False, bias=None, relu=False, o
     d.flags = flags
     d.out, d.out_ld = out.data_ptr(), n
     check(lib().spk_gemm(ctypes.byref(d), stream_ptr(a.device)), "spk_gemm")
+    return out
+
+
+def debug_layout(cfg, batch, frames, samples, precision, keep):
+    """{buffer name: (byte offset, plane stride in elements)} of the encoder workspace (tests only)."""
+    buf = ctypes.create_string_buffer(1 << 14)
+    n = lib().spk_encoder_debug_layout(ctypes.byref(cfg), batch, frames, samples, precision, int(keep), buf, len(buf))
+    out = {}
+    for line in buf.raw[:n].decode().splitlines():
+        name, off, ps = line.split()
+        out[name] = (int(off), int(ps))
+    return out
+
+
+def read_split(ws, layout, name, rows, cols, planes):
+    """Read a split tensor [rows, cols] out of a workspace uint8 tensor as fp32 (hi + lo)."""
+    off, ps = layout[name]
+    base = (ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr() + off
+    out = None
+    for p in range(planes):
+        start = base + p * ps * 2
+        t = ws[start:start + rows * cols * 2].view(torch.bfloat16).view(rows, cols).float()
+        out = t if out is None else out + t
+    return out
+
+
+def prof_enable(on=True):
+    lib().spk_prof_enable(int(on))
+
+
+def prof_report():
+    """-> {tag: dict(launches, ms, flops, bytes)} for the launches since the last report (synchronises)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib().spk_prof_report(buf, len(buf))
+    out = {}
+    for line in buf.raw[:n].decode().splitlines():
+        tag, cnt, ms, fl, by = line.split()
+        out[tag] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by))
     return out

@@ -38,6 +38,12 @@ int spk_encoder_backward(const spk_encoder_config* cfg, const spk_encoder_params
                           workspace_bytes, as_stream(stream));
 }
 
+int spk_encoder_debug_layout(const spk_encoder_config* cfg, int batch, int frames, int samples, int precision,
+                              int keep_stash, char* buf, size_t cap) {
+  SPK_CHECK(cfg && buf, "spk_encoder_debug_layout: null argument");
+  return encoder_debug_layout(*cfg, batch, frames, samples, precision, keep_stash, buf, cap);
+}
+
 size_t spk_ge2e_workspace_bytes(int speakers, int per_speaker) { return ge2e_workspace_bytes(speakers, per_speaker); }
 
 int spk_ge2e_loss(const float* emb, int speakers, int per_speaker, int dim, const float* weight, const float* bias,
@@ -74,12 +80,15 @@ int spk_gemm(const spk_gemm_desc* d, void* stream) {
 }
 
 int spk_split_pack(const float* src, void* dst, int64_t plane_stride, int planes, int64_t n, void* stream) {
-  SPK_CHECK(src && dst && n >= 0 && (planes == 1 || planes == 2), "spk_split_pack: bad argument");
+  SPK_CHECK(src && dst && n >= 0 && planes >= 1 && planes <= 3, "spk_split_pack: bad argument");
   PackTable tab;
   tab.count = 1;
   tab.seg[0].src = src; tab.seg[0].dst_off = 0; tab.seg[0].n = n;
   return pack_weights(tab, dst, plane_stride, planes, as_stream(stream));
 }
+
+int spk_prof_enable(int on) { prof_set(on != 0); return 0; }
+int spk_prof_report(char* buf, size_t cap) { return prof_report(buf, cap); }
 
 int spk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

@@ -13,6 +13,22 @@ namespace spk {
 char* last_error_buf();
 void set_error(const char* fmt, ...);
 
+bool prof_enabled();
+void prof_set(bool on);
+int prof_begin(const char* tag, double flops, double bytes, cudaStream_t st);
+void prof_end(int idx, cudaStream_t st);
+int prof_report(char* buf, size_t cap);
+struct ProfScope {
+  int idx = -1;
+  cudaStream_t st;
+  ProfScope(const char* tag, double flops, double bytes, cudaStream_t s) : st(s) {
+    if (prof_enabled()) idx = prof_begin(tag, flops, bytes, s);
+  }
+  ~ProfScope() {
+    if (idx >= 0) prof_end(idx, st);
+  }
+};
+
 #define SPK_EINVAL (-22)
 #define SPK_ENOMEM (-12)
 #define SPK_EIO (-5)
@@ -41,11 +57,14 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // ----------------------------------------------------------------------------- split-bf16 tensors
-// Every activation / gradient that feeds a tensor-core GEMM is stored as one or two bf16
-// "planes": x ~= hi (planes = 1, inference) or x ~= hi + lo (planes = 2, training; ~16
-// mantissa bits).  A GEMM over two-plane operands issues Ah*Bh + Ah*Bl + Al*Bh, which
-// reproduces fp32 products to ~2^-16 (needed for grad parity <= 1e-3).
-// Plane p of a tensor with `plane_stride` elements starts at base + p * plane_stride.
+// Every activation / gradient that feeds a tensor-core GEMM is stored as 1..3 bf16 "planes":
+//   planes = 1  x ~= hi                (8 mantissa bits;  inference)
+//   planes = 2  x ~= hi + lo           (~16 bits; backward pass: Ah*Bh + Ah*Bl + Al*Bh, 3 MMAs)
+//   planes = 3  x ~= hi + mid + lo     (~24 bits = fp32; training forward, 6 MMAs) -- needed because a
+//               forward error delta flips ~delta of the ReLU gates and the gradient error grows like
+//               sqrt(delta) (DESIGN.md "precision"), so grad parity <= 1e-3 needs an fp32-accurate forward.
+// Plane p of a tensor with `plane_stride` elements starts at base + p * plane_stride; a tensor
+// written with 3 planes can be read with 2 (the backward pass does).
 
 __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
@@ -68,8 +87,8 @@ __device__ __forceinline__ void load8_split(const __nv_bfloat16* base, size_t pl
     v[2 * i] = bf16lo_to_f(hw[i]);
     v[2 * i + 1] = bf16hi_to_f(hw[i]);
   }
-  if (planes > 1) {
-    uint4 l = *reinterpret_cast<const uint4*>(base + plane_stride + off);
+  for (int p = 1; p < planes; ++p) {
+    uint4 l = *reinterpret_cast<const uint4*>(base + p * plane_stride + off);
     const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -78,35 +97,35 @@ __device__ __forceinline__ void load8_split(const __nv_bfloat16* base, size_t pl
     }
   }
 }
-// Store 8 consecutive fp32 values as split planes (16-B aligned).
+// Store 8 consecutive fp32 values as split planes (16-B aligned): plane p holds bf16(residual after planes < p).
 __device__ __forceinline__ void store8_split(__nv_bfloat16* base, size_t plane_stride, int planes, size_t off,
                                              const float (&v)[8]) {
-  uint32_t hw[4];
   float r[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    hw[i] = *reinterpret_cast<uint32_t*>(&p);
-    r[2 * i] = v[2 * i] - __bfloat162float(p.x);
-    r[2 * i + 1] = v[2 * i + 1] - __bfloat162float(p.y);
-  }
-  *reinterpret_cast<uint4*>(base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-  if (planes > 1) {
-    uint32_t lw[4];
+  for (int i = 0; i < 8; ++i) r[i] = v[i];
+  for (int p = 0; p < planes; ++p) {
+    uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) lw[i] = pack_bf16x2(r[2 * i], r[2 * i + 1]);
-    *reinterpret_cast<uint4*>(base + plane_stride + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 q = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&q);
+      r[2 * i] -= __bfloat162float(q.x);
+      r[2 * i + 1] -= __bfloat162float(q.y);
+    }
+    *reinterpret_cast<uint4*>(base + p * plane_stride + off) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 __device__ __forceinline__ float load1_split(const __nv_bfloat16* base, size_t plane_stride, int planes, size_t off) {
   float v = __bfloat162float(base[off]);
-  if (planes > 1) v += __bfloat162float(base[plane_stride + off]);
+  for (int p = 1; p < planes; ++p) v += __bfloat162float(base[p * plane_stride + off]);
   return v;
 }
 __device__ __forceinline__ void store1_split(__nv_bfloat16* base, size_t plane_stride, int planes, size_t off, float x) {
-  __nv_bfloat16 hi = __float2bfloat16_rn(x);
-  base[off] = hi;
-  if (planes > 1) base[plane_stride + off] = __float2bfloat16_rn(x - __bfloat162float(hi));
+  for (int p = 0; p < planes; ++p) {
+    const __nv_bfloat16 q = __float2bfloat16_rn(x);
+    base[p * plane_stride + off] = q;
+    x -= __bfloat162float(q);
+  }
 }
 
 // ----------------------------------------------------------------------------- Philox4x32-10

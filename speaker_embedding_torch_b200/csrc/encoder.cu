@@ -59,7 +59,7 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
   SPK_CHECK(B >= 1 && T >= 1 && T <= c.max_pos && T <= 1024, "encoder: frames %d outside [1, %d]", T,
             c.max_pos < 1024 ? c.max_pos : 1024);
   SPK_CHECK(S >= 1 && B % S == 0, "encoder: batch %d is not a multiple of samples %d", B, S);
-  SPK_CHECK(P == 1 || P == 2, "encoder: precision must be 1 (bf16) or 2 (split-bf16)");
+  SPK_CHECK(P >= 1 && P <= 3, "encoder: precision must be 1 (bf16), 2 (hi+lo) or 3 (hi+mid+lo)");
   pl.B = B; pl.T = T; pl.S = S; pl.P = P; pl.Tp = (T + 7) / 8 * 8;
   pl.H = c.heads; pl.D = c.emb; pl.F = c.ffn; pl.C = c.mel_dim; pl.L = c.layers;
   pl.Mt = static_cast<int64_t>(B) * T;
@@ -103,14 +103,15 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
   pl.emean = take_f32(cur, Bo * D);
   pl.epre = take_f32(cur, Bo * D);
   pl.de = take_f32(cur, Bo * D);
-  if (keep) {
-    pl.dh_a = take_split(cur, Mt * D, P);
-    pl.dh_b = take_split(cur, Mt * D, P);
-    pl.dz = take_split(cur, Mt * D, P);
-    pl.dzd = take_split(cur, Mt * D, P);
-    pl.df = take_split(cur, Mt * F, P);
-    pl.datt = take_split(cur, Mt * D, P);
-    pl.dqkv = take_split(cur, Mt * 3 * D, P);
+  if (keep) {   // gradients are smooth in their inputs: two planes (~2^-16) are enough in the backward pass
+    const int Pb = P < 2 ? P : 2;
+    pl.dh_a = take_split(cur, Mt * D, Pb);
+    pl.dh_b = take_split(cur, Mt * D, Pb);
+    pl.dz = take_split(cur, Mt * D, Pb);
+    pl.dzd = take_split(cur, Mt * D, Pb);
+    pl.df = take_split(cur, Mt * F, Pb);
+    pl.datt = take_split(cur, Mt * D, Pb);
+    pl.dqkv = take_split(cur, Mt * 3 * D, Pb);
   }
   pl.total = cur + 1024;
   return 0;
@@ -120,6 +121,37 @@ size_t encoder_workspace_bytes(const spk_encoder_config& c, int B, int T, int S,
   Plan pl;
   if (make_plan(c, B, T, S, P, keep != 0, pl) != 0) return 0;
   return pl.total;
+}
+
+// Debug aid for the parity tests: byte offset / plane stride of every workspace buffer, one text line
+// per buffer: "name offset plane_stride_elems" (layer buffers as "L<l>.<name>").
+int encoder_debug_layout(const spk_encoder_config& c, int B, int T, int S, int P, int keep, char* buf, size_t cap) {
+  Plan pl;
+  SPK_TRY(make_plan(c, B, T, S, P, keep != 0, pl));
+  size_t off = 0;
+  auto put = [&](const char* pre, int l, const char* name, size_t o, int64_t ps) {
+    int n = l >= 0 ? snprintf(buf + off, off < cap ? cap - off : 0, "L%d.%s %zu %lld\n", l, name, o, (long long)ps)
+                   : snprintf(buf + off, off < cap ? cap - off : 0, "%s %zu %lld\n", name, o, (long long)ps);
+    (void)pre;
+    if (n > 0 && off + n < cap) off += n;
+  };
+  put("", -1, "x0", pl.x0.off, pl.x0.ps); put("", -1, "h0", pl.h0.off, pl.h0.ps);
+  put("", -1, "scr", pl.scr.off, pl.scr.ps); put("", -1, "pe_t", pl.pe_t, 0);
+  for (int l = 0; l < pl.L; ++l) {
+    const LayerBufs& b = pl.Lb[l];
+    put("", l, "qkv", b.qkv.off, b.qkv.ps); put("", l, "p", b.p.off, b.p.ps); put("", l, "att", b.att.off, b.att.ps);
+    put("", l, "z1", b.z1.off, b.z1.ps); put("", l, "h1", b.h1.off, b.h1.ps); put("", l, "f", b.f.off, b.f.ps);
+    put("", l, "z2", b.z2.off, b.z2.ps); put("", l, "hout", b.hout.off, b.hout.ps);
+    put("", l, "st1", b.st1, 0); put("", l, "st2", b.st2, 0);
+  }
+  put("", -1, "hn", pl.hn, 0); put("", -1, "emean", pl.emean, 0); put("", -1, "epre", pl.epre, 0); put("", -1, "de", pl.de, 0);
+  if (keep) {
+    put("", -1, "dh_a", pl.dh_a.off, pl.dh_a.ps); put("", -1, "dh_b", pl.dh_b.off, pl.dh_b.ps);
+    put("", -1, "dz", pl.dz.off, pl.dz.ps); put("", -1, "dzd", pl.dzd.off, pl.dzd.ps);
+    put("", -1, "df", pl.df.off, pl.df.ps); put("", -1, "datt", pl.datt.off, pl.datt.ps);
+    put("", -1, "dqkv", pl.dqkv.off, pl.dqkv.ps);
+  }
+  return static_cast<int>(off);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -294,8 +326,10 @@ int wgrad_ksplit(int64_t K, int M, int N) {
 }
 
 // dW[M_out, N_in] += dY^T[M_out, tokens] * X[tokens, N_in]   (both operands read MN-major, split-K, fp32 atomics)
-int wgrad(const Ctx& c, const Split& dy, int64_t dy_cols, const Split& x, int64_t x_cols, float* dw) {
+int wgrad(const Ctx& c, const Split& dy, int64_t dy_cols, const Split& x, int64_t x_cols, float* dw,
+          const char* tag) {
   GemmProblem g;
+  g.tag = tag;
   g.A = c.mat(dy, 0, c.pl.Mt, dy_cols, dy_cols);
   g.B = c.mat(x, 0, c.pl.Mt, x_cols, x_cols);
   g.a_mn = true; g.b_mn = true; g.planes = c.P;
@@ -344,6 +378,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
 
   {  // prenet k=1 conv + ReLU + alpha * PE (+ dropout)        Modules.py:50-52,98-105
     GemmProblem g;
+    g.tag = "gemm.prenet";
     g.A = c.mat(pl.x0, 0, Mt, pl.C, pl.C);
     g.B = c.mat(pl.wpack, pl.w_pre, D, pl.C, pl.C);
     g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = pl.C;
@@ -359,6 +394,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     const spk_layer_params& lw = w.layer[l];
     {  // in-proj
       GemmProblem g;
+      g.tag = "gemm.qkv";
       g.A = c.mat(hin, 0, Mt, D, D);
       g.B = c.mat(pl.wpack, pl.w_in[l], 3 * D, D, D);
       g.planes = P; g.M = (int)Mt; g.N = (int)(3 * D); g.K = (int)D;
@@ -368,6 +404,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     }
     {  // S = Q K^T / sqrt(dh), per (slice, head)
       GemmProblem g;
+      g.tag = "gemm.attn_qk";
       g.A = c.mat(b.qkv, 0, T, 64, 3 * D, 64, (int64_t)T * 3 * D);
       g.B = c.mat(b.qkv, D, T, 64, 3 * D, 64, (int64_t)T * 3 * D);
       g.planes = P; g.M = T; g.N = Tp; g.K = 64; g.nb0 = H; g.nb1 = B;
@@ -378,6 +415,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     SPK_TRY(softmax_fwd(c.ptr(pl.scr), pl.scr.ps, P, c.ptr(b.p), c.ptr(b.pd), drop, 1 + 4 * l, pl.BH * T, T, Tp, st));
     {  // O = P V, heads written back interleaved into [tokens, 256]
       GemmProblem g;
+      g.tag = "gemm.attn_pv";
       g.A = c.mat(drop.thresh ? b.pd : b.p, 0, T, T, Tp, (int64_t)T * Tp, (int64_t)H * T * Tp);
       g.B = c.mat(b.qkv, 2 * D, T, 64, 3 * D, 64, (int64_t)T * 3 * D);
       g.b_mn = true;
@@ -387,6 +425,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     }
     {  // out-proj + dropout1 + residual
       GemmProblem g;
+      g.tag = "gemm.out_proj";
       g.A = c.mat(b.att, 0, Mt, D, D);
       g.B = c.mat(pl.wpack, pl.w_out[l], D, D, D);
       g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)D;
@@ -399,6 +438,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     SPK_TRY(ln_fwd(c.ptr(b.z1), b.z1.ps, P, 1, lw.norm1_w, lw.norm1_b, c.ptr(b.h1), b.h1.ps, P, c.f32(b.st1), Mt, st));
     {  // linear1 + ReLU + dropout
       GemmProblem g;
+      g.tag = "gemm.ffn1";
       g.A = c.mat(b.h1, 0, Mt, D, D);
       g.B = c.mat(pl.wpack, pl.w_l1[l], F, D, D);
       g.planes = P; g.M = (int)Mt; g.N = (int)F; g.K = (int)D;
@@ -409,6 +449,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     }
     {  // linear2 + dropout2 + residual
       GemmProblem g;
+      g.tag = "gemm.ffn2";
       g.A = c.mat(b.f, 0, Mt, F, F);
       g.B = c.mat(pl.wpack, pl.w_l2[l], D, F, F);
       g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)F;
@@ -421,6 +462,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     SPK_TRY(ln_fwd(c.ptr(b.z2), b.z2.ps, P, 1, lw.norm2_w, lw.norm2_b, c.ptr(b.hout), b.hout.ps, P, c.f32(b.st2), Mt, st));
   }
   const Split& hl = pl.Lb[pl.L - 1].hout;
+  ProfScope prof_head("head_fwd", 2.0 * (B / S) * 256 * 256, 4.0 * B * 256 * 2, st);
   head_fwd_kernel<<<B / S, 256, 0, st>>>(c.ptr(hl), hl.ps, P, T, S, w.norm_w, w.norm_b, w.proj_w, w.proj_b,
                                          c.f32(pl.hn), reinterpret_cast<float2*>(c.f32(pl.hst)), c.f32(pl.emean),
                                          c.f32(pl.epre), dvec);
@@ -429,11 +471,12 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
 }
 
 int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w, const spk_encoder_params& gr,
-                     const float* d_dvec, int B, int T, int S, int P, int training, uint64_t seed, void* ws_v,
+                     const float* d_dvec, int B, int T, int S, int P_fwd, int training, uint64_t seed, void* ws_v,
                      size_t ws_bytes, cudaStream_t st) {
   Plan pl;
-  SPK_TRY(make_plan(cfg, B, T, S, P, true, pl));
+  SPK_TRY(make_plan(cfg, B, T, S, P_fwd, true, pl));
   if (ws_bytes < pl.total) { set_error("encoder: workspace too small (%zu < %zu)", ws_bytes, pl.total); return SPK_ENOMEM; }
+  const int P = P_fwd < 2 ? P_fwd : 2;   // the stash may hold 3 planes; the backward pass reads / writes 2
   Ctx c{pl, reinterpret_cast<char*>(ws_v), st, P};
   const int64_t Mt = pl.Mt, D = pl.D, F = pl.F;
   const int Tp = pl.Tp, H = pl.H;
@@ -443,12 +486,15 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
   // ---- head
   const Split& hl = pl.Lb[pl.L - 1].hout;
   SPK_CUDA(cudaMemsetAsync(c.ptr(pl.dh_a), 0, static_cast<size_t>(pl.dh_a.ps) * P * 2, st));
+  {
+  ProfScope prof_hb("head_bwd", 4.0 * (B / S) * 256 * 256, 4.0 * B * 256 * 2, st);
   head_bwd_kernel<<<B / S, 256, 0, st>>>(d_dvec, c.f32(pl.epre), w.proj_w, c.ptr(hl), hl.ps, P,
                                          reinterpret_cast<const float2*>(c.f32(pl.hst)), w.norm_w, T, S, c.f32(pl.de),
                                          c.ptr(pl.dh_a), pl.dh_a.ps, gr.norm_w, gr.norm_b);
   SPK_CUDA(cudaGetLastError());
   head_wgrad_kernel<<<256, 256, 0, st>>>(c.f32(pl.de), c.f32(pl.emean), B / S, gr.proj_w, gr.proj_b);
   SPK_CUDA(cudaGetLastError());
+  }
 
   for (int l = pl.L - 1; l >= 0; --l) {
     const LayerBufs& b = pl.Lb[l];
@@ -460,9 +506,10 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     SPK_TRY(ln_bwd(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.ptr(b.z2), b.z2.ps, P, c.f32(b.st2), lw.norm2_w, c.ptr(pl.dz),
                    pl.dz.ps, P, c.ptr(pl.dzd), drop, 4 + 4 * l, lg.norm2_w, lg.norm2_b, Mt, st));
     SPK_TRY(colsum(c.ptr(dy_ffn), dy_ffn.ps, P, lg.linear2_b, Mt, (int)D, st));
-    SPK_TRY(wgrad(c, dy_ffn, D, b.f, F, lg.linear2_w));
+    SPK_TRY(wgrad(c, dy_ffn, D, b.f, F, lg.linear2_w, "gemm.bwd.ffn2_wgrad"));
     {  // dU = (dY2 W2) * 1[f > 0] / (1 - p)
       GemmProblem g;
+      g.tag = "gemm.bwd.ffn2_dgrad";
       g.A = c.mat(dy_ffn, 0, Mt, D, D);
       g.B = c.mat(pl.wpack, pl.w_l2[l], D, F, F);
       g.b_mn = true;
@@ -474,9 +521,10 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       SPK_TRY(gemm_run(g, st));
     }
     SPK_TRY(colsum(c.ptr(pl.df), pl.df.ps, P, lg.linear1_b, Mt, (int)F, st));
-    SPK_TRY(wgrad(c, pl.df, F, b.h1, D, lg.linear1_w));
+    SPK_TRY(wgrad(c, pl.df, F, b.h1, D, lg.linear1_w, "gemm.bwd.ffn1_wgrad"));
     {  // dH1 = dU W1 + dZ2
       GemmProblem g;
+      g.tag = "gemm.bwd.ffn1_dgrad";
       g.A = c.mat(pl.df, 0, Mt, F, F);
       g.B = c.mat(pl.wpack, pl.w_l1[l], F, D, D);
       g.b_mn = true;
@@ -491,9 +539,10 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     SPK_TRY(ln_bwd(c.ptr(pl.dh_b), pl.dh_b.ps, P, c.ptr(b.z1), b.z1.ps, P, c.f32(b.st1), lw.norm1_w, c.ptr(pl.dz),
                    pl.dz.ps, P, c.ptr(pl.dzd), drop, 2 + 4 * l, lg.norm1_w, lg.norm1_b, Mt, st));
     SPK_TRY(colsum(c.ptr(dy_att), dy_att.ps, P, lg.out_proj_b, Mt, (int)D, st));
-    SPK_TRY(wgrad(c, dy_att, D, b.att, D, lg.out_proj_w));
+    SPK_TRY(wgrad(c, dy_att, D, b.att, D, lg.out_proj_w, "gemm.bwd.out_wgrad"));
     {  // dATT = dY1 Wo
       GemmProblem g;
+      g.tag = "gemm.bwd.out_dgrad";
       g.A = c.mat(dy_att, 0, Mt, D, D);
       g.B = c.mat(pl.wpack, pl.w_out[l], D, D, D);
       g.b_mn = true;
@@ -507,6 +556,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     const int64_t sQ0 = 64, sQ1 = (int64_t)T * 3 * D, sA1 = (int64_t)T * D;
     {  // dV = P_drop^T dO
       GemmProblem g;
+      g.tag = "gemm.bwd.attn_dv";
       g.A = c.mat(pdrop, 0, T, T, Tp, sP0, sP1);
       g.B = c.mat(pl.datt, 0, T, 64, D, 64, sA1);
       g.a_mn = true; g.b_mn = true;
@@ -516,6 +566,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     }
     {  // dP_drop = dO V^T
       GemmProblem g;
+      g.tag = "gemm.bwd.attn_dp";
       g.A = c.mat(pl.datt, 0, T, 64, D, 64, sA1);
       g.B = c.mat(b.qkv, 2 * D, T, 64, 3 * D, sQ0, sQ1);
       g.planes = P; g.M = T; g.N = Tp; g.K = 64; g.nb0 = H; g.nb1 = B;
@@ -526,6 +577,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
                         Tp, st));
     {  // dQ = dS K
       GemmProblem g;
+      g.tag = "gemm.bwd.attn_dq";
       g.A = c.mat(pl.scr, 0, T, T, Tp, sP0, sP1);
       g.B = c.mat(b.qkv, D, T, 64, 3 * D, sQ0, sQ1);
       g.b_mn = true;
@@ -535,6 +587,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     }
     {  // dK = dS^T Q
       GemmProblem g;
+      g.tag = "gemm.bwd.attn_dk";
       g.A = c.mat(pl.scr, 0, T, T, Tp, sP0, sP1);
       g.B = c.mat(b.qkv, 0, T, 64, 3 * D, sQ0, sQ1);
       g.a_mn = true; g.b_mn = true;
@@ -544,9 +597,10 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     }
     // ---- in-proj
     SPK_TRY(colsum(c.ptr(pl.dqkv), pl.dqkv.ps, P, lg.in_proj_b, Mt, (int)(3 * D), st));
-    SPK_TRY(wgrad(c, pl.dqkv, 3 * D, hin, D, lg.in_proj_w));
+    SPK_TRY(wgrad(c, pl.dqkv, 3 * D, hin, D, lg.in_proj_w, "gemm.bwd.qkv_wgrad"));
     {  // dH(in) = dQKV Win + dZ1
       GemmProblem g;
+      g.tag = "gemm.bwd.qkv_dgrad";
       g.A = c.mat(pl.dqkv, 0, Mt, 3 * D, 3 * D);
       g.B = c.mat(pl.wpack, pl.w_in[l], 3 * D, D, D);
       g.b_mn = true;
@@ -561,9 +615,11 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
   SPK_TRY(pe_alpha_grad(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.f32(pl.pe_t), drop_pe, 0, gr.pe_alpha, Mt, T, st));
   {
     GemmProblem g;
+    g.tag = "gemm.bwd.prenet_gate";
     g.A = c.mat(pl.x0, 0, Mt, pl.C, pl.C);
     g.B = c.mat(pl.wpack, pl.w_pre, D, pl.C, pl.C);
-    g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = pl.C;
+    // same operand planes as the forward prenet GEMM, so the recomputed ReLU gate is the forward's gate
+    g.planes = P_fwd; g.M = (int)Mt; g.N = (int)D; g.K = pl.C;
     g.epi.flags = EPI_BIAS | EPI_ACC_GATES_AUX;
     g.epi.bias = w.prenet_b; g.epi.drop = drop_pe; g.epi.drop_site = 0;
     c.res(g.epi, pl.dh_a, D);
@@ -571,7 +627,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     SPK_TRY(gemm_run(g, st));
   }
   SPK_TRY(colsum(c.ptr(pl.dh_b), pl.dh_b.ps, P, gr.prenet_b, Mt, (int)D, st));
-  SPK_TRY(wgrad(c, pl.dh_b, D, pl.x0, pl.C, gr.prenet_w));
+  SPK_TRY(wgrad(c, pl.dh_b, D, pl.x0, pl.C, gr.prenet_w, "gemm.bwd.prenet_wgrad"));
   return 0;
 }
 

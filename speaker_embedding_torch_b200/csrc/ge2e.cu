@@ -317,6 +317,8 @@ int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float*
   int ng = need_grad;
   void* args[] = {(void*)&E, (void*)&N, (void*)&M, (void*)&w, (void*)&b, (void*)&loss, (void*)&dE, (void*)&dw,
                   (void*)&db, (void*)&chat, (void*)&cinv, (void*)&einv, (void*)&dchat, (void*)&ng, (void*)&eps};
+  ProfScope prof(need_grad ? "ge2e_fused_fwd_bwd" : "ge2e_fused_fwd", (need_grad ? 6.0 : 2.0) * NM * N * GD,
+                 (need_grad ? 2.0 : 1.0) * NM * GD * 4.0, st);
   SPK_CUDA(cudaLaunchCooperativeKernel((void*)ge2e_fused_kernel, dim3(grid), dim3(256), args, smem, st));
   return 0;
 }

@@ -56,11 +56,12 @@ struct GemmEpilogue {
 struct GemmProblem {
   SplitMat A, B;        // A: [M,K] (K-major) or [K,M] (MN-major); B: [N,K] (K-major) or [K,N] (MN-major)
   bool a_mn = false, b_mn = false;
-  int planes = 1;       // 1: Ah*Bh ; 2: Ah*Bh + Ah*Bl + Al*Bh
+  int planes = 1;       // 1: Ah*Bh ; 2: + Ah*Bl + Al*Bh ; 3: six products (fp32-equivalent)
   int M = 0, N = 0, K = 0;
   int nb0 = 1, nb1 = 1; // batch extents; batch index = i1 * nb0 + i0, offset = i0 * sb0 + i1 * sb1
   int ksplit = 1;       // >1 requires EPI_OUT_ATOMIC
   int block_n = 0;      // 0 = auto (64/128/192/256)
+  const char* tag = "gemm";   // profiler label
   GemmEpilogue epi;
 };
 

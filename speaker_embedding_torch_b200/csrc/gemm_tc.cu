@@ -6,7 +6,8 @@
 //   shared-memory ring; each operand may be K-major or MN-major (transposed reads for dgrad /
 //   wgrad / P*V come from the descriptor, never from a transposed copy);
 // * one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16 in, fp32 accumulate in
-//   TMEM); with two planes it issues Ah*Bh + Ah*Bl + Al*Bh into the same accumulator;
+//   TMEM); with two planes it issues Ah*Bh + Ah*Bl + Al*Bh into the same accumulator, with three
+//   planes the six products down to 2^-16 (fp32-equivalent operands);
 // * the accumulator is double-buffered in TMEM so the 4 epilogue warps (tcgen05.ld -> registers
 //   -> fused bias / ReLU / positional term / dropout / residual / gate -> global) drain tile i
 //   while the MMA warp works on tile i+1;
@@ -28,8 +29,8 @@ constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in limit per CTA
 constexpr int BAR_BYTES = 256;
 
 struct GemmKernelArgs {
-  CUtensorMap a_map[2];
-  CUtensorMap b_map[2];
+  CUtensorMap a_map[3];
+  CUtensorMap b_map[3];
   int M, N, K;
   int tiles_m, tiles_n, nb0, nb1, ksplit, kb_total, kb_per_split;
   int a_batched, b_batched;
@@ -241,10 +242,13 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           mbar_wait(full_bar(stage), phase, 0x300u + stage);
           tc_fence_after();
 #pragma unroll
-          for (int combo = 0; combo < (PLANES == 1 ? 1 : 3); ++combo) {
-            // small terms first: Al*Bh, Ah*Bl, then Ah*Bh
-            const int pa = (PLANES == 1) ? 0 : (combo == 0 ? 1 : 0);
-            const int pb = (PLANES == 1) ? 0 : (combo == 1 ? 1 : 0);
+          for (int combo = 0; combo < (PLANES == 1 ? 1 : (PLANES == 2 ? 3 : 6)); ++combo) {
+            // plane products, smallest terms first (plane 0 = hi, 1 = mid/lo, 2 = lo):
+            //   2 planes: a1*b0, a0*b1, a0*b0           3 planes: a1*b1, a0*b2, a2*b0, a0*b1, a1*b0, a0*b0
+            constexpr int PA2[3] = {1, 0, 0}, PB2[3] = {0, 1, 0};
+            constexpr int PA3[6] = {1, 0, 2, 0, 1, 0}, PB3[6] = {1, 2, 0, 1, 0, 0};
+            const int pa = (PLANES == 1) ? 0 : (PLANES == 2 ? PA2[combo % 3] : PA3[combo]);
+            const int pb = (PLANES == 1) ? 0 : (PLANES == 2 ? PB2[combo % 3] : PB3[combo]);
             const uint32_t a_base = sA(stage, pa), b_base = sB(stage, pb);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -385,11 +389,18 @@ static int launch(const GemmKernelArgs& args, int grid, cudaStream_t stream) {
 
 template <bool A_MN, bool B_MN, int PLANES>
 static int launch_bn(int block_n, const GemmKernelArgs& args, int grid, cudaStream_t stream) {
-  switch (block_n) {
-    case 64: return launch<A_MN, B_MN, PLANES, 64>(args, grid, stream);
-    case 128: return launch<A_MN, B_MN, PLANES, 128>(args, grid, stream);
-    case 192: return launch<A_MN, B_MN, PLANES, 192>(args, grid, stream);
-    case 256: return launch<A_MN, B_MN, PLANES, 256>(args, grid, stream);
+  if constexpr (PLANES == 3) {   // three planes of A and B only fit a double-buffered ring up to N = 128
+    switch (block_n) {
+      case 64: return launch<A_MN, B_MN, PLANES, 64>(args, grid, stream);
+      case 128: return launch<A_MN, B_MN, PLANES, 128>(args, grid, stream);
+    }
+  } else {
+    switch (block_n) {
+      case 64: return launch<A_MN, B_MN, PLANES, 64>(args, grid, stream);
+      case 128: return launch<A_MN, B_MN, PLANES, 128>(args, grid, stream);
+      case 192: return launch<A_MN, B_MN, PLANES, 192>(args, grid, stream);
+      case 256: return launch<A_MN, B_MN, PLANES, 256>(args, grid, stream);
+    }
   }
   set_error("unsupported block_n %d", block_n);
   return SPK_EINVAL;
@@ -406,7 +417,7 @@ static int launch_major(bool a_mn, bool b_mn, int block_n, const GemmKernelArgs&
 
 int gemm_run(const GemmProblem& p, cudaStream_t stream) {
   SPK_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %d x %d x %d", p.M, p.N, p.K);
-  SPK_CHECK(p.planes == 1 || p.planes == 2, "gemm: planes must be 1 or 2");
+  SPK_CHECK(p.planes >= 1 && p.planes <= 3, "gemm: planes must be 1, 2 or 3");
   SPK_CHECK(p.N % 8 == 0, "gemm: N (%d) must be a multiple of 8", p.N);
   SPK_CHECK(p.epi.out != nullptr, "gemm: no output");
   SPK_CHECK(p.ksplit == 1 || (p.epi.flags & EPI_OUT_ATOMIC), "gemm: split-K needs the atomic epilogue");
@@ -418,6 +429,7 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
 
   int bn = p.block_n;
   if (bn == 0) bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : (p.N <= 192 ? 192 : 256));
+  if (p.planes == 3 && bn > 128) bn = 128;
 
   GemmKernelArgs a;
   memset(&a, 0, sizeof(a));
@@ -441,8 +453,17 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
   SPK_CHECK(total < (1LL << 30), "gemm: too many tiles");
   const int sms = device_sm_count();
   const int grid = static_cast<int>(total < sms ? total : sms);
+  const double nb = 1.0 * p.nb0 * p.nb1;
+  const double esz = 2.0 * p.planes;
+  const double out_b = (p.epi.flags & (EPI_OUT_F32 | EPI_OUT_ATOMIC)) ? 4.0 : esz;
+  double bytes = nb * (1.0 * p.M * p.K * esz + 1.0 * p.M * p.N * out_b) +
+                 (a.b_batched ? nb : 1.0) * p.N * p.K * esz;
+  if (p.epi.flags & (EPI_RES | EPI_ACC_GATES_AUX)) bytes += nb * p.M * p.N * 2.0 * p.epi.res_planes;
+  if (p.epi.flags & EPI_GATE_POS) bytes += nb * p.M * p.N * 2.0 * p.epi.gate_planes;
+  ProfScope prof(p.tag, 2.0 * nb * p.M * p.N * p.K, bytes, stream);
   if (p.planes == 1) return launch_major<1>(p.a_mn, p.b_mn, bn, a, grid, stream);
-  return launch_major<2>(p.a_mn, p.b_mn, bn, a, grid, stream);
+  if (p.planes == 2) return launch_major<2>(p.a_mn, p.b_mn, bn, a, grid, stream);
+  return launch_major<3>(p.a_mn, p.b_mn, bn, a, grid, stream);
 }
 
 }  // namespace spk

@@ -92,6 +92,9 @@ int optim_step(const spk_optim_tensors& t, int kind, int64_t step, float lr, flo
     s.step_size = (float)(1.0 / (1.0 - b1t));
     s.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - b2t));
   }
+  double numel = 0;
+  for (int i = 0; i < t.count; ++i) numel += (double)t.numel[i];
+  ProfScope prof("optim_step", 0, numel * 4.0 * (max_norm > 0.f ? 8 : 7), st);
   if (max_norm > 0.f) {
     SPK_CUDA(cudaMemsetAsync(norm_scratch, 0, sizeof(float), st));
     grad_sqnorm_kernel<<<296, 256, 0, st>>>(t, grad_scale, norm_scratch);

@@ -17,6 +17,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackTable tab, __nv_
   }
 }
 int pack_weights(const PackTable& tab, void* dst, int64_t plane_stride, int planes, cudaStream_t st) {
+  ProfScope prof("pack_weights", 0, 0, st);
   pack_weights_kernel<<<296, 256, 0, st>>>(tab, reinterpret_cast<__nv_bfloat16*>(dst), plane_stride, planes);
   SPK_CUDA(cudaGetLastError());
   return 0;
@@ -47,6 +48,7 @@ __global__ void mel_pack_kernel(const float* __restrict__ mel, __nv_bfloat16* __
   }
 }
 int mel_pack(const float* mel, void* out, int64_t plane_stride, int planes, int B, int C, int T, cudaStream_t st) {
+  ProfScope prof("mel_pack", 0, 1.0 * B * C * T * (4.0 + 2.0 * planes), st);
   SPK_CHECK(C == 80, "mel_pack: Mel_Dim %d not supported by this build (80)", C);
   dim3 grid((T + 31) / 32, B);
   mel_pack_kernel<80><<<grid, 256, 0, st>>>(mel, reinterpret_cast<__nv_bfloat16*>(out), plane_stride, planes, T);
@@ -70,6 +72,7 @@ __global__ void pe_transpose_kernel(const float* __restrict__ pe, float* __restr
   }
 }
 int pe_transpose(const float* pe, float* pe_t, int D, int max_pos, int T, cudaStream_t st) {
+  ProfScope prof("pe_transpose", 0, 8.0 * D * T, st);
   dim3 grid((T + 31) / 32, (D + 31) / 32);
   pe_transpose_kernel<<<grid, 256, 0, st>>>(pe, pe_t, D, max_pos, T);
   SPK_CUDA(cudaGetLastError());
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
 }
 int ln_fwd(const void* z, int64_t z_ps, int z_planes, int64_t z_row_step, const float* gamma, const float* beta,
            void* y, int64_t y_ps, int y_planes, float* stats, int64_t rows, cudaStream_t st) {
+  ProfScope prof("ln_fwd", 0, 512.0 * rows * (z_planes + y_planes), st);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
   ln_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(z), z_ps, z_planes, gamma, beta,
                                         reinterpret_cast<__nv_bfloat16*>(y), y_ps, y_planes,
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
 int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t z_ps, int z_planes, const float* stats,
            const float* gamma, void* dz, int64_t dz_ps, int dz_planes, void* dz_drop, DropCfg drop, uint32_t site,
            float* dgamma, float* dbeta, int64_t rows, cudaStream_t st) {
+  ProfScope prof("ln_bwd", 0, 512.0 * rows * (dy_planes + z_planes + dz_planes * (drop.thresh ? 2 : 1)), st);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 4));
   ln_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ps, dy_planes,
                                         reinterpret_cast<const __nv_bfloat16*>(z), z_ps, z_planes,
@@ -244,6 +249,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
 }
 int softmax_fwd(const void* s, int64_t ps, int planes, void* p, void* p_drop, DropCfg drop, uint32_t site,
                 int64_t rows, int T, int Tp, cudaStream_t st) {
+  ProfScope prof("softmax_fwd", 0, 2.0 * rows * Tp * planes * (drop.thresh ? 3 : 2), st);
   SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
   softmax_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(s), ps, planes,
@@ -255,9 +261,10 @@ int softmax_fwd(const void* s, int64_t ps, int planes, void* p, void* p_drop, Dr
 }
 
 // dS = scale * P * (dP' - sum_k dP'_k P_k),  dP' = dP_drop * keep/(1-p)
+// dp and ds may alias (in-place): a warp reads its whole row before writing it, so no __restrict__ here.
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p,
-                                                          const __nv_bfloat16* __restrict__ dp, int64_t ps, int planes,
-                                                          __nv_bfloat16* __restrict__ ds, DropCfg drop, uint32_t site,
+                                                          const __nv_bfloat16* dp, int64_t ps, int planes,
+                                                          __nv_bfloat16* ds, DropCfg drop, uint32_t site,
                                                           float scale, int64_t rows, int T, int Tp) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -301,6 +308,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
 }
 int softmax_bwd(const void* p, const void* dp, int64_t ps, int planes, void* ds, DropCfg drop, uint32_t site,
                 float scale, int64_t rows, int T, int Tp, cudaStream_t st) {
+  ProfScope prof("softmax_bwd", 0, 2.0 * rows * Tp * planes * 3, st);
   SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
   softmax_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(p),
@@ -331,6 +339,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   for (int i = 0; i < 8; ++i) atomicAdd(out + g * 8 + i, acc[i]);
 }
 int colsum(const void* x, int64_t ps, int planes, float* out, int64_t rows, int C, cudaStream_t st) {
+  ProfScope prof("colsum", 0, 2.0 * rows * C * planes, st);
   SPK_CHECK(C % 8 == 0 && C / 8 <= 256, "colsum: C=%d unsupported", C);
   const int rpb = 512;
   const int blocks = static_cast<int>((rows + rpb - 1) / rpb);
@@ -374,6 +383,7 @@ __global__ void __launch_bounds__(256) pe_alpha_grad_kernel(const __nv_bfloat16*
 }
 int pe_alpha_grad(const void* dh, int64_t ps, int planes, const float* pe_t, DropCfg drop, uint32_t site, float* dalpha,
                   int64_t rows, int T, cudaStream_t st) {
+  ProfScope prof("pe_alpha_grad", 0, 512.0 * rows * planes, st);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 4));
   pe_alpha_grad_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dh), ps, planes, pe_t, drop, site,
                                                dalpha, rows, T);

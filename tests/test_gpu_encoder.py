@@ -1,0 +1,205 @@
+"""Encoder forward / backward parity on the GPU, through the drop-in modules (C ABI underneath).
+
+Forward: against the reference's own d-vectors (tests/golden/encoder_forward.npz, fp64 run of
+/root/reference/Modules.py) -- tolerance from BASELINE.json: cosine >= 0.9999 per d-vector.
+Backward: against the fp64 oracle (itself pinned to the reference by tests/test_oracle_golden.py)
+and the reference's gradient fingerprints (tests/golden/train_grads.npz) -- relative loss / global
+gradient error <= 1e-3.  Parity is defined in eval mode (dropout masks cannot match).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ge2e_oracle as O
+from oracle import synth
+from oracle.make_golden import fingerprint_indices
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(seed, layers=3):
+    from speaker_embedding_torch_b200 import GE2E
+    from speaker_embedding_torch_b200.Arg_Parser import default_hyper_parameters
+    hp = default_hyper_parameters()
+    hp.GE2E.Transformer.Num_Layers = layers
+    state = synth.make_state(seed)
+    m = GE2E(hp)
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in state.items() if k in m.state_dict()}, strict=True)
+    return m.cuda(), state
+
+
+def _cos(a, b):
+    return (a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
+
+
+@pytest.mark.parametrize("precision,min_cos,max_abs", [(1, 0.9999, 4e-3), (2, 0.99999999, 2e-5)])
+def test_forward_matches_reference_golden(golden_dir, precision, min_cos, max_abs):
+    g = np.load(os.path.join(golden_dir, "encoder_forward.npz"))
+    for i in range(int(g["num_cases"])):
+        ss, ms, B, T, S = [int(v) for v in g["case%d_meta" % i]]
+        m, _ = _model(ss)
+        m.eval()
+        m.eval_precision = precision
+        with torch.no_grad():
+            d = m(torch.as_tensor(synth.make_mel(ms, B, T)).cuda(), S)
+        torch.cuda.synchronize()
+        assert d.shape == (B // S, 256) and d.dtype == torch.float32
+        d = d.cpu().numpy().astype(np.float64)
+        ref = g["case%d_f64" % i]
+        assert _cos(d, ref).min() >= min_cos, (i, B, T, S, _cos(d, ref).min())
+        assert np.abs(d - ref).max() <= max_abs, (i, np.abs(d - ref).max())
+        np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+
+
+def test_forward_full_size_batch_properties():
+    """BASELINE size (960 slices x 160 frames): unit norm, determinism, batch-composition independence."""
+    m, state = _model(7)
+    m.eval()
+    mel = torch.as_tensor(synth.make_mel(70, 960, 160)).cuda()
+    with torch.no_grad():
+        d1 = m(mel)
+        d2 = m(mel)
+        d_part = m(mel[100:132])
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d2)
+    torch.testing.assert_close(d1.norm(dim=1), torch.ones(960, device="cuda"), atol=1e-5, rtol=0)
+    torch.testing.assert_close(d1[100:132], d_part, atol=1e-6, rtol=0)      # slices are independent
+    ref = O.encoder_forward(O.to_torch_state(state, torch.float32), mel[:8].cpu(), 1).numpy()
+    assert _cos(d1[:8].cpu().numpy(), ref).min() >= 0.9999
+
+
+def test_multislice_inference_chunks_whole_utterances():
+    """5 x 64-frame slices with samples=5 (Inference.py:95-115): chunked == unchunked; mean is taken
+    over the slices of one utterance before projection (Modules.py:55-56)."""
+    m, state = _model(8)
+    m.eval()
+    mel = torch.as_tensor(synth.make_mel(80, 35, 64)).cuda()
+    with torch.no_grad():
+        full = m(mel, 5)
+        m.max_slices_per_call = 12                 # -> chunks of 10 slices = 2 utterances
+        chunked = m(mel, 5)
+    torch.cuda.synchronize()
+    assert full.shape == (7, 256)
+    torch.testing.assert_close(full, chunked, atol=1e-6, rtol=0)
+    ref = O.encoder_forward(O.to_torch_state(state, torch.float64), mel.cpu().double(), 5).numpy()
+    assert _cos(full.cpu().numpy().astype(np.float64), ref).min() >= 0.9999
+    with pytest.raises(RuntimeError, match="invalid"):
+        with torch.no_grad():
+            m(mel, 4)                              # 35 slices are not a multiple of 4
+
+
+def _grad_errors(m, g_ref):
+    num = den = 0.0
+    worst = ("", 0.0)
+    for name, p in m.named_parameters():
+        g = p.grad.detach().cpu().numpy().astype(np.float64)
+        r = g_ref[name]
+        num += ((g - r) ** 2).sum()
+        den += (r ** 2).sum()
+        rel = np.linalg.norm(g - r) / max(np.linalg.norm(r), 1e-30)
+        if rel > worst[1]:
+            worst = (name, rel)
+    return (num / den) ** 0.5, worst
+
+
+@pytest.mark.parametrize("nspk,utt,frames", [(3, 2, 24), (4, 3, 50), (10, 4, 24), (2, 2, 128), (4, 3, 160), (3, 2, 177)])
+def test_train_step_grads_match_oracle(nspk, utt, frames):
+    from speaker_embedding_torch_b200 import GE2E_Loss
+    m, state = _model(33)
+    m.eval()
+    crit = GE2E_Loss().cuda()
+    mel = synth.make_mel(500 + frames, nspk * utt, frames)
+    d = m(torch.as_tensor(mel).cuda())
+    loss = crit(d, utt)
+    loss.backward()
+    torch.cuda.synchronize()
+    loss_ref, d_ref, g_ref = O.train_step_grads(state, mel, utt)
+    assert abs(loss.item() - loss_ref) <= 1e-3 * abs(loss_ref)
+    assert _cos(d.detach().cpu().numpy().astype(np.float64), d_ref).min() >= 0.9999
+    rel_all, worst = _grad_errors(m, g_ref)
+    assert rel_all <= 1e-3, (rel_all, worst)
+    assert abs(crit.weight.grad.item() - float(g_ref["loss.weight"])) <= 1e-3 * abs(float(g_ref["loss.weight"]))
+    assert abs(crit.bias.grad.item()) <= 1e-6
+
+
+def test_train_step_grads_match_reference_fingerprints(golden_dir):
+    from speaker_embedding_torch_b200 import GE2E_Loss
+    g = np.load(os.path.join(golden_dir, "train_grads.npz"))
+    for i in range(int(g["num_cases"])):
+        ss, ms, N, M, T = [int(v) for v in g["case%d_meta" % i]]
+        m, _ = _model(ss)
+        m.eval()
+        crit = GE2E_Loss().cuda()
+        loss = crit(m(torch.as_tensor(synth.make_mel(ms, N * M, T)).cuda()), M)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - float(g["case%d_loss" % i])) <= 1e-3 * abs(float(g["case%d_loss" % i]))
+        num = den = 0.0
+        for name, p in m.named_parameters():
+            gr = p.grad.detach().cpu().numpy().astype(np.float64).reshape(-1)
+            ref_norm = float(g["case%d_gnorm_%s" % (i, name)])
+            assert abs(np.linalg.norm(gr) - ref_norm) <= 2e-3 * ref_norm + 1e-12, name
+            samp = g["case%d_gsamp_%s" % (i, name)]
+            num += ((gr[fingerprint_indices(gr.size)] - samp) ** 2).sum()
+            den += (samp ** 2).sum()
+        assert (num / den) ** 0.5 <= 1e-3
+
+
+def test_dropout_train_mode_is_seeded_and_unbiased():
+    from speaker_embedding_torch_b200 import GE2E_Loss
+    m, _ = _model(9)
+    crit = GE2E_Loss().cuda()
+    mel = torch.as_tensor(synth.make_mel(90, 12, 40)).cuda()
+    m.train()
+    torch.manual_seed(1)
+    d1 = m(mel)
+    torch.manual_seed(1)
+    d2 = m(mel)
+    torch.manual_seed(2)
+    d3 = m(mel)
+    assert torch.equal(d1, d2) and not torch.equal(d1, d3)          # mask = f(seed)
+    loss = crit(d1, 3)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+    m.eval()
+    d_eval = m(mel).detach()
+    # averaged over masks the train-mode d-vectors stay close to the eval ones
+    m.train()
+    acc = torch.zeros_like(d_eval)
+    for s in range(24):
+        torch.manual_seed(100 + s)
+        acc += m(mel).detach()
+    cos = torch.nn.functional.cosine_similarity(acc, d_eval, dim=1)
+    assert cos.min().item() > 0.9
+
+
+def test_dropout_zero_equals_eval():
+    from speaker_embedding_torch_b200 import GE2E
+    from speaker_embedding_torch_b200.Arg_Parser import default_hyper_parameters
+    hp = default_hyper_parameters()
+    hp.GE2E.Positional_Encoding.Dropout_Rate = 0.0
+    hp.GE2E.Transformer.Dropout_Rate = 0.0
+    m = GE2E(hp)
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in synth.make_state(4).items()})
+    m = m.cuda()
+    mel = torch.as_tensor(synth.make_mel(41, 6, 30)).cuda()
+    m.train()
+    a = m(mel).detach()
+    m.eval()
+    b = m(mel).detach()
+    torch.testing.assert_close(a, b, atol=1e-7, rtol=0)
+
+
+def test_shape_and_device_errors():
+    m, _ = _model(5)
+    m.eval()
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="Mel_Dim"):
+            m(torch.zeros(2, 64, 16, device="cuda"))
+        with pytest.raises(RuntimeError, match="frames"):
+            m(torch.zeros(2, 80, 1025, device="cuda"))
+        out = m(torch.zeros(3, 80, 1, device="cuda"))                 # T = 1 edge case
+    assert out.shape == (3, 256) and torch.isfinite(out).all()
