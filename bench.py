@@ -306,6 +306,16 @@ def run_native(args):
             e1.record()
             torch.cuda.synchronize()
         dv_ms = e0.elapsed_time(e1) / reps
+        _native.prof_enable(True)
+        with torch.no_grad():
+            model(mel160)
+        torch.cuda.synchronize()
+        irep = _native.prof_report()
+        _native.prof_enable(False)
+        line_extra["infer_breakdown"] = {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                                             "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else 0.0,
+                                             "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)}
+                                         for k, v in sorted(irep.items(), key=lambda kv: -kv[1]["ms"])}
         model.train()
         line_extra["extra"] = {"dvectors_per_sec_160f_1gpu": batch / (dv_ms * 1e-3), "infer_ms_per_960x160_batch": dv_ms,
                                "infer_tensor_frac_of_sustained": batch * dense_flops_fwd(160) / (dv_ms * 1e-3) / 1e12 / pk["tf_sus"],

@@ -504,8 +504,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     const Split& dy_ffn = drop.thresh ? pl.dzd : pl.dz;
     // ---- LayerNorm2 backward: dH(out) -> dZ2 (residual path) and dZ2 * mask (FFN path)
     SPK_TRY(ln_bwd(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.ptr(b.z2), b.z2.ps, P, c.f32(b.st2), lw.norm2_w, c.ptr(pl.dz),
-                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 4 + 4 * l, lg.norm2_w, lg.norm2_b, Mt, st));
-    SPK_TRY(colsum(c.ptr(dy_ffn), dy_ffn.ps, P, lg.linear2_b, Mt, (int)D, st));
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 4 + 4 * l, lg.norm2_w, lg.norm2_b, lg.linear2_b, Mt, st));
     SPK_TRY(wgrad(c, dy_ffn, D, b.f, F, lg.linear2_w, "gemm.bwd.ffn2_wgrad"));
     {  // dU = (dY2 W2) * 1[f > 0] / (1 - p)
       GemmProblem g;
@@ -514,13 +513,13 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.B = c.mat(pl.wpack, pl.w_l2[l], D, F, F);
       g.b_mn = true;
       g.planes = P; g.M = (int)Mt; g.N = (int)F; g.K = (int)D;
-      g.epi.flags = EPI_GATE_POS;
+      g.epi.flags = EPI_GATE_POS | EPI_COLSUM;
+      g.epi.colsum = lg.linear1_b;
       g.epi.gate = c.ptr(b.f); g.epi.gate_plane_stride = b.f.ps; g.epi.gate_ld = F; g.epi.gate_planes = P;
       g.epi.gate_scale = drop.inv_keep;
       c.out(g.epi, pl.df, 0, F);
       SPK_TRY(gemm_run(g, st));
     }
-    SPK_TRY(colsum(c.ptr(pl.df), pl.df.ps, P, lg.linear1_b, Mt, (int)F, st));
     SPK_TRY(wgrad(c, pl.df, F, b.h1, D, lg.linear1_w, "gemm.bwd.ffn1_wgrad"));
     {  // dH1 = dU W1 + dZ2
       GemmProblem g;
@@ -537,8 +536,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     // ---- LayerNorm1 backward
     const Split& dy_att = drop.thresh ? pl.dzd : pl.dz;
     SPK_TRY(ln_bwd(c.ptr(pl.dh_b), pl.dh_b.ps, P, c.ptr(b.z1), b.z1.ps, P, c.f32(b.st1), lw.norm1_w, c.ptr(pl.dz),
-                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 2 + 4 * l, lg.norm1_w, lg.norm1_b, Mt, st));
-    SPK_TRY(colsum(c.ptr(dy_att), dy_att.ps, P, lg.out_proj_b, Mt, (int)D, st));
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 2 + 4 * l, lg.norm1_w, lg.norm1_b, lg.out_proj_b, Mt, st));
     SPK_TRY(wgrad(c, dy_att, D, b.att, D, lg.out_proj_w, "gemm.bwd.out_wgrad"));
     {  // dATT = dY1 Wo
       GemmProblem g;
@@ -561,6 +559,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.B = c.mat(pl.datt, 0, T, 64, D, 64, sA1);
       g.a_mn = true; g.b_mn = true;
       g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
+      g.epi.flags = EPI_COLSUM; g.epi.colsum = lg.in_proj_b + 2 * D; g.epi.colsum_sb0 = 64;
       c.out(g.epi, pl.dqkv, 2 * D, 3 * D, sQ0, sQ1);
       SPK_TRY(gemm_run(g, st));
     }
@@ -582,6 +581,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.B = c.mat(b.qkv, D, T, 64, 3 * D, sQ0, sQ1);
       g.b_mn = true;
       g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
+      g.epi.flags = EPI_COLSUM; g.epi.colsum = lg.in_proj_b; g.epi.colsum_sb0 = 64;
       c.out(g.epi, pl.dqkv, 0, 3 * D, sQ0, sQ1);
       SPK_TRY(gemm_run(g, st));
     }
@@ -592,11 +592,11 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.B = c.mat(b.qkv, 0, T, 64, 3 * D, sQ0, sQ1);
       g.a_mn = true; g.b_mn = true;
       g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
+      g.epi.flags = EPI_COLSUM; g.epi.colsum = lg.in_proj_b + D; g.epi.colsum_sb0 = 64;
       c.out(g.epi, pl.dqkv, D, 3 * D, sQ0, sQ1);
       SPK_TRY(gemm_run(g, st));
     }
     // ---- in-proj
-    SPK_TRY(colsum(c.ptr(pl.dqkv), pl.dqkv.ps, P, lg.in_proj_b, Mt, (int)(3 * D), st));
     SPK_TRY(wgrad(c, pl.dqkv, 3 * D, hin, D, lg.in_proj_w, "gemm.bwd.qkv_wgrad"));
     {  // dH(in) = dQKV Win + dZ1
       GemmProblem g;
@@ -620,13 +620,13 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     g.B = c.mat(pl.wpack, pl.w_pre, D, pl.C, pl.C);
     // same operand planes as the forward prenet GEMM, so the recomputed ReLU gate is the forward's gate
     g.planes = P_fwd; g.M = (int)Mt; g.N = (int)D; g.K = pl.C;
-    g.epi.flags = EPI_BIAS | EPI_ACC_GATES_AUX;
+    g.epi.flags = EPI_BIAS | EPI_ACC_GATES_AUX | EPI_COLSUM;
+    g.epi.colsum = gr.prenet_b;
     g.epi.bias = w.prenet_b; g.epi.drop = drop_pe; g.epi.drop_site = 0;
     c.res(g.epi, pl.dh_a, D);
     c.out(g.epi, pl.dh_b, 0, D);
     SPK_TRY(gemm_run(g, st));
   }
-  SPK_TRY(colsum(c.ptr(pl.dh_b), pl.dh_b.ps, P, gr.prenet_b, Mt, (int)D, st));
   SPK_TRY(wgrad(c, pl.dh_b, D, pl.x0, pl.C, gr.prenet_w, "gemm.bwd.prenet_wgrad"));
   return 0;
 }

@@ -25,6 +25,7 @@ enum : uint32_t {
   EPI_RES = 1u << 4,        // v += res[row, col]                      (after dropout)
   EPI_GATE_POS = 1u << 5,   // v = gate[row, col] > 0 ? v * gate_scale : 0   (ReLU backward from saved output)
   EPI_ACC_GATES_AUX = 1u << 6,  // v = (v > 0) ? res[row, col] * dropout_keep : 0  (prenet backward by recompute)
+  EPI_COLSUM = 1u << 7,     // colsum[col] += sum_rows(v)  (bias gradient fused into the producing GEMM)
   EPI_OUT_F32 = 1u << 8,    // plain fp32 store instead of split planes
   EPI_OUT_ATOMIC = 1u << 9  // fp32 atomicAdd (split-K weight gradients)
 };
@@ -47,6 +48,9 @@ struct GemmEpilogue {
   int64_t gate_plane_stride = 0, gate_ld = 0;
   int gate_planes = 1;
   float gate_scale = 1.f;
+  // fused column sums (fp32, atomically accumulated); colsum_sb0: elements per batch index i0
+  float* colsum = nullptr;
+  int64_t colsum_sb0 = 0;
   // output: split planes (default) or fp32
   void* out = nullptr;
   int64_t out_plane_stride = 0, out_ld = 0, out_sb0 = 0, out_sb1 = 0;   // batch strides, elements

@@ -27,6 +27,7 @@ constexpr int BLOCK_K = 64;              // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in limit per CTA
 constexpr int BAR_BYTES = 256;
+constexpr int EPI_SMEM = 4 * 4352;       // four epilogue warps x staging tile
 
 struct GemmKernelArgs {
   CUtensorMap a_map[3];
@@ -42,88 +43,225 @@ struct TileCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-  static constexpr int RAW_STAGES = (SMEM_LIMIT - 1024 - BAR_BYTES) / STAGE_BYTES;
+  static constexpr int RAW_STAGES = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_SMEM) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_SMEM;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
   static_assert(STAGES >= 2, "need at least a double buffer");
   static_assert(2 * BLOCK_N <= 512, "accumulator double buffer must fit TMEM");
 };
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue for 8 consecutive columns of one accumulator row.
-__device__ __forceinline__ void epilogue8(const GemmEpilogue& e, int N, int batch_M, int64_t row_in_batch,
-                                          int64_t batch, int64_t out_boff, int64_t res_boff, int col,
-                                          const uint32_t* acc, float pe_alpha) {
-  float v[8];
+// Epilogue of one 32 x 32 accumulator chunk per warp (lane == row).  Global traffic never goes out
+// row-strided from the lanes: every residual / gate read and every output store is transposed through
+// a per-warp shared-memory tile (32 rows x 64 B, 16-B chunks XOR-swizzled so that both the "lane owns a
+// row" and the "8 lanes cover 2 rows x 64 B" access patterns are bank-conflict free), so each warp
+// memory instruction touches 8 rows x 64 contiguous bytes (full 32-B sectors).
+constexpr int EPI_STAGE_BYTES = 4352;    // per warp: bf16 tile (2 KB) or fp32 32 x 33 column-sum tile
+
+__device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
+  return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+
+// r[32] += aux[row0 + lane][col0 .. col0+31]  (split tensor, rows >= M / cols >= N read as 0)
+__device__ __forceinline__ void load_aux_tile(uint32_t stage, int lane, const void* base_v, int64_t ps, int planes,
+                                              int64_t ld, int64_t boff, int64_t row0, int col0, int M, int N,
+                                              float (&r)[32]) {
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(base_v);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = e.alpha * __uint_as_float(acc[i]);
+  for (int i = 0; i < 32; ++i) r[i] = 0.f;
+  for (int p = 0; p < planes; ++p) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2), cc = lane & 3;
+      const int64_t grow = row0 + rr;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (grow < M && col0 + cc * 8 < N)
+        v = *reinterpret_cast<const uint4*>(base + p * ps + boff + grow * ld + col0 + cc * 8);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(rr, cc)), "r"(v.x), "r"(v.y),
+                   "r"(v.z), "r"(v.w)
+                   : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                   : "r"(stage + stage_off(lane, cc))
+                   : "memory");
+      const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        r[cc * 8 + 2 * i] += bf16lo_to_f(ww[i]);
+        r[cc * 8 + 2 * i + 1] += bf16hi_to_f(ww[i]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// out[row0 + lane][col0 .. col0+31] = v (split planes), coalesced through the staging tile
+__device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void* base_v, int64_t ps, int planes,
+                                                 int64_t ld, int64_t boff, int64_t row0, int col0, int M, int N,
+                                                 float (&v)[32]) {
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(base_v);
+  for (int p = 0; p < planes; ++p) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 q = __floats2bfloat162_rn(v[cc * 8 + 2 * i], v[cc * 8 + 2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&q);
+        v[cc * 8 + 2 * i] -= __bfloat162float(q.x);
+        v[cc * 8 + 2 * i + 1] -= __bfloat162float(q.y);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(lane, cc)), "r"(w[0]),
+                   "r"(w[1]), "r"(w[2]), "r"(w[3])
+                   : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2), cc = lane & 3;
+      const int64_t grow = row0 + rr;
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                   : "r"(stage + stage_off(rr, cc))
+                   : "memory");
+      if (grow < M && col0 + cc * 8 < N)
+        *reinterpret_cast<uint4*>(base + p * ps + boff + grow * ld + col0 + cc * 8) = make_uint4(w0, w1, w2, w3);
+    }
+    __syncwarp();
+  }
+}
+
+// fp32 tile (plain store or atomic add), coalesced through a 32 x 33 fp32 staging tile
+template <bool ATOMIC>
+__device__ __forceinline__ void store_f32_tile(uint32_t stage, int lane, float* base, int64_t ld, int64_t boff,
+                                               int64_t row0, int col0, int M, int N, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage + (lane * 33 + i) * 4), "f"(v[i]) : "memory");
+  __syncwarp();
+  const bool col_ok = col0 + lane < N;
+#pragma unroll 4
+  for (int rr = 0; rr < 32; ++rr) {
+    float x;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stage + (rr * 33 + lane) * 4) : "memory");
+    const int64_t grow = row0 + rr;
+    if (col_ok && grow < M) {
+      float* dst = base + boff + grow * ld + col0 + lane;
+      if (ATOMIC) atomicAdd(dst, x);
+      else *dst = x;
+    }
+  }
+  __syncwarp();
+}
+
+// colsum[col0 + lane] += sum over the warp's 32 rows of v[.][lane]   (bias gradients, fused)
+__device__ __forceinline__ void colsum_tile(uint32_t stage, int lane, float* colsum, int col0, int N,
+                                            const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage + (lane * 33 + i) * 4), "f"(v[i]) : "memory");
+  __syncwarp();
+  float s = 0.f;
+#pragma unroll 8
+  for (int rr = 0; rr < 32; ++rr) {
+    float x;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stage + (rr * 33 + lane) * 4) : "memory");
+    s += x;
+  }
+  if (col0 + lane < N) atomicAdd(colsum + col0 + lane, s);
+  __syncwarp();
+}
+
+__device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage, int lane, int M, int N,
+                                           int64_t row0, int64_t batch, int64_t out_boff, int64_t res_boff,
+                                           int64_t cs_boff, int col0, const uint32_t (&acc)[32], float pe_alpha) {
   const uint32_t f = e.flags;
+  const int64_t row = row0 + lane;
+  const bool row_ok = row < M;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = e.alpha * __uint_as_float(acc[i]);
   if (f & EPI_BIAS) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (col0 + i < N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    }
   }
   if (f & EPI_RELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
-  if (f & EPI_PE) {
-    const int64_t t = row_in_batch % e.pe_T;
-    const float4 p0 = __ldg(reinterpret_cast<const float4*>(e.pe_t + t * N + col));
-    const float4 p1 = __ldg(reinterpret_cast<const float4*>(e.pe_t + t * N + col + 4));
-    v[0] += pe_alpha * p0.x; v[1] += pe_alpha * p0.y; v[2] += pe_alpha * p0.z; v[3] += pe_alpha * p0.w;
-    v[4] += pe_alpha * p1.x; v[5] += pe_alpha * p1.y; v[6] += pe_alpha * p1.z; v[7] += pe_alpha * p1.w;
-  }
-  float keep[8];
-  if (f & (EPI_DROPOUT | EPI_ACC_GATES_AUX)) {
-    if (e.drop.thresh != 0) {
-      const uint64_t idx = (static_cast<uint64_t>(batch) * batch_M + row_in_batch) * N + col;
-      float s0[4], s1[4];
-      dropout_scale4(e.drop.seed, e.drop_site, idx >> 2, e.drop.thresh, e.drop.inv_keep, s0);
-      dropout_scale4(e.drop.seed, e.drop_site, (idx >> 2) + 1, e.drop.thresh, e.drop.inv_keep, s1);
+  if ((f & EPI_PE) && row_ok) {
+    const float* pr = e.pe_t + (row % e.pe_T) * N + col0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { keep[i] = s0[i]; keep[4 + i] = s1[i]; }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) keep[i] = 1.f;
+    for (int i = 0; i < 32; i += 4) {
+      if (col0 + i < N) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(pr + i));
+        v[i] += pe_alpha * q.x; v[i + 1] += pe_alpha * q.y; v[i + 2] += pe_alpha * q.z; v[i + 3] += pe_alpha * q.w;
+      }
     }
   }
+  const bool use_keep = (f & (EPI_DROPOUT | EPI_ACC_GATES_AUX)) && e.drop.thresh != 0;
   if (f & EPI_DROPOUT) {
+    if (use_keep) {
+      const uint64_t idx = (static_cast<uint64_t>(batch) * M + row) * N + col0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= keep[i];
+      for (int q = 0; q < 8; ++q) {
+        float k4[4];
+        dropout_scale4(e.drop.seed, e.drop_site, (idx >> 2) + q, e.drop.thresh, e.drop.inv_keep, k4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[q * 4 + i] *= k4[i];
+      }
+    }
   }
   if (f & (EPI_RES | EPI_ACC_GATES_AUX)) {
-    float r[8];
-    load8_split(reinterpret_cast<const __nv_bfloat16*>(e.res), e.res_plane_stride, e.res_planes,
-                res_boff + row_in_batch * e.res_ld + col, r);
+    float r[32];
+    load_aux_tile(stage, lane, e.res, e.res_plane_stride, e.res_planes, e.res_ld, res_boff, row0, col0, M, N, r);
     if (f & EPI_RES) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += r[i];
+      for (int i = 0; i < 32; ++i) v[i] += r[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? r[i] * keep[i] : 0.f;
+      for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? r[i] : 0.f;
+      if (use_keep) {
+        const uint64_t idx = (static_cast<uint64_t>(batch) * M + row) * N + col0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float k4[4];
+          dropout_scale4(e.drop.seed, e.drop_site, (idx >> 2) + q, e.drop.thresh, e.drop.inv_keep, k4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[q * 4 + i] *= k4[i];
+        }
+      }
     }
   }
   if (f & EPI_GATE_POS) {
-    float g[8];
-    load8_split(reinterpret_cast<const __nv_bfloat16*>(e.gate), e.gate_plane_stride, e.gate_planes,
-                row_in_batch * e.gate_ld + col, g);
+    float g[32];
+    load_aux_tile(stage, lane, e.gate, e.gate_plane_stride, e.gate_planes, e.gate_ld, 0, row0, col0, M, N, g);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = g[i] > 0.f ? v[i] * e.gate_scale : 0.f;
+    for (int i = 0; i < 32; ++i) v[i] = g[i] > 0.f ? v[i] * e.gate_scale : 0.f;
   }
-  const int64_t o = out_boff + row_in_batch * e.out_ld + col;
-  if (f & EPI_OUT_ATOMIC) {
-    float* dst = reinterpret_cast<float*>(e.out) + o;
+  if (!row_ok) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(dst + i, v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  }
+  if (f & EPI_COLSUM) colsum_tile(stage, lane, e.colsum + cs_boff, col0, N, v);
+  if (f & EPI_OUT_ATOMIC) {
+    store_f32_tile<true>(stage, lane, reinterpret_cast<float*>(e.out), e.out_ld, out_boff, row0, col0, M, N, v);
   } else if (f & EPI_OUT_F32) {
-    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + o);
-    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    store_f32_tile<false>(stage, lane, reinterpret_cast<float*>(e.out), e.out_ld, out_boff, row0, col0, M, N, v);
   } else {
-    store8_split(reinterpret_cast<__nv_bfloat16*>(e.out), e.out_plane_stride, e.out_planes, o, v);
+    store_split_tile(stage, lane, e.out, e.out_plane_stride, e.out_planes, e.out_ld, out_boff, row0, col0, M, N, v);
   }
 }
 
@@ -143,6 +281,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t epi_stage_base = bar_base + BAR_BYTES;
   auto sA = [&](int s, int p) { return smem_base + s * Cfg::STAGE_BYTES + p * Cfg::A_BYTES; };
   auto sB = [&](int s, int p) { return smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES + p * Cfg::B_BYTES; };
 
@@ -282,11 +421,13 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase, 0x400u + acc);
       tc_fence_after();
-      const int64_t row = static_cast<int64_t>(tm) * BLOCK_M + w * 32 + lane;
-      const bool row_ok = row < args.M;
+      const int64_t row0 = static_cast<int64_t>(tm) * BLOCK_M + w * 32;
       const int64_t out_boff = i0 * e.out_sb0 + i1 * e.out_sb1;
       const int64_t res_boff = i0 * e.res_sb0 + i1 * e.res_sb1;
+      const int64_t cs_boff = i0 * e.colsum_sb0;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BLOCK_N;
+      const uint32_t stage_buf = epi_stage_base + w * EPI_STAGE_BYTES;
+      const bool warp_rows_ok = row0 < args.M;     // warp-uniform
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         const int col0 = tn * BLOCK_N + c * 32;
@@ -294,13 +435,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         uint32_t r[32];
         tmem_ld_32x32(t_row + c * 32, r);
         tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < args.N) epilogue8(e, args.N, args.M, row, t, out_boff, res_boff, col, r + g * 8, pe_alpha);
-          }
-        }
+        if (warp_rows_ok)
+          epilogue32(e, stage_buf, lane, args.M, args.N, row0, t, out_boff, res_boff, cs_boff, col0, r, pe_alpha);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));

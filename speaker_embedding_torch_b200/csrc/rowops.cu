@@ -129,14 +129,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
                                                      __nv_bfloat16* __restrict__ dz, int64_t dz_ps, int dz_planes,
                                                      __nv_bfloat16* __restrict__ dz_drop, DropCfg drop, uint32_t site,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                     int64_t rows) {
-  __shared__ float red[2][8][256];
+                                                     float* __restrict__ dbias, int64_t rows) {
+  __shared__ float red[3][8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float g[8], ag[8], ab[8];
+  float g[8], ag[8], ab[8], az[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { g[i] = __ldg(gamma + lane * 8 + i); ag[i] = 0.f; ab[i] = 0.f; }
+  for (int i = 0; i < 8; ++i) { g[i] = __ldg(gamma + lane * 8 + i); ag[i] = 0.f; ab[i] = 0.f; az[i] = 0.f; }
   for (int64_t r = warp; r < rows; r += nwarps) {
     float d[8], x[8];
     load8_split(dy, dy_ps, dy_planes, r * 256 + lane * 8, d);
@@ -167,19 +167,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
       for (int i = 0; i < 4; ++i) { o[i] *= k0[i]; o[4 + i] *= k1[i]; }
       store8_split(dz_drop, dz_ps, dz_planes, r * 256 + lane * 8, o);
     }
+    // o is now the gradient of the sub-layer output (dz, or dz * keep): its column sum is that layer's bias grad
+#pragma unroll
+    for (int i = 0; i < 8; ++i) az[i] += o[i];
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { red[0][wib][lane * 8 + i] = ag[i]; red[1][wib][lane * 8 + i] = ab[i]; }
+  for (int i = 0; i < 8; ++i) {
+    red[0][wib][lane * 8 + i] = ag[i]; red[1][wib][lane * 8 + i] = ab[i]; red[2][wib][lane * 8 + i] = az[i];
+  }
   __syncthreads();
-  float sg = 0.f, sb = 0.f;
+  float sg = 0.f, sb = 0.f, sz = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) { sg += red[0][w][threadIdx.x]; sb += red[1][w][threadIdx.x]; }
+  for (int w = 0; w < 8; ++w) { sg += red[0][w][threadIdx.x]; sb += red[1][w][threadIdx.x]; sz += red[2][w][threadIdx.x]; }
   atomicAdd(dgamma + threadIdx.x, sg);
   atomicAdd(dbeta + threadIdx.x, sb);
+  if (dbias != nullptr) atomicAdd(dbias + threadIdx.x, sz);
 }
 int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t z_ps, int z_planes, const float* stats,
            const float* gamma, void* dz, int64_t dz_ps, int dz_planes, void* dz_drop, DropCfg drop, uint32_t site,
-           float* dgamma, float* dbeta, int64_t rows, cudaStream_t st) {
+           float* dgamma, float* dbeta, float* dbias, int64_t rows, cudaStream_t st) {
   ProfScope prof("ln_bwd", 0, 512.0 * rows * (dy_planes + z_planes + dz_planes * (drop.thresh ? 2 : 1)), st);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 4));
   ln_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ps, dy_planes,
@@ -187,7 +193,7 @@ int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t 
                                         reinterpret_cast<const float2*>(stats), gamma,
                                         reinterpret_cast<__nv_bfloat16*>(dz), dz_ps, dz_planes,
                                         (drop.thresh != 0) ? reinterpret_cast<__nv_bfloat16*>(dz_drop) : nullptr, drop,
-                                        site, dgamma, dbeta, rows);
+                                        site, dgamma, dbeta, dbias, rows);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -195,6 +201,7 @@ int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t 
 // ------------------------------------------------------------------------------------------------
 // Row softmax over the first T of Tp columns (Tp % 8 == 0, Tp <= 1024); one warp per row.
 // Writes P (and P_drop = P * keep / (1-p) when dropout is on); pad columns are written as zeros.
+template <int CH>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* __restrict__ s, int64_t ps, int planes,
                                                           __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ p_drop,
                                                           DropCfg drop, uint32_t site, int64_t rows, int T, int Tp) {
@@ -202,10 +209,10 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = warp; r < rows; r += nwarps) {
-    float v[4][8];
+    float v[CH][8];
     float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < Tp) {
         load8_split(s, ps, planes, r * Tp + col, v[c]);
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < Tp) {
 #pragma unroll
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
     }
     const float inv = 1.f / warp_sum(sum);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < Tp) {
 #pragma unroll
@@ -252,16 +259,23 @@ int softmax_fwd(const void* s, int64_t ps, int planes, void* p, void* p_drop, Dr
   ProfScope prof("softmax_fwd", 0, 2.0 * rows * Tp * planes * (drop.thresh ? 3 : 2), st);
   SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
-  softmax_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(s), ps, planes,
-                                             reinterpret_cast<__nv_bfloat16*>(p),
-                                             drop.thresh != 0 ? reinterpret_cast<__nv_bfloat16*>(p_drop) : nullptr,
-                                             drop, site, rows, T, Tp);
+  const int ch = (Tp + 255) / 256;
+  auto* sp = reinterpret_cast<const __nv_bfloat16*>(s);
+  auto* pp = reinterpret_cast<__nv_bfloat16*>(p);
+  auto* pdp = drop.thresh != 0 ? reinterpret_cast<__nv_bfloat16*>(p_drop) : nullptr;
+  switch (ch) {
+    case 1: softmax_fwd_kernel<1><<<blocks, 256, 0, st>>>(sp, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
+    case 2: softmax_fwd_kernel<2><<<blocks, 256, 0, st>>>(sp, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
+    case 3: softmax_fwd_kernel<3><<<blocks, 256, 0, st>>>(sp, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
+    default: softmax_fwd_kernel<4><<<blocks, 256, 0, st>>>(sp, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
+  }
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
 
 // dS = scale * P * (dP' - sum_k dP'_k P_k),  dP' = dP_drop * keep/(1-p)
 // dp and ds may alias (in-place): a warp reads its whole row before writing it, so no __restrict__ here.
+template <int CH>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p,
                                                           const __nv_bfloat16* dp, int64_t ps, int planes,
                                                           __nv_bfloat16* ds, DropCfg drop, uint32_t site,
@@ -270,10 +284,10 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = warp; r < rows; r += nwarps) {
-    float pv[4][8], dv[4][8];
+    float pv[CH][8], dv[CH][8];
     float dot = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < Tp) {
         load8_split(p, ps, planes, r * Tp + col, pv[c]);
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
     }
     dot = warp_sum(dot);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < Tp) {
         float o[8];
@@ -311,9 +325,16 @@ int softmax_bwd(const void* p, const void* dp, int64_t ps, int planes, void* ds,
   ProfScope prof("softmax_bwd", 0, 2.0 * rows * Tp * planes * 3, st);
   SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
-  softmax_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(p),
-                                             reinterpret_cast<const __nv_bfloat16*>(dp), ps, planes,
-                                             reinterpret_cast<__nv_bfloat16*>(ds), drop, site, scale, rows, T, Tp);
+  const int ch = (Tp + 255) / 256;
+  auto* pp = reinterpret_cast<const __nv_bfloat16*>(p);
+  auto* dpp = reinterpret_cast<const __nv_bfloat16*>(dp);
+  auto* dsp = reinterpret_cast<__nv_bfloat16*>(ds);
+  switch (ch) {
+    case 1: softmax_bwd_kernel<1><<<blocks, 256, 0, st>>>(pp, dpp, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
+    case 2: softmax_bwd_kernel<2><<<blocks, 256, 0, st>>>(pp, dpp, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
+    case 3: softmax_bwd_kernel<3><<<blocks, 256, 0, st>>>(pp, dpp, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
+    default: softmax_bwd_kernel<4><<<blocks, 256, 0, st>>>(pp, dpp, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
+  }
   SPK_CUDA(cudaGetLastError());
   return 0;
 }

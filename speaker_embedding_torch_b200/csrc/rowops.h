@@ -24,7 +24,7 @@ int ln_fwd(const void* z, int64_t z_ps, int z_planes, int64_t z_row_step, const 
            void* y, int64_t y_ps, int y_planes, float* stats, int64_t rows, cudaStream_t st);
 int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t z_ps, int z_planes, const float* stats,
            const float* gamma, void* dz, int64_t dz_ps, int dz_planes, void* dz_drop, DropCfg drop, uint32_t site,
-           float* dgamma, float* dbeta, int64_t rows, cudaStream_t st);
+           float* dgamma, float* dbeta, float* dbias, int64_t rows, cudaStream_t st);
 
 int softmax_fwd(const void* s, int64_t ps, int planes, void* p, void* p_drop, DropCfg drop, uint32_t site,
                 int64_t rows, int T, int Tp, cudaStream_t st);
