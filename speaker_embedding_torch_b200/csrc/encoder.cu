@@ -515,7 +515,8 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.planes = P; g.M = (int)Mt; g.N = (int)F; g.K = (int)D;
       g.epi.flags = EPI_GATE_POS | EPI_COLSUM;
       g.epi.colsum = lg.linear1_b;
-      g.epi.gate = c.ptr(b.f); g.epi.gate_plane_stride = b.f.ps; g.epi.gate_ld = F; g.epi.gate_planes = P;
+      g.epi.gate = c.ptr(b.f); g.epi.gate_plane_stride = b.f.ps; g.epi.gate_ld = F;
+      g.epi.gate_planes = 1;   // f >= 0 and bf16(f) > 0 <=> f > 0: the hi plane alone decides the ReLU gate
       g.epi.gate_scale = drop.inv_keep;
       c.out(g.epi, pl.df, 0, F);
       SPK_TRY(gemm_run(g, st));

@@ -13,8 +13,9 @@
 //   while the MMA warp works on tile i+1;
 // * grid = min(#tiles, #SMs); tiles are assigned round-robin (persistent CTAs).
 //
-// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
-// 4..7 = epilogue (warp w owns TMEM lanes 32*(w-4) .. +31 == accumulator rows).
+// Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
+// 4..11 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31 == accumulator rows; warps 4-7 take the even
+// 32-column chunks of a tile, warps 8-11 the odd ones).
 #include "gemm.h"
 #include "ptx.cuh"
 
@@ -27,7 +28,8 @@ constexpr int BLOCK_K = 64;              // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in limit per CTA
 constexpr int BAR_BYTES = 256;
-constexpr int EPI_SMEM = 4 * 4352;       // four epilogue warps x staging tile
+constexpr int NUM_EPI_WARPS = 8;         // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int EPI_SMEM = NUM_EPI_WARPS * 2176;
 
 struct GemmKernelArgs {
   CUtensorMap a_map[3];
@@ -47,7 +49,7 @@ struct TileCfg {
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_SMEM;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static_assert(STAGES >= 2, "need at least a double buffer");
+  static_assert(STAGES >= 1, "operand ring does not fit shared memory");
   static_assert(2 * BLOCK_N <= 512, "accumulator double buffer must fit TMEM");
 };
 
@@ -57,47 +59,61 @@ struct TileCfg {
 // a per-warp shared-memory tile (32 rows x 64 B, 16-B chunks XOR-swizzled so that both the "lane owns a
 // row" and the "8 lanes cover 2 rows x 64 B" access patterns are bank-conflict free), so each warp
 // memory instruction touches 8 rows x 64 contiguous bytes (full 32-B sectors).
-constexpr int EPI_STAGE_BYTES = 4352;    // per warp: bf16 tile (2 KB) or fp32 32 x 33 column-sum tile
+constexpr int EPI_STAGE_BYTES = 2176;    // per warp: bf16 tile 32 x 32 (2 KB) or fp32 tile 32 x 17
 
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
-// r[32] += aux[row0 + lane][col0 .. col0+31]  (split tensor, rows >= M / cols >= N read as 0)
+// r[32] = aux[row0 + lane][col0 .. col0+31]  (split tensor, rows >= M / cols >= N read as 0).
+// All planes' global loads are issued before the first wait so up to 12 x 16 B per lane are in flight.
 __device__ __forceinline__ void load_aux_tile(uint32_t stage, int lane, const void* base_v, int64_t ps, int planes,
                                               int64_t ld, int64_t boff, int64_t row0, int col0, int M, int N,
                                               float (&r)[32]) {
   const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(base_v);
+  uint4 g[3][4];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) r[i] = 0.f;
-  for (int p = 0; p < planes; ++p) {
+  for (int p = 0; p < 3; ++p) {
+    if (p < planes) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + (lane >> 2), cc = lane & 3;
-      const int64_t grow = row0 + rr;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (grow < M && col0 + cc * 8 < N)
-        v = *reinterpret_cast<const uint4*>(base + p * ps + boff + grow * ld + col0 + cc * 8);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(rr, cc)), "r"(v.x), "r"(v.y),
-                   "r"(v.z), "r"(v.w)
-                   : "memory");
-    }
-    __syncwarp();
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      uint32_t w0, w1, w2, w3;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                   : "r"(stage + stage_off(lane, cc))
-                   : "memory");
-      const uint32_t ww[4] = {w0, w1, w2, w3};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        r[cc * 8 + 2 * i] += bf16lo_to_f(ww[i]);
-        r[cc * 8 + 2 * i + 1] += bf16hi_to_f(ww[i]);
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2), cc = lane & 3;
+        const int64_t grow = row0 + rr;
+        g[p][it] = make_uint4(0u, 0u, 0u, 0u);
+        if (grow < M && col0 + cc * 8 < N)
+          g[p][it] = __ldg(reinterpret_cast<const uint4*>(base + p * ps + boff + grow * ld + col0 + cc * 8));
       }
     }
-    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = 0.f;
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    if (p < planes) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2), cc = lane & 3;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(rr, cc)), "r"(g[p][it].x),
+                     "r"(g[p][it].y), "r"(g[p][it].z), "r"(g[p][it].w)
+                     : "memory");
+      }
+      __syncwarp();
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                     : "r"(stage + stage_off(lane, cc))
+                     : "memory");
+        const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          r[cc * 8 + 2 * i] += bf16lo_to_f(ww[i]);
+          r[cc * 8 + 2 * i + 1] += bf16hi_to_f(ww[i]);
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -138,45 +154,55 @@ __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void*
   }
 }
 
-// fp32 tile (plain store or atomic add), coalesced through a 32 x 33 fp32 staging tile
+// fp32 tile (plain store or atomic add), coalesced through a 32 x 17 fp32 staging tile, 16 columns at a time:
+// each instruction covers 2 rows x 64 contiguous bytes.
 template <bool ATOMIC>
 __device__ __forceinline__ void store_f32_tile(uint32_t stage, int lane, float* base, int64_t ld, int64_t boff,
                                                int64_t row0, int col0, int M, int N, const float (&v)[32]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage + (lane * 33 + i) * 4), "f"(v[i]) : "memory");
-  __syncwarp();
-  const bool col_ok = col0 + lane < N;
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage + (lane * 17 + i) * 4), "f"(v[h * 16 + i]) : "memory");
+    __syncwarp();
+    const int cl = lane & 15, rh = lane >> 4;
+    const bool col_ok = col0 + h * 16 + cl < N;
 #pragma unroll 4
-  for (int rr = 0; rr < 32; ++rr) {
-    float x;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stage + (rr * 33 + lane) * 4) : "memory");
-    const int64_t grow = row0 + rr;
-    if (col_ok && grow < M) {
-      float* dst = base + boff + grow * ld + col0 + lane;
-      if (ATOMIC) atomicAdd(dst, x);
-      else *dst = x;
+    for (int rr = 0; rr < 32; rr += 2) {
+      float x;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stage + ((rr + rh) * 17 + cl) * 4) : "memory");
+      const int64_t grow = row0 + rr + rh;
+      if (col_ok && grow < M) {
+        float* dst = base + boff + grow * ld + col0 + h * 16 + cl;
+        if (ATOMIC) atomicAdd(dst, x);
+        else *dst = x;
+      }
     }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
-// colsum[col0 + lane] += sum over the warp's 32 rows of v[.][lane]   (bias gradients, fused)
+// colsum[col0 + c] += sum over the warp's 32 rows of v[.][c]   (bias gradients, fused)
 __device__ __forceinline__ void colsum_tile(uint32_t stage, int lane, float* colsum, int col0, int N,
                                             const float (&v)[32]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage + (lane * 33 + i) * 4), "f"(v[i]) : "memory");
-  __syncwarp();
-  float s = 0.f;
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage + (lane * 17 + i) * 4), "f"(v[h * 16 + i]) : "memory");
+    __syncwarp();
+    const int cl = lane & 15, rh = lane >> 4;
+    float sacc = 0.f;
 #pragma unroll 8
-  for (int rr = 0; rr < 32; ++rr) {
-    float x;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stage + (rr * 33 + lane) * 4) : "memory");
-    s += x;
+    for (int rr = 0; rr < 16; ++rr) {
+      float x;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stage + ((rh * 16 + rr) * 17 + cl) * 4) : "memory");
+      sacc += x;
+    }
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+    if (rh == 0 && col0 + h * 16 + cl < N) atomicAdd(colsum + col0 + h * 16 + cl, sacc);
+    __syncwarp();
   }
-  if (col0 + lane < N) atomicAdd(colsum + col0 + lane, s);
-  __syncwarp();
 }
 
 __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage, int lane, int M, int N,
@@ -267,7 +293,7 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
 
 // ------------------------------------------------------------------------------------------------
 template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
-__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ GemmKernelArgs args) {
+__global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(const __grid_constant__ GemmKernelArgs args) {
   using Cfg = TileCfg<PLANES, BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 32 * NUM_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -407,7 +433,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
-    const int w = warp - 4;
+    const int w = (warp - 4) & 3;          // TMEM lane quarter (warp % 4) -> accumulator rows 32w .. 32w+31
+    const int cgroup = (warp - 4) >> 2;    // this warp handles the 32-column chunks with (c & 1) == cgroup
     const GemmEpilogue& e = args.epi;
     const float pe_alpha = (e.flags & EPI_PE) ? __ldg(e.pe_alpha) : 0.f;
     int it = 0;
@@ -426,10 +453,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       const int64_t res_boff = i0 * e.res_sb0 + i1 * e.res_sb1;
       const int64_t cs_boff = i0 * e.colsum_sb0;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BLOCK_N;
-      const uint32_t stage_buf = epi_stage_base + w * EPI_STAGE_BYTES;
+      const uint32_t stage_buf = epi_stage_base + (warp - 4) * EPI_STAGE_BYTES;
       const bool warp_rows_ok = row0 < args.M;     // warp-uniform
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = cgroup; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
         const int col0 = tn * BLOCK_N + c * 32;
         if (col0 >= args.N) break;             // warp-uniform
         uint32_t r[32];
@@ -518,7 +545,7 @@ static int launch(const GemmKernelArgs& args, int grid, cudaStream_t stream) {
     SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(args);
+  kern<<<grid, 128 + 32 * NUM_EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(args);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
