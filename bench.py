@@ -49,8 +49,13 @@ def synth_mel(gen, batch, frames, device):
 
 
 def dense_flops_fwd(T):
-    """Algorithmic forward FLOPs per slice (dense accounting)."""
+    """Algorithmic forward FLOPs per slice as the reference executes it (dense accounting)."""
     return 40960.0 * T + 3 * (1572864.0 * T + 1024.0 * T * T) + 131072.0
+
+
+def min_flops_fwd(T):
+    """Forward FLOPs per slice of the variant executed here: last layer pruned to the t = 0 query (SURVEY.md 8d F_min)."""
+    return 40960.0 * T + 2 * (1572864.0 * T + 1024.0 * T * T) + (262144.0 * T + 1024.0 * T + 1310720.0) + 131072.0
 
 
 class ClockSampler:
@@ -186,7 +191,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     K, W = max(1, args.steps), max(3, args.warmup)
     pk = peaks()
 
@@ -261,15 +267,17 @@ def run_native(args):
 
     # ---- per-kernel profile (events around every launch; separate pass so it does not perturb `value`)
     line_extra = {}
+    # every rank runs the profiled steps (backward contains the gradient all-reduce); rank 0 reports
+    _native.prof_enable(True)
+    prof_steps = 2
+    Tp = lengths[W]
+    for i in range(prof_steps):
+        step(synth_mel(gen, batch, Tp, dev))
+    torch.cuda.synchronize()
+    rep = _native.prof_report()
+    _native.prof_enable(False)
+    barrier()
     if rank == 0:
-        _native.prof_enable(True)
-        prof_steps = 2
-        Tp = lengths[W]
-        for i in range(prof_steps):
-            step(synth_mel(gen, batch, Tp, dev))
-        torch.cuda.synchronize()
-        rep = _native.prof_report()
-        _native.prof_enable(False)
         launches_per_step = sum(r["launches"] for r in rep.values()) // prof_steps
         tot_ms = sum(r["ms"] for r in rep.values())
         top = max(rep.items(), key=lambda kv: kv[1]["ms"])
@@ -318,8 +326,9 @@ def run_native(args):
                                          for k, v in sorted(irep.items(), key=lambda kv: -kv[1]["ms"])}
         model.train()
         line_extra["extra"] = {"dvectors_per_sec_160f_1gpu": batch / (dv_ms * 1e-3), "infer_ms_per_960x160_batch": dv_ms,
-                               "infer_tensor_frac_of_sustained": batch * dense_flops_fwd(160) / (dv_ms * 1e-3) / 1e12 / pk["tf_sus"],
-                               "train_tensor_frac_of_sustained": 3 * batch * dense_flops_fwd(160) * value / world / 1e12 / pk["tf_sus"],
+                               "flop_accounting": "F_min (last layer pruned to the t=0 query), bf16 dense count, extra split-plane MMAs not credited",
+                               "infer_tensor_frac_of_sustained": batch * min_flops_fwd(160) / (dv_ms * 1e-3) / 1e12 / pk["tf_sus"],
+                               "train_tensor_frac_of_sustained": 3 * batch * min_flops_fwd(160) * value / world / 1e12 / pk["tf_sus"],
                                "last_loss": last_loss}
 
     barrier()

@@ -136,6 +136,10 @@ int spk_split_pack(const float* src, void* dst, int64_t plane_stride, int planes
 
 int spk_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Library options.  "prune_last_layer" (default 1): run the last encoder layer only for the t = 0 query row
+ * the d-vector head consumes (exact; K and V are still projected for every frame). */
+int spk_set_option(const char* name, int value);
+
 /* Launch profiler (used by bench.py for the per-kernel roofline): when enabled every launcher brackets
  * its kernel with CUDA events on the launching stream.  spk_prof_report synchronises those events,
  * writes one text line per kernel tag -- "tag launches total_ms algorithmic_flops algorithmic_bytes" --

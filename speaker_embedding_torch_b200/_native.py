@@ -22,7 +22,7 @@ EXPORTS = (
     "spk_abi_version", "spk_last_error", "spk_encoder_workspace_bytes", "spk_encoder_forward",
     "spk_encoder_backward", "spk_ge2e_workspace_bytes", "spk_ge2e_loss", "spk_optim_step",
     "spk_gemm", "spk_split_pack", "spk_device_info", "spk_prof_enable", "spk_prof_report",
-    "spk_encoder_debug_layout",
+    "spk_encoder_debug_layout", "spk_set_option",
 )
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
@@ -127,6 +127,8 @@ def lib():
         L.spk_split_pack.argtypes = [vp, vp, i64, i32, i64, vp]
         L.spk_device_info.restype = i32
         L.spk_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        L.spk_set_option.restype = i32
+        L.spk_set_option.argtypes = [ctypes.c_char_p, i32]
         L.spk_prof_enable.restype = i32
         L.spk_prof_enable.argtypes = [i32]
         L.spk_prof_report.restype = i32
@@ -257,3 +259,7 @@ def prof_report():
         tag, cnt, ms, fl, by = line.split()
         out[tag] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by))
     return out
+
+
+def set_option(name, value):
+    check(lib().spk_set_option(name.encode(), int(value)), "spk_set_option")

@@ -87,6 +87,13 @@ int spk_split_pack(const float* src, void* dst, int64_t plane_stride, int planes
   return pack_weights(tab, dst, plane_stride, planes, as_stream(stream));
 }
 
+int spk_set_option(const char* name, int value) {
+  SPK_CHECK(name != nullptr, "spk_set_option: null name");
+  if (strcmp(name, "prune_last_layer") == 0) { encoder_set_prune(value != 0); return 0; }
+  set_error("spk_set_option: unknown option '%s'", name);
+  return SPK_EINVAL;
+}
+
 int spk_prof_enable(int on) { prof_set(on != 0); return 0; }
 int spk_prof_report(char* buf, size_t cap) { return prof_report(buf, cap); }
 

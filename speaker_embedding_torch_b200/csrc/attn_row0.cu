@@ -1,0 +1,201 @@
+// Last-layer attention for the single query row t = 0.
+//
+// The d-vector head consumes only the first frame of the last encoder layer (Modules.py:54,
+// `x.permute(1, 2, 0)[:, :, :1]`), so in that layer only the t = 0 query is ever needed: K and V are
+// still projected for every frame, but Q, the attention output, out-proj, both LayerNorms and the FFN
+// run on one row per slice (exact; SURVEY.md Appendix B, "Last layer").  With one query per (slice, head)
+// the score / softmax / PV contraction is 2 x T x 64 MACs -- a bandwidth-bound sweep over K and V that
+// is done here in fp32 by one warp per (slice, head), forward and backward.
+//
+// Layouts: q0 [B, 256] and kv [B*T, 512] (K | V, head h at columns h*64) are split-bf16 tensors;
+// probabilities p / p*keep are kept in fp32 [B*H, Tp] for the backward pass.
+#include "rowops.h"
+
+namespace spk {
+
+constexpr int R0_WARPS = 4;   // warps per block == heads of one slice
+
+__device__ __forceinline__ float2 load2_split(const __nv_bfloat16* base, int64_t ps, int planes, int64_t off) {
+  float2 r = make_float2(0.f, 0.f);
+  for (int p = 0; p < planes; ++p) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(base + p * ps + off);
+    r.x += bf16lo_to_f(w);
+    r.y += bf16hi_to_f(w);
+  }
+  return r;
+}
+__device__ __forceinline__ void store2_split(__nv_bfloat16* base, int64_t ps, int planes, int64_t off, float a, float b) {
+  for (int p = 0; p < planes; ++p) {
+    __nv_bfloat162 q = __floats2bfloat162_rn(a, b);
+    *reinterpret_cast<__nv_bfloat162*>(base + p * ps + off) = q;
+    a -= __bfloat162float(q.x);
+    b -= __bfloat162float(q.y);
+  }
+}
+__device__ __forceinline__ float keep_of(const DropCfg& d, uint32_t site, uint64_t idx) {
+  if (d.thresh == 0) return 1.f;
+  float k4[4];
+  dropout_scale4(d.seed, site, idx >> 2, d.thresh, d.inv_keep, k4);
+  return k4[idx & 3];
+}
+
+// one warp per (slice b, head h); lane owns head dims 2*lane, 2*lane+1
+__global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
+    const __nv_bfloat16* __restrict__ q0, int64_t q_ps, const __nv_bfloat16* __restrict__ kv, int64_t kv_ps, int planes,
+    __nv_bfloat16* __restrict__ att0, int64_t a_ps, float* __restrict__ p0, float* __restrict__ pd0, DropCfg drop,
+    uint32_t site, int B, int H, int T, int Tp) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t bh = static_cast<int64_t>(blockIdx.x) * R0_WARPS + warp;
+  if (bh >= static_cast<int64_t>(B) * H) return;
+  const int b = static_cast<int>(bh / H), h = static_cast<int>(bh % H);
+  float* sc = sm + warp * Tp;
+  const float2 q = load2_split(q0, q_ps, planes, static_cast<int64_t>(b) * 256 + h * 64 + 2 * lane);
+  const int64_t kv_row0 = static_cast<int64_t>(b) * T * 512 + h * 64 + 2 * lane;
+  for (int t = 0; t < T; ++t) {
+    const float2 k = load2_split(kv, kv_ps, planes, kv_row0 + static_cast<int64_t>(t) * 512);
+    const float s = warp_sum(q.x * k.x + q.y * k.y);
+    if (lane == 0) sc[t] = s * 0.125f;
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int t = lane; t < T; t += 32) mx = fmaxf(mx, sc[t]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int t = lane; t < T; t += 32) {
+    const float e = __expf(sc[t] - mx);
+    sc[t] = e;
+    sum += e;
+  }
+  const float inv = 1.f / warp_sum(sum);
+  for (int t = lane; t < Tp; t += 32) {
+    float p = 0.f, pd = 0.f;
+    if (t < T) {
+      p = sc[t] * inv;
+      pd = p * keep_of(drop, site, static_cast<uint64_t>(bh) * Tp + t);
+      sc[t] = pd;
+    }
+    if (p0 != nullptr) {
+      p0[bh * Tp + t] = p;
+      pd0[bh * Tp + t] = pd;
+    }
+  }
+  __syncwarp();
+  float2 o = make_float2(0.f, 0.f);
+  for (int t = 0; t < T; ++t) {
+    const float2 v = load2_split(kv, kv_ps, planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512);
+    const float pd = sc[t];
+    o.x = fmaf(pd, v.x, o.x);
+    o.y = fmaf(pd, v.y, o.y);
+  }
+  store2_split(att0, a_ps, planes, static_cast<int64_t>(b) * 256 + h * 64 + 2 * lane, o.x, o.y);
+}
+
+int attn_row0_fwd(const void* q0, int64_t q_ps, const void* kv, int64_t kv_ps, int planes, void* att0, int64_t a_ps,
+                  float* p0, float* pd0, DropCfg drop, uint32_t site, int B, int H, int T, int Tp, cudaStream_t st) {
+  SPK_CHECK(H == R0_WARPS, "attn_row0: %d heads unsupported", H);
+  ProfScope prof("attn_row0_fwd", 4.0 * B * H * T * 64, 2.0 * B * T * 512 * planes, st);
+  const int blocks = (B * H + R0_WARPS - 1) / R0_WARPS;
+  attn_row0_fwd_kernel<<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q0), q_ps, reinterpret_cast<const __nv_bfloat16*>(kv), kv_ps, planes,
+      reinterpret_cast<__nv_bfloat16*>(att0), a_ps, p0, pd0, drop, site, B, H, T, Tp);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Backward: given d(att0), produces dq0 [B,256], dense dK | dV rows [B*T, 512] and the three in-proj bias
+// gradient slices.  p*dp' = pd*dp (pd = p*keep), so the saved p / pd pair is all the dropout state needed.
+__global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
+    const __nv_bfloat16* __restrict__ datt0, int64_t da_ps, int g_planes, const __nv_bfloat16* __restrict__ q0,
+    int64_t q_ps, const __nv_bfloat16* __restrict__ kv, int64_t kv_ps, int planes, const float* __restrict__ p0,
+    const float* __restrict__ pd0, __nv_bfloat16* __restrict__ dq0, int64_t dq_ps, __nv_bfloat16* __restrict__ dkv,
+    int64_t dkv_ps, float* __restrict__ dbias /* [768] q | k | v */, int B, int H, int T, int Tp) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t bh = static_cast<int64_t>(blockIdx.x) * R0_WARPS + warp;
+  if (bh >= static_cast<int64_t>(B) * H) return;
+  const int b = static_cast<int>(bh / H), h = static_cast<int>(bh % H);
+  float* ds = sm + warp * Tp;
+  const int64_t col = h * 64 + 2 * lane;
+  const float2 dout = load2_split(datt0, da_ps, g_planes, static_cast<int64_t>(b) * 256 + col);
+  const float2 q = load2_split(q0, q_ps, planes, static_cast<int64_t>(b) * 256 + col);
+  const int64_t kv_row0 = static_cast<int64_t>(b) * T * 512 + col;
+  const float* p = p0 + bh * Tp;
+  const float* pd = pd0 + bh * Tp;
+  // dV rows and dp_t = dO . V_t
+  float pd_sum = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float2 v = load2_split(kv, kv_ps, planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512);
+    const float dp = warp_sum(dout.x * v.x + dout.y * v.y);
+    const float pdt = pd[t];
+    if (lane == 0) ds[t] = dp;
+    pd_sum += pdt;
+    store2_split(dkv, dkv_ps, g_planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512, pdt * dout.x, pdt * dout.y);
+  }
+  __syncwarp();
+  float dot = 0.f;
+  for (int t = lane; t < T; t += 32) dot += pd[t] * ds[t];
+  dot = warp_sum(dot);
+  float ds_sum = 0.f;
+  for (int t = lane; t < T; t += 32) {
+    const float d = 0.125f * (pd[t] * ds[t] - p[t] * dot);
+    ds[t] = d;
+    ds_sum += d;
+  }
+  ds_sum = warp_sum(ds_sum);
+  __syncwarp();
+  float2 dq = make_float2(0.f, 0.f);
+  for (int t = 0; t < T; ++t) {
+    const float2 k = load2_split(kv, kv_ps, planes, kv_row0 + static_cast<int64_t>(t) * 512);
+    const float d = ds[t];
+    dq.x = fmaf(d, k.x, dq.x);
+    dq.y = fmaf(d, k.y, dq.y);
+    store2_split(dkv, dkv_ps, g_planes, kv_row0 + static_cast<int64_t>(t) * 512, d * q.x, d * q.y);
+  }
+  store2_split(dq0, dq_ps, g_planes, static_cast<int64_t>(b) * 256 + col, dq.x, dq.y);
+  atomicAdd(dbias + col, dq.x);
+  atomicAdd(dbias + col + 1, dq.y);
+  atomicAdd(dbias + 256 + col, ds_sum * q.x);
+  atomicAdd(dbias + 256 + col + 1, ds_sum * q.y);
+  atomicAdd(dbias + 512 + col, pd_sum * dout.x);
+  atomicAdd(dbias + 512 + col + 1, pd_sum * dout.y);
+}
+
+int attn_row0_bwd(const void* datt0, int64_t da_ps, int g_planes, const void* q0, int64_t q_ps, const void* kv,
+                  int64_t kv_ps, int planes, const float* p0, const float* pd0, void* dq0, int64_t dq_ps, void* dkv,
+                  int64_t dkv_ps, float* dbias, int B, int H, int T, int Tp, cudaStream_t st) {
+  SPK_CHECK(H == R0_WARPS, "attn_row0: %d heads unsupported", H);
+  ProfScope prof("attn_row0_bwd", 8.0 * B * H * T * 64, 2.0 * B * T * 512 * (planes + g_planes), st);
+  const int blocks = (B * H + R0_WARPS - 1) / R0_WARPS;
+  attn_row0_bwd_kernel<<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(datt0), da_ps, g_planes, reinterpret_cast<const __nv_bfloat16*>(q0), q_ps,
+      reinterpret_cast<const __nv_bfloat16*>(kv), kv_ps, planes, p0, pd0, reinterpret_cast<__nv_bfloat16*>(dq0), dq_ps,
+      reinterpret_cast<__nv_bfloat16*>(dkv), dkv_ps, dbias, B, H, T, Tp);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dst[b * dst_row_step, :] += src[b, :]   (256 columns; scatters the t = 0 rows back into a token-major tensor)
+__global__ void __launch_bounds__(256) rows_add_kernel(__nv_bfloat16* __restrict__ dst, int64_t d_ps, int64_t dst_row_step,
+                                                       const __nv_bfloat16* __restrict__ src, int64_t s_ps, int planes,
+                                                       int rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  float a[8], c[8];
+  load8_split(dst, d_ps, planes, r * dst_row_step * 256 + lane * 8, a);
+  load8_split(src, s_ps, planes, r * 256 + lane * 8, c);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] += c[i];
+  store8_split(dst, d_ps, planes, r * dst_row_step * 256 + lane * 8, a);
+}
+int rows_add(void* dst, int64_t d_ps, int64_t dst_row_step, const void* src, int64_t s_ps, int planes, int rows,
+             cudaStream_t st) {
+  ProfScope prof("rows_add", 0, 3.0 * rows * 512 * planes, st);
+  rows_add_kernel<<<(rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(dst), d_ps, dst_row_step,
+                                                  reinterpret_cast<const __nv_bfloat16*>(src), s_ps, planes, rows);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace spk

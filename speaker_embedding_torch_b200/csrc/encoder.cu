@@ -12,6 +12,14 @@
 
 namespace spk {
 
+int attn_row0_fwd(const void* q0, int64_t q_ps, const void* kv, int64_t kv_ps, int planes, void* att0, int64_t a_ps,
+                  float* p0, float* pd0, DropCfg drop, uint32_t site, int B, int H, int T, int Tp, cudaStream_t st);
+int attn_row0_bwd(const void* datt0, int64_t da_ps, int g_planes, const void* q0, int64_t q_ps, const void* kv,
+                  int64_t kv_ps, int planes, const float* p0, const float* pd0, void* dq0, int64_t dq_ps, void* dkv,
+                  int64_t dkv_ps, float* dbias, int B, int H, int T, int Tp, cudaStream_t st);
+int rows_add(void* dst, int64_t d_ps, int64_t dst_row_step, const void* src, int64_t s_ps, int planes, int rows,
+             cudaStream_t st);
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Split {
@@ -24,10 +32,17 @@ struct LayerBufs {
   size_t st1 = 0, st2 = 0;
 };
 
+// Last layer, t = 0 rows only (see attn_row0.cu): compact [B, .] buffers + K|V for every frame.
+struct LastBufs {
+  Split kv, q0, att0, z1, h1, f, z2, hout;
+  size_t st1 = 0, st2 = 0, p0 = 0, pd0 = 0;
+};
+
 struct Plan {
   int B, T, S, P, Tp, H, D, F, C, L;
   int64_t Mt, BH;
-  bool keep;
+  bool keep, prune;
+  LastBufs last;
   Split wpack;
   int64_t w_pre, w_in[SPK_MAX_LAYERS], w_out[SPK_MAX_LAYERS], w_l1[SPK_MAX_LAYERS], w_l2[SPK_MAX_LAYERS];
   Split x0, h0, scr;
@@ -51,6 +66,9 @@ static size_t take_f32(size_t& cur, int64_t elems) {
   return o;
 }
 
+static bool g_prune_last = true;   // spk_set_option("prune_last_layer", 0/1)
+void encoder_set_prune(bool on) { g_prune_last = on; }
+
 static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bool keep, Plan& pl) {
   SPK_CHECK(c.mel_dim == 80 && c.emb == 256 && c.heads == 4 && c.ffn == 1024,
             "encoder: this build supports Mel_Dim 80, Embedding_Size 256, Head 4 (got %d/%d/%d/%d)", c.mel_dim, c.emb,
@@ -65,6 +83,7 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
   pl.Mt = static_cast<int64_t>(B) * T;
   pl.BH = static_cast<int64_t>(B) * pl.H;
   pl.keep = keep;
+  pl.prune = g_prune_last;
   const int64_t D = pl.D, F = pl.F, Mt = pl.Mt;
   size_t cur = 0;
   // packed weights
@@ -82,7 +101,8 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
   pl.pe_t = take_f32(cur, static_cast<int64_t>(T) * D);
   pl.scr = take_split(cur, pl.BH * T * pl.Tp, P);
   const bool drop = keep;   // P_drop is only distinct in training; allocate with the stash
-  for (int l = 0; l < pl.L; ++l) {
+  const int dense_layers = pl.prune ? pl.L - 1 : pl.L;
+  for (int l = 0; l < dense_layers; ++l) {
     if (l > 0 && !keep) { pl.Lb[l] = pl.Lb[0]; continue; }
     LayerBufs& b = pl.Lb[l];
     b.qkv = take_split(cur, Mt * 3 * D, P);
@@ -96,6 +116,21 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
     b.z2 = take_split(cur, Mt * D, P);
     b.st2 = take_f32(cur, Mt * 2);
     b.hout = keep ? take_split(cur, Mt * D, P) : pl.h0;
+  }
+  if (pl.prune) {
+    LastBufs& lb = pl.last;
+    lb.kv = take_split(cur, Mt * 2 * D, P);
+    lb.q0 = take_split(cur, B * D, P);
+    lb.att0 = take_split(cur, B * D, P);
+    lb.z1 = take_split(cur, B * D, P);
+    lb.st1 = take_f32(cur, static_cast<int64_t>(B) * 2);
+    lb.h1 = take_split(cur, B * D, P);
+    lb.f = take_split(cur, B * F, P);
+    lb.z2 = take_split(cur, B * D, P);
+    lb.st2 = take_f32(cur, static_cast<int64_t>(B) * 2);
+    lb.hout = take_split(cur, B * D, P);
+    lb.p0 = take_f32(cur, pl.BH * pl.Tp);
+    lb.pd0 = take_f32(cur, pl.BH * pl.Tp);
   }
   const int64_t Bo = B / S;
   pl.hn = take_f32(cur, static_cast<int64_t>(B) * D);
@@ -137,7 +172,7 @@ int encoder_debug_layout(const spk_encoder_config& c, int B, int T, int S, int P
   };
   put("", -1, "x0", pl.x0.off, pl.x0.ps); put("", -1, "h0", pl.h0.off, pl.h0.ps);
   put("", -1, "scr", pl.scr.off, pl.scr.ps); put("", -1, "pe_t", pl.pe_t, 0);
-  for (int l = 0; l < pl.L; ++l) {
+  for (int l = 0; l < (pl.prune ? pl.L - 1 : pl.L); ++l) {
     const LayerBufs& b = pl.Lb[l];
     put("", l, "qkv", b.qkv.off, b.qkv.ps); put("", l, "p", b.p.off, b.p.ps); put("", l, "att", b.att.off, b.att.ps);
     put("", l, "z1", b.z1.off, b.z1.ps); put("", l, "h1", b.h1.off, b.h1.ps); put("", l, "f", b.f.off, b.f.ps);
@@ -388,7 +423,8 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     c.out(g.epi, pl.h0, 0, D);
     SPK_TRY(gemm_run(g, st));
   }
-  for (int l = 0; l < pl.L; ++l) {
+  const int dense_layers = pl.prune ? pl.L - 1 : pl.L;
+  for (int l = 0; l < dense_layers; ++l) {
     const LayerBufs& b = pl.Lb[l];
     const Split& hin = (l == 0) ? pl.h0 : pl.Lb[l - 1].hout;
     const spk_layer_params& lw = w.layer[l];
@@ -461,9 +497,76 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     }
     SPK_TRY(ln_fwd(c.ptr(b.z2), b.z2.ps, P, 1, lw.norm2_w, lw.norm2_b, c.ptr(b.hout), b.hout.ps, P, c.f32(b.st2), Mt, st));
   }
-  const Split& hl = pl.Lb[pl.L - 1].hout;
+  if (pl.prune) {
+    // ---- last layer: only the t = 0 query row of every slice is consumed (Modules.py:54)
+    const int l = pl.L - 1;
+    const LastBufs& lb = pl.last;
+    const Split& hin = (l == 0) ? pl.h0 : pl.Lb[l - 1].hout;
+    const spk_layer_params& lw = w.layer[l];
+    {  // K | V for every frame
+      GemmProblem g;
+      g.tag = "gemm.last.kv";
+      g.A = c.mat(hin, 0, Mt, D, D);
+      g.B = c.mat(pl.wpack, pl.w_in[l] + D * D, 2 * D, D, D);
+      g.planes = P; g.M = (int)Mt; g.N = (int)(2 * D); g.K = (int)D;
+      g.epi.flags = EPI_BIAS; g.epi.bias = lw.in_proj_b + D;
+      c.out(g.epi, lb.kv, 0, 2 * D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    {  // Q for the first frame of every slice (rows gathered by the row stride T*D)
+      GemmProblem g;
+      g.tag = "gemm.last.q0";
+      g.A = c.mat(hin, 0, B, D, (int64_t)T * D);
+      g.B = c.mat(pl.wpack, pl.w_in[l], D, D, D);
+      g.planes = P; g.M = B; g.N = (int)D; g.K = (int)D;
+      g.epi.flags = EPI_BIAS; g.epi.bias = lw.in_proj_b;
+      c.out(g.epi, lb.q0, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(attn_row0_fwd(c.ptr(lb.q0), lb.q0.ps, c.ptr(lb.kv), lb.kv.ps, P, c.ptr(lb.att0), lb.att0.ps,
+                          keep ? c.f32(lb.p0) : nullptr, keep ? c.f32(lb.pd0) : nullptr, drop, 1 + 4 * l, B, H, T, Tp, st));
+    {  // out-proj + dropout1 + residual (t = 0 rows of the layer input)
+      GemmProblem g;
+      g.tag = "gemm.last.out_proj";
+      g.A = c.mat(lb.att0, 0, B, D, D);
+      g.B = c.mat(pl.wpack, pl.w_out[l], D, D, D);
+      g.planes = P; g.M = B; g.N = (int)D; g.K = (int)D;
+      g.epi.flags = EPI_BIAS | EPI_RES | (drop.thresh ? EPI_DROPOUT : 0);
+      g.epi.bias = lw.out_proj_b; g.epi.drop = drop; g.epi.drop_site = 2 + 4 * l;
+      c.res(g.epi, hin, (int64_t)T * D);
+      c.out(g.epi, lb.z1, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(ln_fwd(c.ptr(lb.z1), lb.z1.ps, P, 1, lw.norm1_w, lw.norm1_b, c.ptr(lb.h1), lb.h1.ps, P, c.f32(lb.st1), B, st));
+    {
+      GemmProblem g;
+      g.tag = "gemm.last.ffn1";
+      g.A = c.mat(lb.h1, 0, B, D, D);
+      g.B = c.mat(pl.wpack, pl.w_l1[l], F, D, D);
+      g.planes = P; g.M = B; g.N = (int)F; g.K = (int)D;
+      g.epi.flags = EPI_BIAS | EPI_RELU | (drop.thresh ? EPI_DROPOUT : 0);
+      g.epi.bias = lw.linear1_b; g.epi.drop = drop; g.epi.drop_site = 3 + 4 * l;
+      c.out(g.epi, lb.f, 0, F);
+      SPK_TRY(gemm_run(g, st));
+    }
+    {
+      GemmProblem g;
+      g.tag = "gemm.last.ffn2";
+      g.A = c.mat(lb.f, 0, B, F, F);
+      g.B = c.mat(pl.wpack, pl.w_l2[l], D, F, F);
+      g.planes = P; g.M = B; g.N = (int)D; g.K = (int)F;
+      g.epi.flags = EPI_BIAS | EPI_RES | (drop.thresh ? EPI_DROPOUT : 0);
+      g.epi.bias = lw.linear2_b; g.epi.drop = drop; g.epi.drop_site = 4 + 4 * l;
+      c.res(g.epi, lb.h1, D);
+      c.out(g.epi, lb.z2, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(ln_fwd(c.ptr(lb.z2), lb.z2.ps, P, 1, lw.norm2_w, lw.norm2_b, c.ptr(lb.hout), lb.hout.ps, P, c.f32(lb.st2), B, st));
+  }
+  const Split& hl = pl.prune ? pl.last.hout : pl.Lb[pl.L - 1].hout;
+  const int head_T = pl.prune ? 1 : T;     // the compact buffer holds one row per slice
   ProfScope prof_head("head_fwd", 2.0 * (B / S) * 256 * 256, 4.0 * B * 256 * 2, st);
-  head_fwd_kernel<<<B / S, 256, 0, st>>>(c.ptr(hl), hl.ps, P, T, S, w.norm_w, w.norm_b, w.proj_w, w.proj_b,
+  head_fwd_kernel<<<B / S, 256, 0, st>>>(c.ptr(hl), hl.ps, P, head_T, S, w.norm_w, w.norm_b, w.proj_w, w.proj_b,
                                          c.f32(pl.hn), reinterpret_cast<float2*>(c.f32(pl.hst)), c.f32(pl.emean),
                                          c.f32(pl.epre), dvec);
   SPK_CUDA(cudaGetLastError());
@@ -484,19 +587,128 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
   const DropCfg drop = make_drop(seed, cfg.dropout, training != 0);
 
   // ---- head
-  const Split& hl = pl.Lb[pl.L - 1].hout;
-  SPK_CUDA(cudaMemsetAsync(c.ptr(pl.dh_a), 0, static_cast<size_t>(pl.dh_a.ps) * P * 2, st));
+  const Split& hl = pl.prune ? pl.last.hout : pl.Lb[pl.L - 1].hout;
+  const int head_T = pl.prune ? 1 : T;
+  // dense: the gradient of the last layer's output is zero except the t = 0 rows; pruned: compact [B, 256] in dh_b
+  const Split& dhead = pl.prune ? pl.dh_b : pl.dh_a;
+  if (!pl.prune) SPK_CUDA(cudaMemsetAsync(c.ptr(pl.dh_a), 0, static_cast<size_t>(pl.dh_a.ps) * P * 2, st));
   {
   ProfScope prof_hb("head_bwd", 4.0 * (B / S) * 256 * 256, 4.0 * B * 256 * 2, st);
   head_bwd_kernel<<<B / S, 256, 0, st>>>(d_dvec, c.f32(pl.epre), w.proj_w, c.ptr(hl), hl.ps, P,
-                                         reinterpret_cast<const float2*>(c.f32(pl.hst)), w.norm_w, T, S, c.f32(pl.de),
-                                         c.ptr(pl.dh_a), pl.dh_a.ps, gr.norm_w, gr.norm_b);
+                                         reinterpret_cast<const float2*>(c.f32(pl.hst)), w.norm_w, head_T, S, c.f32(pl.de),
+                                         c.ptr(dhead), dhead.ps, gr.norm_w, gr.norm_b);
   SPK_CUDA(cudaGetLastError());
   head_wgrad_kernel<<<256, 256, 0, st>>>(c.f32(pl.de), c.f32(pl.emean), B / S, gr.proj_w, gr.proj_b);
   SPK_CUDA(cudaGetLastError());
   }
 
-  for (int l = pl.L - 1; l >= 0; --l) {
+  if (pl.prune) {
+    // ---- last layer on the compact t = 0 rows (buffers dh_b / dz / dzd / df / datt hold B rows here)
+    const int l = pl.L - 1;
+    const LastBufs& lb = pl.last;
+    const Split& hin = (l == 0) ? pl.h0 : pl.Lb[l - 1].hout;
+    const spk_layer_params& lw = w.layer[l];
+    const spk_layer_params& lg = gr.layer[l];
+    const Split& dy = drop.thresh ? pl.dzd : pl.dz;
+    auto small_wgrad = [&](const Split& dyt, int64_t dy_cols, const Split& x, int64_t x_cols, int64_t x_ld, float* dw,
+                           const char* tag) {
+      GemmProblem g;
+      g.tag = tag;
+      g.A = c.mat(dyt, 0, B, dy_cols, dy_cols);
+      g.B = c.mat(x, 0, B, x_cols, x_ld);
+      g.a_mn = true; g.b_mn = true; g.planes = P;
+      g.M = (int)dy_cols; g.N = (int)x_cols; g.K = B;
+      g.ksplit = wgrad_ksplit(B, g.M, g.N);
+      g.epi.flags = EPI_OUT_ATOMIC;
+      g.epi.out = dw; g.epi.out_ld = x_cols;
+      return gemm_run(g, st);
+    };
+    SPK_TRY(ln_bwd(c.ptr(pl.dh_b), pl.dh_b.ps, P, c.ptr(lb.z2), lb.z2.ps, P, c.f32(lb.st2), lw.norm2_w, c.ptr(pl.dz),
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 4 + 4 * l, lg.norm2_w, lg.norm2_b, lg.linear2_b, B, st));
+    SPK_TRY(small_wgrad(dy, D, lb.f, F, F, lg.linear2_w, "gemm.last.bwd.ffn2_wgrad"));
+    {
+      GemmProblem g;
+      g.tag = "gemm.last.bwd.ffn2_dgrad";
+      g.A = c.mat(dy, 0, B, D, D);
+      g.B = c.mat(pl.wpack, pl.w_l2[l], D, F, F);
+      g.b_mn = true;
+      g.planes = P; g.M = B; g.N = (int)F; g.K = (int)D;
+      g.epi.flags = EPI_GATE_POS | EPI_COLSUM;
+      g.epi.colsum = lg.linear1_b;
+      g.epi.gate = c.ptr(lb.f); g.epi.gate_plane_stride = lb.f.ps; g.epi.gate_ld = F; g.epi.gate_planes = 1;
+      g.epi.gate_scale = drop.inv_keep;
+      c.out(g.epi, pl.df, 0, F);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(small_wgrad(pl.df, F, lb.h1, D, D, lg.linear1_w, "gemm.last.bwd.ffn1_wgrad"));
+    {
+      GemmProblem g;
+      g.tag = "gemm.last.bwd.ffn1_dgrad";
+      g.A = c.mat(pl.df, 0, B, F, F);
+      g.B = c.mat(pl.wpack, pl.w_l1[l], F, D, D);
+      g.b_mn = true;
+      g.planes = P; g.M = B; g.N = (int)D; g.K = (int)F;
+      g.epi.flags = EPI_RES;
+      c.res(g.epi, pl.dz, D);
+      c.out(g.epi, pl.dh_b, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(ln_bwd(c.ptr(pl.dh_b), pl.dh_b.ps, P, c.ptr(lb.z1), lb.z1.ps, P, c.f32(lb.st1), lw.norm1_w, c.ptr(pl.dz),
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 2 + 4 * l, lg.norm1_w, lg.norm1_b, lg.out_proj_b, B, st));
+    SPK_TRY(small_wgrad(dy, D, lb.att0, D, D, lg.out_proj_w, "gemm.last.bwd.out_wgrad"));
+    {
+      GemmProblem g;
+      g.tag = "gemm.last.bwd.out_dgrad";
+      g.A = c.mat(dy, 0, B, D, D);
+      g.B = c.mat(pl.wpack, pl.w_out[l], D, D, D);
+      g.b_mn = true;
+      g.planes = P; g.M = B; g.N = (int)D; g.K = (int)D;
+      c.out(g.epi, pl.datt, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    // single-query attention backward: dq0 -> scr (compact), dK | dV -> dqkv viewed as [Mt, 512]
+    SPK_TRY(attn_row0_bwd(c.ptr(pl.datt), pl.datt.ps, P, c.ptr(lb.q0), lb.q0.ps, c.ptr(lb.kv), lb.kv.ps, P_fwd,
+                          c.f32(lb.p0), c.f32(lb.pd0), c.ptr(pl.scr), pl.scr.ps, c.ptr(pl.dqkv), pl.dqkv.ps,
+                          lg.in_proj_b, B, H, T, Tp, st));
+    SPK_TRY(small_wgrad(pl.scr, D, hin, D, (int64_t)T * D, lg.in_proj_w, "gemm.last.bwd.q_wgrad"));
+    {  // dW[K|V rows] = dKV^T hin
+      GemmProblem g;
+      g.tag = "gemm.last.bwd.kv_wgrad";
+      g.A = c.mat(pl.dqkv, 0, Mt, 2 * D, 2 * D);
+      g.B = c.mat(hin, 0, Mt, D, D);
+      g.a_mn = true; g.b_mn = true; g.planes = P;
+      g.M = (int)(2 * D); g.N = (int)D; g.K = (int)Mt;
+      g.ksplit = wgrad_ksplit(Mt, g.M, g.N);
+      g.epi.flags = EPI_OUT_ATOMIC;
+      g.epi.out = lg.in_proj_w + D * D; g.epi.out_ld = D;
+      SPK_TRY(gemm_run(g, st));
+    }
+    {  // dH(in) = dKV W[K|V rows]  for every frame
+      GemmProblem g;
+      g.tag = "gemm.last.bwd.kv_dgrad";
+      g.A = c.mat(pl.dqkv, 0, Mt, 2 * D, 2 * D);
+      g.B = c.mat(pl.wpack, pl.w_in[l] + D * D, 2 * D, D, D);
+      g.b_mn = true;
+      g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)(2 * D);
+      c.out(g.epi, pl.dh_a, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    {  // t = 0 rows additionally receive dq0 Wq and the residual path dZ1
+      GemmProblem g;
+      g.tag = "gemm.last.bwd.q_dgrad";
+      g.A = c.mat(pl.scr, 0, B, D, D);
+      g.B = c.mat(pl.wpack, pl.w_in[l], D, D, D);
+      g.b_mn = true;
+      g.planes = P; g.M = B; g.N = (int)D; g.K = (int)D;
+      g.epi.flags = EPI_RES;
+      c.res(g.epi, pl.dz, D);
+      c.out(g.epi, pl.dh_b, 0, D);
+      SPK_TRY(gemm_run(g, st));
+    }
+    SPK_TRY(rows_add(c.ptr(pl.dh_a), pl.dh_a.ps, T, c.ptr(pl.dh_b), pl.dh_b.ps, P, B, st));
+  }
+
+  for (int l = (pl.prune ? pl.L - 2 : pl.L - 1); l >= 0; --l) {
     const LayerBufs& b = pl.Lb[l];
     const Split& hin = (l == 0) ? pl.h0 : pl.Lb[l - 1].hout;
     const spk_layer_params& lw = w.layer[l];

@@ -13,4 +13,5 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
                      const float* d_dvec, int B, int T, int S, int P, int training, uint64_t seed, void* ws,
                      size_t ws_bytes, cudaStream_t st);
 int encoder_debug_layout(const spk_encoder_config& c, int B, int T, int S, int P, int keep, char* buf, size_t cap);
+void encoder_set_prune(bool on);
 }  // namespace spk

@@ -203,3 +203,30 @@ def test_shape_and_device_errors():
             m(torch.zeros(2, 80, 1025, device="cuda"))
         out = m(torch.zeros(3, 80, 1, device="cuda"))                 # T = 1 edge case
     assert out.shape == (3, 256) and torch.isfinite(out).all()
+
+
+def test_last_layer_pruning_is_exact():
+    """Only the t = 0 query of the last layer is consumed (Modules.py:54): the pruned path (default) and the
+    dense path must give the same d-vectors and gradients, in eval and with the same dropout seed."""
+    from speaker_embedding_torch_b200 import GE2E_Loss, _native
+    mel = torch.as_tensor(synth.make_mel(77, 8, 150)).cuda()
+    results = {}
+    try:
+        for prune in (1, 0):
+            _native.set_option("prune_last_layer", prune)
+            m, _ = _model(21)
+            m.eval()
+            crit = GE2E_Loss().cuda()
+            with torch.no_grad():
+                d_inf = m(mel).clone()
+            d = m(mel)
+            crit(d, 4).backward()
+            torch.cuda.synchronize()
+            results[prune] = (d_inf, d.detach().clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
+    finally:
+        _native.set_option("prune_last_layer", 1)
+    torch.testing.assert_close(results[1][0], results[0][0], atol=2e-3, rtol=0)        # bf16 inference path
+    torch.testing.assert_close(results[1][1], results[0][1], atol=2e-6, rtol=0)        # fp32-equivalent training path
+    num = sum(float(((results[1][2][n] - results[0][2][n]).double() ** 2).sum()) for n in results[0][2])
+    den = sum(float((results[0][2][n].double() ** 2).sum()) for n in results[0][2])
+    assert (num / den) ** 0.5 <= 2e-4
