@@ -324,8 +324,21 @@ def run_native(args):
                                              "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else 0.0,
                                              "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)}
                                          for k, v in sorted(irep.items(), key=lambda kv: -kv[1]["ms"])}
+        # config 3 shape: multi-slice inference, 5 x 64-frame slices per utterance (Inference.py:95-115)
+        utt = 4000
+        mel564 = synth_mel(gen, utt * 5, 64, dev)
+        with torch.no_grad():
+            model(mel564, 5)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                model(mel564, 5)
+            e1.record()
+            torch.cuda.synchronize()
+        ms564 = e0.elapsed_time(e1) / 3
+        del mel564
         model.train()
-        line_extra["extra"] = {"dvectors_per_sec_160f_1gpu": batch / (dv_ms * 1e-3), "infer_ms_per_960x160_batch": dv_ms,
+        line_extra["extra"] = {"multislice_utt_per_sec_5x64_1gpu": utt / (ms564 * 1e-3),"dvectors_per_sec_160f_1gpu": batch / (dv_ms * 1e-3), "infer_ms_per_960x160_batch": dv_ms,
                                "flop_accounting": "F_min (last layer pruned to the t=0 query), bf16 dense count, extra split-plane MMAs not credited",
                                "infer_tensor_frac_of_sustained": batch * min_flops_fwd(160) / (dv_ms * 1e-3) / 1e12 / pk["tf_sus"],
                                "train_tensor_frac_of_sustained": 3 * batch * min_flops_fwd(160) * value / world / 1e12 / pk["tf_sus"],
@@ -361,6 +374,79 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def run_infer(args):
+    """Config 3: batched multi-slice extraction (5 x 64-frame slices, 32 overlap => 192-frame windows per
+    utterance, Inference.py:95-115).  Utterances are independent: rank r embeds its own shard, no collective.
+    A step = one chunk of 4000 utterances per GPU; value = utterances/s over all ranks."""
+    import torch.distributed as dist
+    from speaker_embedding_torch_b200 import GE2E
+    from speaker_embedding_torch_b200.Arg_Parser import default_hyper_parameters
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
+    K, W = max(1, args.steps), max(3, args.warmup)
+    torch.manual_seed(0)
+    model = GE2E(default_hyper_parameters()).to(dev).eval()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    utt, S, F, O = 4000, 5, 64, 32
+    windows = synth_mel(gen, utt, S * (F - O) + O, dev)                      # [utt, 80, 192]
+    # the collater's overlapping slices (stride F - O), utterance-major rows
+    chunk = torch.stack([windows[:, :, i * (F - O):i * (F - O) + F] for i in range(S)], dim=1).reshape(utt * S, MEL, F).contiguous()
+    host = chunk.cpu().pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    with torch.no_grad():
+        for _ in range(W):
+            model(chunk, S)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            e0.record()
+            for _ in range(K):
+                out = model(chunk, S)
+            e1.record()
+            barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        barrier()
+        e0.record()
+        for _ in range(K):
+            o = model(host.to(dev, non_blocking=True), S).cpu()
+        e1.record()
+        barrier()
+        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        pk = peaks()
+        flops = utt * S * min_flops_fwd(F)
+        print(json.dumps({
+            "metric": "utterances/sec, multi-slice d-vector extraction (5 x 64 frames, 32 overlap)",
+            "value": world * K * utt / (ms * 1e-3), "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 operands, fp32 accumulate", "data": "synthetic",
+            "config": {"workload": "multislice_inference_5x64_o32", "utterances_per_step_per_gpu": utt,
+                       "parallelism": "dp%d (utterance shards, no collective)" % world},
+            "clocks": clk.summary(),
+            "e2e": {"value": world * K * utt / (float(t2.item()) * 1e-3), "unit": "utterances/s",
+                    "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": utt * 256 * 4},
+            "extra": {"tensor_frac_of_sustained": flops * K / (ms * 1e-3) / 1e12 / pk["tf_sus"],
+                      "dvec_checksum": float(out.float().sum().item())},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -368,9 +454,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train: GE2E training step (headline, BASELINE config 2/4); infer: multi-slice extraction (config 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "infer":
+        run_infer(args)
     else:
         run_native(args)
 

@@ -128,30 +128,36 @@ ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __rest
     for (int r = 0; r < TR; ++r) dacc[r] = 0.f;
     float dw_part = 0.f, db_part = 0.f;
 
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (int pass = 0; pass < (need_grad ? 2 : 1); ++pass) {
       for (int ct = 0; ct < col_tiles; ++ct) {
         const int c0 = ct * TC;
-        __syncthreads();
-        // centroid tile -> smem (coalesced float4)
-        for (int i = tid; i < TC * (GD / 4); i += 256) {
-          const int cr = i / (GD / 4), c4 = i % (GD / 4);
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c0 + cr < N) v = __ldg(reinterpret_cast<const float4*>(chat + static_cast<int64_t>(c0 + cr) * GD) + c4);
-          *reinterpret_cast<float4*>(&sm.c[cr][c4 * 4]) = v;
-        }
-        __syncthreads();
-        // S tile: 4 dot products of length 256 per thread
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        // N <= 64 (the training configuration): one centroid tile -- the second sweep reuses the tile in shared
+        // memory and the S values still held in registers instead of recomputing them.
+        const bool reuse = (pass == 1 && col_tiles == 1);
+        if (!reuse) {
+          __syncthreads();
+          // centroid tile -> smem (coalesced float4)
+          for (int i = tid; i < TC * (GD / 4); i += 256) {
+            const int cr = i / (GD / 4), c4 = i % (GD / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + cr < N) v = __ldg(reinterpret_cast<const float4*>(chat + static_cast<int64_t>(c0 + cr) * GD) + c4);
+            *reinterpret_cast<float4*>(&sm.c[cr][c4 * 4]) = v;
+          }
+          __syncthreads();
+          // S tile: 4 dot products of length 256 per thread
+          s[0] = s[1] = s[2] = s[3] = 0.f;
 #pragma unroll 4
-        for (int d = 0; d < GD; d += 4) {
-          const float4 ev = *reinterpret_cast<const float4*>(&sm.e[r_loc][d]);
+          for (int d = 0; d < GD; d += 4) {
+            const float4 ev = *reinterpret_cast<const float4*>(&sm.e[r_loc][d]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 cvv = *reinterpret_cast<const float4*>(&sm.c[cgp + 16 * j][d]);
-            s[j] = fmaf(ev.x, cvv.x, s[j]);
-            s[j] = fmaf(ev.y, cvv.y, s[j]);
-            s[j] = fmaf(ev.z, cvv.z, s[j]);
-            s[j] = fmaf(ev.w, cvv.w, s[j]);
+            for (int j = 0; j < 4; ++j) {
+              const float4 cvv = *reinterpret_cast<const float4*>(&sm.c[cgp + 16 * j][d]);
+              s[j] = fmaf(ev.x, cvv.x, s[j]);
+              s[j] = fmaf(ev.y, cvv.y, s[j]);
+              s[j] = fmaf(ev.z, cvv.z, s[j]);
+              s[j] = fmaf(ev.w, cvv.w, s[j]);
+            }
           }
         }
         if (pass == 0) {
