@@ -34,9 +34,9 @@ __device__ __forceinline__ void store2_split(__nv_bfloat16* base, int64_t ps, in
 }
 __device__ __forceinline__ float keep_of(const DropCfg& d, uint32_t site, uint64_t idx) {
   if (d.thresh == 0) return 1.f;
-  float k4[4];
-  dropout_scale4(d.seed, site, idx >> 2, d.thresh, d.inv_keep, k4);
-  return k4[idx & 3];
+  float k8[8];
+  dropout_scale8(d.seed, site, idx >> 3, d.thresh, d.inv_keep, k8);
+  return k8[idx & 7];
 }
 
 // one warp per (slice b, head h); lane owns head dims 2*lane, 2*lane+1

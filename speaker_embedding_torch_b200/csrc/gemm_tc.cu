@@ -242,11 +242,11 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
     if (use_keep) {
       const uint64_t idx = (static_cast<uint64_t>(batch) * M + row) * N + col0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float k4[4];
-        dropout_scale4(e.drop.seed, e.drop_site, (idx >> 2) + q, e.drop.thresh, e.drop.inv_keep, k4);
+      for (int q = 0; q < 4; ++q) {
+        float k8[8];
+        dropout_scale8(e.drop.seed, e.drop_site, (idx >> 3) + q, e.drop.thresh, e.drop.inv_keep, k8);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[q * 4 + i] *= k4[i];
+        for (int i = 0; i < 8; ++i) v[q * 8 + i] *= k8[i];
       }
     }
   }
@@ -262,11 +262,11 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
       if (use_keep) {
         const uint64_t idx = (static_cast<uint64_t>(batch) * M + row) * N + col0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float k4[4];
-          dropout_scale4(e.drop.seed, e.drop_site, (idx >> 2) + q, e.drop.thresh, e.drop.inv_keep, k4);
+        for (int q = 0; q < 4; ++q) {
+          float k8[8];
+          dropout_scale8(e.drop.seed, e.drop_site, (idx >> 3) + q, e.drop.thresh, e.drop.inv_keep, k8);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[q * 4 + i] *= k4[i];
+          for (int i = 0; i < 8; ++i) v[q * 8 + i] *= k8[i];
         }
       }
     }

@@ -159,12 +159,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
     for (int i = 0; i < 8; ++i) o[i] = ms.y * (d[i] - s1 - x[i] * s2);
     store8_split(dz, dz_ps, dz_planes, r * 256 + lane * 8, o);
     if (dz_drop != nullptr) {
-      float k0[4], k1[4];
+      float k8[8];
       const uint64_t idx = static_cast<uint64_t>(r) * 256 + lane * 8;
-      dropout_scale4(drop.seed, site, idx >> 2, drop.thresh, drop.inv_keep, k0);
-      dropout_scale4(drop.seed, site, (idx >> 2) + 1, drop.thresh, drop.inv_keep, k1);
+      dropout_scale8(drop.seed, site, idx >> 3, drop.thresh, drop.inv_keep, k8);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { o[i] *= k0[i]; o[4 + i] *= k1[i]; }
+      for (int i = 0; i < 8; ++i) o[i] *= k8[i];
       store8_split(dz_drop, dz_ps, dz_planes, r * 256 + lane * 8, o);
     }
     // o is now the gradient of the sub-layer output (dz, or dz * keep): its column sum is that layer's bias grad
@@ -242,12 +241,11 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
         for (int i = 0; i < 8; ++i) v[c][i] *= inv;
         store8_split(p, ps, planes, r * Tp + col, v[c]);
         if (p_drop != nullptr) {
-          float k0[4], k1[4];
+          float k8[8];
           const uint64_t idx = static_cast<uint64_t>(r) * Tp + col;
-          dropout_scale4(drop.seed, site, idx >> 2, drop.thresh, drop.inv_keep, k0);
-          dropout_scale4(drop.seed, site, (idx >> 2) + 1, drop.thresh, drop.inv_keep, k1);
+          dropout_scale8(drop.seed, site, idx >> 3, drop.thresh, drop.inv_keep, k8);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { v[c][i] *= k0[i]; v[c][4 + i] *= k1[i]; }
+          for (int i = 0; i < 8; ++i) v[c][i] *= k8[i];
           store8_split(p_drop, ps, planes, r * Tp + col, v[c]);
         }
       }
@@ -293,12 +291,11 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
         load8_split(p, ps, planes, r * Tp + col, pv[c]);
         load8_split(dp, ps, planes, r * Tp + col, dv[c]);
         if (drop.thresh != 0) {
-          float k0[4], k1[4];
+          float k8[8];
           const uint64_t idx = static_cast<uint64_t>(r) * Tp + col;
-          dropout_scale4(drop.seed, site, idx >> 2, drop.thresh, drop.inv_keep, k0);
-          dropout_scale4(drop.seed, site, (idx >> 2) + 1, drop.thresh, drop.inv_keep, k1);
+          dropout_scale8(drop.seed, site, idx >> 3, drop.thresh, drop.inv_keep, k8);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { dv[c][i] *= k0[i]; dv[c][4 + i] *= k1[i]; }
+          for (int i = 0; i < 8; ++i) dv[c][i] *= k8[i];
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -382,12 +379,11 @@ __global__ void __launch_bounds__(256) pe_alpha_grad_kernel(const __nv_bfloat16*
     float d[8];
     load8_split(dh, ps, planes, r * 256 + lane * 8, d);
     if (drop.thresh != 0) {
-      float k0[4], k1[4];
+      float k8[8];
       const uint64_t idx = static_cast<uint64_t>(r) * 256 + lane * 8;
-      dropout_scale4(drop.seed, site, idx >> 2, drop.thresh, drop.inv_keep, k0);
-      dropout_scale4(drop.seed, site, (idx >> 2) + 1, drop.thresh, drop.inv_keep, k1);
+      dropout_scale8(drop.seed, site, idx >> 3, drop.thresh, drop.inv_keep, k8);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { d[i] *= k0[i]; d[4 + i] *= k1[i]; }
+      for (int i = 0; i < 8; ++i) d[i] *= k8[i];
     }
     const float* pr = pe_t + (r % T) * 256 + lane * 8;
 #pragma unroll
