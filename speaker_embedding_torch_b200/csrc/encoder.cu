@@ -49,7 +49,7 @@ struct Plan {
   size_t pe_t;
   LayerBufs Lb[SPK_MAX_LAYERS];
   size_t hn, hst, emean, epre, de;
-  Split dh_a, dh_b, dz, dzd, df, datt, dqkv;
+  Split dh_a, dh_b, dz, dzd, df, datt, dqkv, ds;
   size_t total;
 };
 
@@ -99,7 +99,7 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
   pl.x0 = take_split(cur, Mt * pl.C, P);
   pl.h0 = take_split(cur, Mt * D, P);
   pl.pe_t = take_f32(cur, static_cast<int64_t>(T) * D);
-  pl.scr = take_split(cur, pl.BH * T * pl.Tp, P);
+  pl.scr = take_split(cur, pl.BH * T * pl.Tp, P < 2 ? 2 : P);   // also holds fp32 scores / dP (4 B per element)
   const bool drop = keep;   // P_drop is only distinct in training; allocate with the stash
   const int dense_layers = pl.prune ? pl.L - 1 : pl.L;
   for (int l = 0; l < dense_layers; ++l) {
@@ -147,6 +147,7 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
     pl.df = take_split(cur, Mt * F, Pb);
     pl.datt = take_split(cur, Mt * D, Pb);
     pl.dqkv = take_split(cur, Mt * 3 * D, Pb);
+    pl.ds = take_split(cur, pl.BH * T * pl.Tp, Pb);
   }
   pl.total = cur + 1024;
   return 0;
@@ -184,7 +185,7 @@ int encoder_debug_layout(const spk_encoder_config& c, int B, int T, int S, int P
     put("", -1, "dh_a", pl.dh_a.off, pl.dh_a.ps); put("", -1, "dh_b", pl.dh_b.off, pl.dh_b.ps);
     put("", -1, "dz", pl.dz.off, pl.dz.ps); put("", -1, "dzd", pl.dzd.off, pl.dzd.ps);
     put("", -1, "df", pl.df.off, pl.df.ps); put("", -1, "datt", pl.datt.off, pl.datt.ps);
-    put("", -1, "dqkv", pl.dqkv.off, pl.dqkv.ps);
+    put("", -1, "dqkv", pl.dqkv.off, pl.dqkv.ps); put("", -1, "ds", pl.ds.off, pl.ds.ps);
   }
   return static_cast<int>(off);
 }
@@ -446,9 +447,11 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       g.planes = P; g.M = T; g.N = Tp; g.K = 64; g.nb0 = H; g.nb1 = B;
       g.epi.alpha = 0.125f;
       c.out(g.epi, pl.scr, 0, Tp, (int64_t)T * Tp, (int64_t)H * T * Tp);
+      if (P >= 2) g.epi.flags |= EPI_OUT_F32;   // multi-plane modes keep the scores in fp32 (cheaper epilogue, 4 B instead of 2P B)
       SPK_TRY(gemm_run(g, st));
     }
-    SPK_TRY(softmax_fwd(c.ptr(pl.scr), pl.scr.ps, P, c.ptr(b.p), c.ptr(b.pd), drop, 1 + 4 * l, pl.BH * T, T, Tp, st));
+    SPK_TRY(softmax_fwd(c.ptr(pl.scr), P >= 2 ? reinterpret_cast<const float*>(c.ptr(pl.scr)) : nullptr, pl.scr.ps, P,
+                        c.ptr(b.p), c.ptr(b.pd), drop, 1 + 4 * l, pl.BH * T, T, Tp, st));
     {  // O = P V, heads written back interleaved into [tokens, 256]
       GemmProblem g;
       g.tag = "gemm.attn_pv";
@@ -783,14 +786,15 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.B = c.mat(b.qkv, 2 * D, T, 64, 3 * D, sQ0, sQ1);
       g.planes = P; g.M = T; g.N = Tp; g.K = 64; g.nb0 = H; g.nb1 = B;
       c.out(g.epi, pl.scr, 0, Tp, sP0, sP1);
+      if (P >= 2) g.epi.flags |= EPI_OUT_F32;
       SPK_TRY(gemm_run(g, st));
     }
-    SPK_TRY(softmax_bwd(c.ptr(b.p), c.ptr(pl.scr), pl.scr.ps, P, c.ptr(pl.scr), drop, 1 + 4 * l, 0.125f, pl.BH * T, T,
-                        Tp, st));
+    SPK_TRY(softmax_bwd(c.ptr(b.p), c.ptr(pl.scr), P >= 2 ? reinterpret_cast<const float*>(c.ptr(pl.scr)) : nullptr,
+                        b.p.ps, P, c.ptr(pl.ds), drop, 1 + 4 * l, 0.125f, pl.BH * T, T, Tp, st));
     {  // dQ = dS K
       GemmProblem g;
       g.tag = "gemm.bwd.attn_dq";
-      g.A = c.mat(pl.scr, 0, T, T, Tp, sP0, sP1);
+      g.A = c.mat(pl.ds, 0, T, T, Tp, sP0, sP1);
       g.B = c.mat(b.qkv, D, T, 64, 3 * D, sQ0, sQ1);
       g.b_mn = true;
       g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
@@ -801,7 +805,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     {  // dK = dS^T Q
       GemmProblem g;
       g.tag = "gemm.bwd.attn_dk";
-      g.A = c.mat(pl.scr, 0, T, T, Tp, sP0, sP1);
+      g.A = c.mat(pl.ds, 0, T, T, Tp, sP0, sP1);
       g.B = c.mat(b.qkv, 0, T, 64, 3 * D, sQ0, sQ1);
       g.a_mn = true; g.b_mn = true;
       g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;

@@ -285,9 +285,12 @@ ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __rest
   }
 }
 
-size_t ge2e_workspace_bytes(int N, int M) {
+static size_t ge2e_simt_workspace_bytes(int N, int M) {
   const size_t NM = static_cast<size_t>(N) * M;
   return (2 * static_cast<size_t>(N) * GD + N + NM) * sizeof(float) + 256;
+}
+size_t ge2e_workspace_bytes(int N, int M) {
+  return N >= GE2E_TC_MIN_SPEAKERS ? ge2e_tc_workspace_bytes(N, M) : ge2e_simt_workspace_bytes(N, M);
 }
 
 int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float* b, float* loss, float* dE, float* dw,
@@ -295,8 +298,10 @@ int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float*
   SPK_CHECK(D == GD, "ge2e: embedding size %d not supported by this build (256)", D);
   SPK_CHECK(N >= 1 && M >= 1, "ge2e: need at least one speaker and one utterance");
   SPK_CHECK((reinterpret_cast<uintptr_t>(E) & 15) == 0, "ge2e: embeddings must be 16-byte aligned");
-  if (ws_bytes < ge2e_workspace_bytes(N, M)) {
-    set_error("ge2e: workspace too small (%zu < %zu)", ws_bytes, ge2e_workspace_bytes(N, M));
+  if (N >= GE2E_TC_MIN_SPEAKERS)   // intensity 0.75 N FLOP/B: tensor-core composition (ge2e_tc.cu)
+    return ge2e_tc(E, N, M, w, b, loss, dE, dw, db, ws, ws_bytes, st);
+  if (ws_bytes < ge2e_simt_workspace_bytes(N, M)) {
+    set_error("ge2e: workspace too small (%zu < %zu)", ws_bytes, ge2e_simt_workspace_bytes(N, M));
     return SPK_ENOMEM;
   }
   const int need_grad = (dE != nullptr);

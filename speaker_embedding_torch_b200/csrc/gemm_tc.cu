@@ -154,11 +154,44 @@ __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void*
   }
 }
 
-// fp32 tile (plain store or atomic add), coalesced through a 32 x 17 fp32 staging tile, 16 columns at a time:
+// fp32 tile, plain store: a 16-column half of the 32 x 32 chunk is 32 rows x 64 B -- the same geometry as one bf16
+// plane -- so it goes through the same swizzled staging tile with 16-byte shared / global accesses.
+__device__ __forceinline__ void store_f32_tile_plain(uint32_t stage, int lane, float* base, int64_t ld, int64_t boff,
+                                                     int64_t row0, int col0, int M, int N, const float (&v)[32]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(lane, cc)),
+                   "r"(__float_as_uint(v[h * 16 + cc * 4])), "r"(__float_as_uint(v[h * 16 + cc * 4 + 1])),
+                   "r"(__float_as_uint(v[h * 16 + cc * 4 + 2])), "r"(__float_as_uint(v[h * 16 + cc * 4 + 3]))
+                   : "memory");
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2), cc = lane & 3;
+      const int64_t grow = row0 + rr;
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                   : "r"(stage + stage_off(rr, cc))
+                   : "memory");
+      const int col = col0 + h * 16 + cc * 4;
+      if (grow < M && col < N) *reinterpret_cast<uint4*>(base + boff + grow * ld + col) = make_uint4(w0, w1, w2, w3);
+    }
+    __syncwarp();
+  }
+}
+
+// fp32 tile, atomic add (split-K weight gradients), through a 32 x 17 fp32 staging tile, 16 columns at a time:
 // each instruction covers 2 rows x 64 contiguous bytes.
 template <bool ATOMIC>
 __device__ __forceinline__ void store_f32_tile(uint32_t stage, int lane, float* base, int64_t ld, int64_t boff,
                                                int64_t row0, int col0, int M, int N, const float (&v)[32]) {
+  if (!ATOMIC && (ld & 3) == 0 && (N & 3) == 0) {   // 16-byte aligned rows: vector path
+    store_f32_tile_plain(stage, lane, base, ld, boff, row0, col0, M, N, v);
+    return;
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
 #pragma unroll

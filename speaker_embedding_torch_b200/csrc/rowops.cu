@@ -201,7 +201,8 @@ int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t 
 // Row softmax over the first T of Tp columns (Tp % 8 == 0, Tp <= 1024); one warp per row.
 // Writes P (and P_drop = P * keep / (1-p) when dropout is on); pad columns are written as zeros.
 template <int CH>
-__global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* __restrict__ s, int64_t ps, int planes,
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* __restrict__ s,
+                                                          const float* __restrict__ s_f32, int64_t ps, int planes,
                                                           __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ p_drop,
                                                           DropCfg drop, uint32_t site, int64_t rows, int T, int Tp) {
   const int lane = threadIdx.x & 31;
@@ -214,7 +215,14 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
     for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < Tp) {
-        load8_split(s, ps, planes, r * Tp + col, v[c]);
+        if (s_f32 != nullptr) {
+          const float4 a0 = *reinterpret_cast<const float4*>(s_f32 + r * Tp + col);
+          const float4 a1 = *reinterpret_cast<const float4*>(s_f32 + r * Tp + col + 4);
+          v[c][0] = a0.x; v[c][1] = a0.y; v[c][2] = a0.z; v[c][3] = a0.w;
+          v[c][4] = a1.x; v[c][5] = a1.y; v[c][6] = a1.z; v[c][7] = a1.w;
+        } else {
+          load8_split(s, ps, planes, r * Tp + col, v[c]);
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (col + i >= T) v[c][i] = -INFINITY;
@@ -252,9 +260,9 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
     }
   }
 }
-int softmax_fwd(const void* s, int64_t ps, int planes, void* p, void* p_drop, DropCfg drop, uint32_t site,
-                int64_t rows, int T, int Tp, cudaStream_t st) {
-  ProfScope prof("softmax_fwd", 0, 2.0 * rows * Tp * planes * (drop.thresh ? 3 : 2), st);
+int softmax_fwd(const void* s, const float* s_f32, int64_t ps, int planes, void* p, void* p_drop, DropCfg drop,
+                uint32_t site, int64_t rows, int T, int Tp, cudaStream_t st) {
+  ProfScope prof("softmax_fwd", 0, 2.0 * rows * Tp * planes * (drop.thresh ? 2 : 1) + rows * Tp * (s_f32 ? 4.0 : 2.0 * planes), st);
   SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
   const int ch = (Tp + 255) / 256;
@@ -262,10 +270,10 @@ int softmax_fwd(const void* s, int64_t ps, int planes, void* p, void* p_drop, Dr
   auto* pp = reinterpret_cast<__nv_bfloat16*>(p);
   auto* pdp = drop.thresh != 0 ? reinterpret_cast<__nv_bfloat16*>(p_drop) : nullptr;
   switch (ch) {
-    case 1: softmax_fwd_kernel<1><<<blocks, 256, 0, st>>>(sp, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
-    case 2: softmax_fwd_kernel<2><<<blocks, 256, 0, st>>>(sp, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
-    case 3: softmax_fwd_kernel<3><<<blocks, 256, 0, st>>>(sp, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
-    default: softmax_fwd_kernel<4><<<blocks, 256, 0, st>>>(sp, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
+    case 1: softmax_fwd_kernel<1><<<blocks, 256, 0, st>>>(sp, s_f32, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
+    case 2: softmax_fwd_kernel<2><<<blocks, 256, 0, st>>>(sp, s_f32, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
+    case 3: softmax_fwd_kernel<3><<<blocks, 256, 0, st>>>(sp, s_f32, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
+    default: softmax_fwd_kernel<4><<<blocks, 256, 0, st>>>(sp, s_f32, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
   }
   SPK_CUDA(cudaGetLastError());
   return 0;
@@ -275,8 +283,8 @@ int softmax_fwd(const void* s, int64_t ps, int planes, void* p, void* p_drop, Dr
 // dp and ds may alias (in-place): a warp reads its whole row before writing it, so no __restrict__ here.
 template <int CH>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p,
-                                                          const __nv_bfloat16* dp, int64_t ps, int planes,
-                                                          __nv_bfloat16* ds, DropCfg drop, uint32_t site,
+                                                          const __nv_bfloat16* dp, const float* dp_f32, int64_t ps,
+                                                          int planes, __nv_bfloat16* ds, DropCfg drop, uint32_t site,
                                                           float scale, int64_t rows, int T, int Tp) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -289,7 +297,14 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
       const int col = c * 256 + lane * 8;
       if (col < Tp) {
         load8_split(p, ps, planes, r * Tp + col, pv[c]);
-        load8_split(dp, ps, planes, r * Tp + col, dv[c]);
+        if (dp_f32 != nullptr) {
+          const float4 a0 = *reinterpret_cast<const float4*>(dp_f32 + r * Tp + col);
+          const float4 a1 = *reinterpret_cast<const float4*>(dp_f32 + r * Tp + col + 4);
+          dv[c][0] = a0.x; dv[c][1] = a0.y; dv[c][2] = a0.z; dv[c][3] = a0.w;
+          dv[c][4] = a1.x; dv[c][5] = a1.y; dv[c][6] = a1.z; dv[c][7] = a1.w;
+        } else {
+          load8_split(dp, ps, planes, r * Tp + col, dv[c]);
+        }
         if (drop.thresh != 0) {
           float k8[8];
           const uint64_t idx = static_cast<uint64_t>(r) * Tp + col;
@@ -317,8 +332,8 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
     }
   }
 }
-int softmax_bwd(const void* p, const void* dp, int64_t ps, int planes, void* ds, DropCfg drop, uint32_t site,
-                float scale, int64_t rows, int T, int Tp, cudaStream_t st) {
+int softmax_bwd(const void* p, const void* dp, const float* dp_f32, int64_t ps, int planes, void* ds, DropCfg drop,
+                uint32_t site, float scale, int64_t rows, int T, int Tp, cudaStream_t st) {
   ProfScope prof("softmax_bwd", 0, 2.0 * rows * Tp * planes * 3, st);
   SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
@@ -327,10 +342,10 @@ int softmax_bwd(const void* p, const void* dp, int64_t ps, int planes, void* ds,
   auto* dpp = reinterpret_cast<const __nv_bfloat16*>(dp);
   auto* dsp = reinterpret_cast<__nv_bfloat16*>(ds);
   switch (ch) {
-    case 1: softmax_bwd_kernel<1><<<blocks, 256, 0, st>>>(pp, dpp, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
-    case 2: softmax_bwd_kernel<2><<<blocks, 256, 0, st>>>(pp, dpp, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
-    case 3: softmax_bwd_kernel<3><<<blocks, 256, 0, st>>>(pp, dpp, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
-    default: softmax_bwd_kernel<4><<<blocks, 256, 0, st>>>(pp, dpp, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
+    case 1: softmax_bwd_kernel<1><<<blocks, 256, 0, st>>>(pp, dpp, dp_f32, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
+    case 2: softmax_bwd_kernel<2><<<blocks, 256, 0, st>>>(pp, dpp, dp_f32, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
+    case 3: softmax_bwd_kernel<3><<<blocks, 256, 0, st>>>(pp, dpp, dp_f32, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
+    default: softmax_bwd_kernel<4><<<blocks, 256, 0, st>>>(pp, dpp, dp_f32, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
   }
   SPK_CUDA(cudaGetLastError());
   return 0;

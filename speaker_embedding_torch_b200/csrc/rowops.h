@@ -26,10 +26,11 @@ int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t 
            const float* gamma, void* dz, int64_t dz_ps, int dz_planes, void* dz_drop, DropCfg drop, uint32_t site,
            float* dgamma, float* dbeta, float* dbias, int64_t rows, cudaStream_t st);
 
-int softmax_fwd(const void* s, int64_t ps, int planes, void* p, void* p_drop, DropCfg drop, uint32_t site,
-                int64_t rows, int T, int Tp, cudaStream_t st);
-int softmax_bwd(const void* p, const void* dp, int64_t ps, int planes, void* ds, DropCfg drop, uint32_t site,
-                float scale, int64_t rows, int T, int Tp, cudaStream_t st);
+// scores / dP come either as split planes (s / dp) or as plain fp32 (s_f32 / dp_f32 != nullptr)
+int softmax_fwd(const void* s, const float* s_f32, int64_t ps, int planes, void* p, void* p_drop, DropCfg drop,
+                uint32_t site, int64_t rows, int T, int Tp, cudaStream_t st);
+int softmax_bwd(const void* p, const void* dp, const float* dp_f32, int64_t ps, int planes, void* ds, DropCfg drop,
+                uint32_t site, float scale, int64_t rows, int T, int Tp, cudaStream_t st);
 
 int colsum(const void* x, int64_t ps, int planes, float* out, int64_t rows, int C, cudaStream_t st);
 int pe_alpha_grad(const void* dh, int64_t ps, int planes, const float* pe_t, DropCfg drop, uint32_t site, float* dalpha,

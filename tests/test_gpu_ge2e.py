@@ -41,7 +41,7 @@ def test_matches_reference_golden(golden_dir):
         assert abs(l2 - loss) <= 1e-6 * max(1.0, abs(loss))
 
 
-@pytest.mark.parametrize("n,m", [(1, 4), (2, 1), (3, 7), (130, 2), (512, 15), (1024, 15)])
+@pytest.mark.parametrize("n,m", [(1, 4), (2, 1), (3, 7), (130, 2), (255, 3), (256, 3), (261, 5), (512, 15), (1024, 15)])
 def test_closed_form_sizes(n, m):
     """Sizes the reference cannot hold in memory are checked against the fp64 closed form (App. B)."""
     E = synth.make_embeddings(900 + n, n, m, unit_norm=(n % 2 == 0))

@@ -214,7 +214,7 @@ def enc_stage_case(Nspk, M, T, layers=1, precision=3):
         return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
 
     def rd(name, rows, cols):
-        bwd = name in ("dh_a", "dh_b", "dz", "dzd", "df", "datt", "dqkv", "scr")
+        bwd = name in ("dh_a", "dh_b", "dz", "dzd", "df", "datt", "dqkv", "scr", "ds")
         return N.read_split(ws, lay, name, rows, cols, min(precision, 2) if bwd else precision)
     print("loss %.7f ref %.7f" % (loss.item(), lref.item()))
     pre = "L%d." % l
@@ -226,7 +226,7 @@ def enc_stage_case(Nspk, M, T, layers=1, precision=3):
     pmine = rd(pre + "p", B * H * T, Tp).view(B, H, T, Tp)[..., :T]
     print("fwd  p %.2e" % rel(pmine, inter["p%d" % l]))
     # backward buffers hold the values of the LAST processed layer (layer 0)
-    ds_mine = rd("scr", B * H * T, Tp).view(B, H, T, Tp)[..., :T]
+    ds_mine = rd("ds", B * H * T, Tp).view(B, H, T, Tp)[..., :T]
     print("bwd(layer0) dS %.2e dqkv %.2e datt %.2e dZ1 %.2e dU %.2e dH0 %.2e du0 %.2e" % (
         rel(ds_mine, inter["sraw0"].grad), rel(rd("dqkv", Mt, 3 * D), inter["qkv0"].grad),
         rel(rd("datt", Mt, D), inter["att0"].grad), rel(rd("dz", Mt, D), inter["z10"].grad),
