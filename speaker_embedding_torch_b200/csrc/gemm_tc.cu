@@ -65,64 +65,84 @@ __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
+// Per-tile, per-lane addressing of the cooperative "8 rows x 64 B per instruction" pattern: lane (lane>>2, lane&3)
+// touches row row0 + it*8 + (lane>>2), 16-byte chunk (lane&3), it = 0..3.  Computed once per tile so the
+// per-chunk code has no 64-bit multiplies (ncu r01: address arithmetic was > 50 % of the epilogue's instructions).
+struct CoopIO {
+  int64_t off0;      // element offset of (row0 + (lane>>2), chunk (lane&3)) including the batch offset
+  int64_t ld8;       // 8 rows further down
+  uint32_t rowmask;  // bit it: row0 + it*8 + (lane>>2) < M
+};
+__device__ __forceinline__ CoopIO make_coop(int lane, int64_t boff, int64_t row0, int64_t ld, int M, int elems_per_chunk) {
+  CoopIO io;
+  const int64_t r = row0 + (lane >> 2);
+  io.off0 = boff + r * ld + (lane & 3) * elems_per_chunk;
+  io.ld8 = 8 * ld;
+  io.rowmask = (r < M ? 1u : 0u) | (r + 8 < M ? 2u : 0u) | (r + 16 < M ? 4u : 0u) | (r + 24 < M ? 8u : 0u);
+  return io;
+}
+
 // r[32] = aux[row0 + lane][col0 .. col0+31]  (split tensor, rows >= M / cols >= N read as 0).
 // All planes' global loads are issued before the first wait so up to 12 x 16 B per lane are in flight.
 __device__ __forceinline__ void load_aux_tile(uint32_t stage, int lane, const void* base_v, int64_t ps, int planes,
-                                              int64_t ld, int64_t boff, int64_t row0, int col0, int M, int N,
-                                              float (&r)[32]) {
-  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(base_v);
-  uint4 g[3][4];
-#pragma unroll
-  for (int p = 0; p < 3; ++p) {
-    if (p < planes) {
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int rr = it * 8 + (lane >> 2), cc = lane & 3;
-        const int64_t grow = row0 + rr;
-        g[p][it] = make_uint4(0u, 0u, 0u, 0u);
-        if (grow < M && col0 + cc * 8 < N)
-          g[p][it] = __ldg(reinterpret_cast<const uint4*>(base + p * ps + boff + grow * ld + col0 + cc * 8));
-      }
-    }
-  }
+                                              const CoopIO& io, int col0, int N, float (&r)[32]) {
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(base_v) + io.off0 + col0;
+  const bool col_ok = col0 + (lane & 3) * 8 < N;
 #pragma unroll
   for (int i = 0; i < 32; ++i) r[i] = 0.f;
 #pragma unroll
-  for (int p = 0; p < 3; ++p) {
-    if (p < planes) {
+  for (int p0 = 0; p0 < 3; p0 += 2) {      // two planes (8 x 16 B per lane) in flight at a time
+    if (p0 < planes) {
+      uint4 g[2][4];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int rr = it * 8 + (lane >> 2), cc = lane & 3;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(rr, cc)), "r"(g[p][it].x),
-                     "r"(g[p][it].y), "r"(g[p][it].z), "r"(g[p][it].w)
-                     : "memory");
-      }
-      __syncwarp();
+      for (int q = 0; q < 2; ++q) {
+        if (p0 + q < planes && p0 + q < 3) {
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t w0, w1, w2, w3;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                     : "r"(stage + stage_off(lane, cc))
-                     : "memory");
-        const uint32_t ww[4] = {w0, w1, w2, w3};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          r[cc * 8 + 2 * i] += bf16lo_to_f(ww[i]);
-          r[cc * 8 + 2 * i + 1] += bf16hi_to_f(ww[i]);
+          for (int it = 0; it < 4; ++it) {
+            g[q][it] = make_uint4(0u, 0u, 0u, 0u);
+            if (col_ok && ((io.rowmask >> it) & 1u))
+              g[q][it] = __ldg(reinterpret_cast<const uint4*>(base + (p0 + q) * ps + it * io.ld8));
+          }
         }
       }
-      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (p0 + q < planes && p0 + q < 3) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(it * 8 + (lane >> 2), lane & 3)),
+                         "r"(g[q][it].x), "r"(g[q][it].y), "r"(g[q][it].z), "r"(g[q][it].w)
+                         : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(stage + stage_off(lane, cc))
+                         : "memory");
+            const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              r[cc * 8 + 2 * i] += bf16lo_to_f(ww[i]);
+              r[cc * 8 + 2 * i + 1] += bf16hi_to_f(ww[i]);
+            }
+          }
+          __syncwarp();
+        }
+      }
     }
   }
 }
 
 // out[row0 + lane][col0 .. col0+31] = v (split planes), coalesced through the staging tile
 __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void* base_v, int64_t ps, int planes,
-                                                 int64_t ld, int64_t boff, int64_t row0, int col0, int M, int N,
-                                                 float (&v)[32]) {
-  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(base_v);
+                                                 const CoopIO& io, int col0, int N, float (&v)[32]) {
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(base_v) + io.off0 + col0;
+  const bool col_ok = col0 + (lane & 3) * 8 < N;
   for (int p = 0; p < planes; ++p) {
+    const bool more = p + 1 < planes;   // the residual is only needed if another plane follows
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
       uint32_t w[4];
@@ -130,8 +150,10 @@ __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void*
       for (int i = 0; i < 4; ++i) {
         __nv_bfloat162 q = __floats2bfloat162_rn(v[cc * 8 + 2 * i], v[cc * 8 + 2 * i + 1]);
         w[i] = *reinterpret_cast<uint32_t*>(&q);
-        v[cc * 8 + 2 * i] -= __bfloat162float(q.x);
-        v[cc * 8 + 2 * i + 1] -= __bfloat162float(q.y);
+        if (more) {
+          v[cc * 8 + 2 * i] -= bf16lo_to_f(w[i]);
+          v[cc * 8 + 2 * i + 1] -= bf16hi_to_f(w[i]);
+        }
       }
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(lane, cc)), "r"(w[0]),
                    "r"(w[1]), "r"(w[2]), "r"(w[3])
@@ -140,15 +162,13 @@ __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void*
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + (lane >> 2), cc = lane & 3;
-      const int64_t grow = row0 + rr;
       uint32_t w0, w1, w2, w3;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                   : "r"(stage + stage_off(rr, cc))
+                   : "r"(stage + stage_off(it * 8 + (lane >> 2), lane & 3))
                    : "memory");
-      if (grow < M && col0 + cc * 8 < N)
-        *reinterpret_cast<uint4*>(base + p * ps + boff + grow * ld + col0 + cc * 8) = make_uint4(w0, w1, w2, w3);
+      if (col_ok && ((io.rowmask >> it) & 1u))
+        *reinterpret_cast<uint4*>(base + p * ps + it * io.ld8) = make_uint4(w0, w1, w2, w3);
     }
     __syncwarp();
   }
@@ -156,8 +176,10 @@ __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void*
 
 // fp32 tile, plain store: a 16-column half of the 32 x 32 chunk is 32 rows x 64 B -- the same geometry as one bf16
 // plane -- so it goes through the same swizzled staging tile with 16-byte shared / global accesses.
-__device__ __forceinline__ void store_f32_tile_plain(uint32_t stage, int lane, float* base, int64_t ld, int64_t boff,
-                                                     int64_t row0, int col0, int M, int N, const float (&v)[32]) {
+// `io` is built with 4 elements per chunk.
+__device__ __forceinline__ void store_f32_tile_plain(uint32_t stage, int lane, float* base_f, const CoopIO& io, int col0,
+                                                     int N, const float (&v)[32]) {
+  float* base = base_f + io.off0 + col0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -167,17 +189,16 @@ __device__ __forceinline__ void store_f32_tile_plain(uint32_t stage, int lane, f
                    "r"(__float_as_uint(v[h * 16 + cc * 4 + 2])), "r"(__float_as_uint(v[h * 16 + cc * 4 + 3]))
                    : "memory");
     __syncwarp();
+    const bool col_ok = col0 + h * 16 + (lane & 3) * 4 < N;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + (lane >> 2), cc = lane & 3;
-      const int64_t grow = row0 + rr;
       uint32_t w0, w1, w2, w3;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                   : "r"(stage + stage_off(rr, cc))
+                   : "r"(stage + stage_off(it * 8 + (lane >> 2), lane & 3))
                    : "memory");
-      const int col = col0 + h * 16 + cc * 4;
-      if (grow < M && col < N) *reinterpret_cast<uint4*>(base + boff + grow * ld + col) = make_uint4(w0, w1, w2, w3);
+      if (col_ok && ((io.rowmask >> it) & 1u))
+        *reinterpret_cast<uint4*>(base + h * 16 + it * io.ld8) = make_uint4(w0, w1, w2, w3);
     }
     __syncwarp();
   }
@@ -188,10 +209,6 @@ __device__ __forceinline__ void store_f32_tile_plain(uint32_t stage, int lane, f
 template <bool ATOMIC>
 __device__ __forceinline__ void store_f32_tile(uint32_t stage, int lane, float* base, int64_t ld, int64_t boff,
                                                int64_t row0, int col0, int M, int N, const float (&v)[32]) {
-  if (!ATOMIC && (ld & 3) == 0 && (N & 3) == 0) {   // 16-byte aligned rows: vector path
-    store_f32_tile_plain(stage, lane, base, ld, boff, row0, col0, M, N, v);
-    return;
-  }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -239,20 +256,35 @@ __device__ __forceinline__ void colsum_tile(uint32_t stage, int lane, float* col
 }
 
 __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage, int lane, int M, int N,
-                                           int64_t row0, int64_t batch, int64_t out_boff, int64_t res_boff,
-                                           int64_t cs_boff, int col0, const uint32_t (&acc)[32], float pe_alpha) {
+                                           int64_t row0, int64_t batch, int64_t out_boff, const CoopIO& io_out,
+                                           const CoopIO& io_res, const CoopIO& io_gate, int64_t cs_boff, int col0,
+                                           const uint32_t (&acc)[32], float pe_alpha) {
   const uint32_t f = e.flags;
   const int64_t row = row0 + lane;
   const bool row_ok = row < M;
   float v[32];
+  if (e.alpha != 1.f) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = e.alpha * __uint_as_float(acc[i]);
+    for (int i = 0; i < 32; ++i) v[i] = e.alpha * __uint_as_float(acc[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+  }
   if (f & EPI_BIAS) {
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + col0);
+    if (col0 + 32 <= N) {          // warp-uniform: whole chunk inside the matrix
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (col0 + i < N) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + i));
-        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(bp + i);
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (col0 + 4 * i < N) {
+          const float4 b = __ldg(bp + i);
+          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
       }
     }
   }
@@ -285,7 +317,7 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
   }
   if (f & (EPI_RES | EPI_ACC_GATES_AUX)) {
     float r[32];
-    load_aux_tile(stage, lane, e.res, e.res_plane_stride, e.res_planes, e.res_ld, res_boff, row0, col0, M, N, r);
+    load_aux_tile(stage, lane, e.res, e.res_plane_stride, e.res_planes, io_res, col0, N, r);
     if (f & EPI_RES) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] += r[i];
@@ -306,21 +338,24 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
   }
   if (f & EPI_GATE_POS) {
     float g[32];
-    load_aux_tile(stage, lane, e.gate, e.gate_plane_stride, e.gate_planes, e.gate_ld, 0, row0, col0, M, N, g);
+    load_aux_tile(stage, lane, e.gate, e.gate_plane_stride, e.gate_planes, io_gate, col0, N, g);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = g[i] > 0.f ? v[i] * e.gate_scale : 0.f;
   }
-  if (!row_ok) {
+  if (f & EPI_COLSUM) {   // rows past M must not contribute to the column sums (the stores are guarded per row)
+    if (!row_ok) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+    colsum_tile(stage, lane, e.colsum + cs_boff, col0, N, v);
   }
-  if (f & EPI_COLSUM) colsum_tile(stage, lane, e.colsum + cs_boff, col0, N, v);
   if (f & EPI_OUT_ATOMIC) {
     store_f32_tile<true>(stage, lane, reinterpret_cast<float*>(e.out), e.out_ld, out_boff, row0, col0, M, N, v);
   } else if (f & EPI_OUT_F32) {
-    store_f32_tile<false>(stage, lane, reinterpret_cast<float*>(e.out), e.out_ld, out_boff, row0, col0, M, N, v);
+    if (((e.out_ld | N) & 3) == 0) store_f32_tile_plain(stage, lane, reinterpret_cast<float*>(e.out), io_out, col0, N, v);
+    else store_f32_tile<false>(stage, lane, reinterpret_cast<float*>(e.out), e.out_ld, out_boff, row0, col0, M, N, v);
   } else {
-    store_split_tile(stage, lane, e.out, e.out_plane_stride, e.out_planes, e.out_ld, out_boff, row0, col0, M, N, v);
+    store_split_tile(stage, lane, e.out, e.out_plane_stride, e.out_planes, io_out, col0, N, v);
   }
 }
 
@@ -484,6 +519,10 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
       const int64_t row0 = static_cast<int64_t>(tm) * BLOCK_M + w * 32;
       const int64_t out_boff = i0 * e.out_sb0 + i1 * e.out_sb1;
       const int64_t res_boff = i0 * e.res_sb0 + i1 * e.res_sb1;
+      const CoopIO io_out = make_coop(lane, out_boff, row0, e.out_ld, args.M, (e.flags & EPI_OUT_F32) ? 4 : 8);
+      CoopIO io_res = io_out, io_gate = io_out;
+      if (e.flags & (EPI_RES | EPI_ACC_GATES_AUX)) io_res = make_coop(lane, res_boff, row0, e.res_ld, args.M, 8);
+      if (e.flags & EPI_GATE_POS) io_gate = make_coop(lane, 0, row0, e.gate_ld, args.M, 8);
       const int64_t cs_boff = i0 * e.colsum_sb0;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BLOCK_N;
       const uint32_t stage_buf = epi_stage_base + (warp - 4) * EPI_STAGE_BYTES;
@@ -496,7 +535,8 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
         tmem_ld_32x32(t_row + c * 32, r);
         tmem_ld_wait();
         if (warp_rows_ok)
-          epilogue32(e, stage_buf, lane, args.M, args.N, row0, t, out_boff, res_boff, cs_boff, col0, r, pe_alpha);
+          epilogue32(e, stage_buf, lane, args.M, args.N, row0, t, out_boff, io_out, io_res, io_gate, cs_boff, col0, r,
+                     pe_alpha);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
