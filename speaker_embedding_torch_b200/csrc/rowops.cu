@@ -137,11 +137,36 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
   float g[8], ag[8], ab[8], az[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { g[i] = __ldg(gamma + lane * 8 + i); ag[i] = 0.f; ab[i] = 0.f; az[i] = 0.f; }
+  // software pipeline: the raw loads of the next row are issued before the current row is reduced
+  uint4 nd[3], nz[3];
+  float2 nms = make_float2(0.f, 0.f);
+  auto fetch = [&](int64_t r) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      if (p < dy_planes) nd[p] = *reinterpret_cast<const uint4*>(dy + p * dy_ps + r * 256 + lane * 8);
+      if (p < z_planes) nz[p] = *reinterpret_cast<const uint4*>(z + p * z_ps + r * 256 + lane * 8);
+    }
+    nms = stats[r];
+  };
+  auto unpack = [&](const uint4 (&raw)[3], int planes, float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      if (p < planes) {
+        const uint32_t w[4] = {raw[p].x, raw[p].y, raw[p].z, raw[p].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] += bf16lo_to_f(w[i]); v[2 * i + 1] += bf16hi_to_f(w[i]); }
+      }
+    }
+  };
+  if (warp < rows) fetch(warp);
   for (int64_t r = warp; r < rows; r += nwarps) {
     float d[8], x[8];
-    load8_split(dy, dy_ps, dy_planes, r * 256 + lane * 8, d);
-    load8_split(z, z_ps, z_planes, r * 256 + lane * 8, x);
-    const float2 ms = stats[r];
+    unpack(nd, dy_planes, d);
+    unpack(nz, z_planes, x);
+    const float2 ms = nms;
+    if (r + nwarps < rows) fetch(r + nwarps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -186,7 +211,7 @@ int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t 
            const float* gamma, void* dz, int64_t dz_ps, int dz_planes, void* dz_drop, DropCfg drop, uint32_t site,
            float* dgamma, float* dbeta, float* dbias, int64_t rows, cudaStream_t st) {
   ProfScope prof("ln_bwd", 0, 512.0 * rows * (dy_planes + z_planes + dz_planes * (drop.thresh ? 2 : 1)), st);
-  const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 4));
+  const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 6));
   ln_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ps, dy_planes,
                                         reinterpret_cast<const __nv_bfloat16*>(z), z_ps, z_planes,
                                         reinterpret_cast<const float2*>(stats), gamma,
