@@ -233,6 +233,13 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // software pipeline for the common case (fp32 scores, T <= 256): next row's loads are issued one row ahead
+  const bool pipelined = (CH == 1) && (s_f32 != nullptr) && (lane * 8 < Tp);
+  float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
+  if (pipelined && warp < rows) {
+    n0 = *reinterpret_cast<const float4*>(s_f32 + warp * Tp + lane * 8);
+    n1 = *reinterpret_cast<const float4*>(s_f32 + warp * Tp + lane * 8 + 4);
+  }
   for (int64_t r = warp; r < rows; r += nwarps) {
     float v[CH][8];
     float mx = -INFINITY;
@@ -241,8 +248,17 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
       const int col = c * 256 + lane * 8;
       if (col < Tp) {
         if (s_f32 != nullptr) {
-          const float4 a0 = *reinterpret_cast<const float4*>(s_f32 + r * Tp + col);
-          const float4 a1 = *reinterpret_cast<const float4*>(s_f32 + r * Tp + col + 4);
+          float4 a0, a1;
+          if (pipelined) {
+            a0 = n0; a1 = n1;
+            if (r + nwarps < rows) {
+              n0 = *reinterpret_cast<const float4*>(s_f32 + (r + nwarps) * Tp + col);
+              n1 = *reinterpret_cast<const float4*>(s_f32 + (r + nwarps) * Tp + col + 4);
+            }
+          } else {
+            a0 = *reinterpret_cast<const float4*>(s_f32 + r * Tp + col);
+            a1 = *reinterpret_cast<const float4*>(s_f32 + r * Tp + col + 4);
+          }
           v[c][0] = a0.x; v[c][1] = a0.y; v[c][2] = a0.z; v[c][3] = a0.w;
           v[c][4] = a1.x; v[c][5] = a1.y; v[c][6] = a1.z; v[c][7] = a1.w;
         } else {
@@ -314,6 +330,18 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // software pipeline for the common case (fp32 dP, T <= 256): raw loads of the next row one row ahead
+  const bool pipelined = (CH == 1) && (dp_f32 != nullptr) && (lane * 8 < Tp) && planes <= 3;
+  float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
+  uint4 np[3];
+  auto fetch = [&](int64_t r) {
+    n0 = *reinterpret_cast<const float4*>(dp_f32 + r * Tp + lane * 8);
+    n1 = *reinterpret_cast<const float4*>(dp_f32 + r * Tp + lane * 8 + 4);
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (q < planes) np[q] = *reinterpret_cast<const uint4*>(p + q * ps + r * Tp + lane * 8);
+  };
+  if (pipelined && warp < rows) fetch(warp);
   for (int64_t r = warp; r < rows; r += nwarps) {
     float pv[CH][8], dv[CH][8];
     float dot = 0.f;
@@ -321,6 +349,21 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
     for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < Tp) {
+        if (pipelined) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[c][i] = 0.f;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            if (q < planes) {
+              const uint32_t w[4] = {np[q].x, np[q].y, np[q].z, np[q].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { pv[c][2 * i] += bf16lo_to_f(w[i]); pv[c][2 * i + 1] += bf16hi_to_f(w[i]); }
+            }
+          }
+          dv[c][0] = n0.x; dv[c][1] = n0.y; dv[c][2] = n0.z; dv[c][3] = n0.w;
+          dv[c][4] = n1.x; dv[c][5] = n1.y; dv[c][6] = n1.z; dv[c][7] = n1.w;
+          if (r + nwarps < rows) fetch(r + nwarps);
+        } else {
         load8_split(p, ps, planes, r * Tp + col, pv[c]);
         if (dp_f32 != nullptr) {
           const float4 a0 = *reinterpret_cast<const float4*>(dp_f32 + r * Tp + col);
@@ -329,6 +372,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
           dv[c][4] = a1.x; dv[c][5] = a1.y; dv[c][6] = a1.z; dv[c][7] = a1.w;
         } else {
           load8_split(dp, ps, planes, r * Tp + col, dv[c]);
+        }
         }
         if (drop.thresh != 0) {
           float k8[8];
