@@ -17,6 +17,7 @@ int attn_row0_fwd(const void* q0, int64_t q_ps, const void* kv, int64_t kv_ps, i
 int attn_row0_bwd(const void* datt0, int64_t da_ps, int g_planes, const void* q0, int64_t q_ps, const void* kv,
                   int64_t kv_ps, int planes, const float* p0, const float* pd0, void* dq0, int64_t dq_ps, void* dkv,
                   int64_t dkv_ps, float* dbias, int B, int H, int T, int Tp, cudaStream_t st);
+int attn_fused_fwd(const void* qkv, void* out, int64_t out_ld, int B, int H, int T, cudaStream_t st);
 int rows_add(void* dst, int64_t d_ps, int64_t dst_row_step, const void* src, int64_t s_ps, int planes, int rows,
              cudaStream_t st);
 
@@ -68,6 +69,8 @@ static size_t take_f32(size_t& cur, int64_t elems) {
 
 static bool g_prune_last = true;   // spk_set_option("prune_last_layer", 0/1)
 void encoder_set_prune(bool on) { g_prune_last = on; }
+static bool g_fused_attn = true;   // spk_set_option("fused_inference_attention", 0/1)
+void encoder_set_fused_attn(bool on) { g_fused_attn = on; }
 
 static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bool keep, Plan& pl) {
   SPK_CHECK(c.mel_dim == 80 && c.emb == 256 && c.heads == 4 && c.ffn == 1024,
@@ -439,6 +442,11 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       c.out(g.epi, b.qkv, 0, 3 * D);
       SPK_TRY(gemm_run(g, st));
     }
+    // inference (one plane, nothing kept for a backward pass): scores, softmax and PV in one tcgen05 kernel
+    const bool fused_attn = (P == 1) && !keep && !training && T <= 256 && g_fused_attn;
+    if (fused_attn) {
+      SPK_TRY(attn_fused_fwd(c.ptr(b.qkv), c.ptr(b.att), D, B, H, T, st));
+    } else {
     {  // S = Q K^T / sqrt(dh), per (slice, head)
       GemmProblem g;
       g.tag = "gemm.attn_qk";
@@ -461,6 +469,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
       c.out(g.epi, b.att, 0, D, 64, (int64_t)T * D);
       SPK_TRY(gemm_run(g, st));
+    }
     }
     {  // out-proj + dropout1 + residual
       GemmProblem g;

@@ -14,4 +14,5 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
                      size_t ws_bytes, cudaStream_t st);
 int encoder_debug_layout(const spk_encoder_config& c, int B, int T, int S, int P, int keep, char* buf, size_t cap);
 void encoder_set_prune(bool on);
+void encoder_set_fused_attn(bool on);
 }  // namespace spk

@@ -1,5 +1,6 @@
 // Host-side description of one (batched, optionally split-K) tensor-core GEMM on split-bf16 operands.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "common.cuh"
@@ -73,5 +74,9 @@ struct GemmProblem {
 int gemm_run(const GemmProblem& p, cudaStream_t stream);
 
 int device_sm_count();
+
+// bf16 4-D tiled tensor map {dims[0] (contiguous), dims[1], dims[2], dims[3]} with element strides for dims 1..3,
+// box {64, box_rows, 1, 1}, 128-byte swizzle, out-of-bounds elements read as zero.
+int encode_map_4d(CUtensorMap* map, const void* base, const int64_t dims[4], const int64_t strides[3], int box_rows);
 
 }  // namespace spk

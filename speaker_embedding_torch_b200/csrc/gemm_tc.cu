@@ -609,6 +609,22 @@ static int make_map(CUtensorMap* map, const SplitMat& m, int plane, int nb0, int
   return 0;
 }
 
+int encode_map_4d(CUtensorMap* map, const void* base, const int64_t dims[4], const int64_t strides[3], int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  SPK_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  SPK_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
+  cuuint64_t d[4] = {(cuuint64_t)dims[0], (cuuint64_t)dims[1], (cuuint64_t)dims[2], (cuuint64_t)dims[3]};
+  cuuint64_t st[3] = {(cuuint64_t)(strides[0] * 2), (cuuint64_t)(strides[1] * 2), (cuuint64_t)(strides[2] * 2)};
+  SPK_CHECK(st[0] % 16 == 0 && st[1] % 16 == 0 && st[2] % 16 == 0, "tensor map strides must be multiples of 16 bytes");
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, st, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SPK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
 static int launch(const GemmKernelArgs& args, int grid, cudaStream_t stream) {
   using Cfg = TileCfg<PLANES, BLOCK_N>;

@@ -230,3 +230,26 @@ def test_last_layer_pruning_is_exact():
     num = sum(float(((results[1][2][n] - results[0][2][n]).double() ** 2).sum()) for n in results[0][2])
     den = sum(float((results[0][2][n].double() ** 2).sum()) for n in results[0][2])
     assert (num / den) ** 0.5 <= 2e-4
+
+
+@pytest.mark.parametrize("frames", [1, 24, 64, 128, 129, 160, 177, 200, 256])
+def test_fused_inference_attention_matches_unfused_and_oracle(frames):
+    """The one-kernel tcgen05 attention of the inference path (scores stay in TMEM / shared memory) against the
+    GEMM + softmax + GEMM composition and the fp64 oracle."""
+    from speaker_embedding_torch_b200 import _native
+    m, state = _model(44)
+    m.eval()
+    mel = torch.as_tensor(synth.make_mel(300 + frames, 6, frames)).cuda()
+    out = {}
+    try:
+        for fused in (1, 0):
+            _native.set_option("fused_inference_attention", fused)
+            with torch.no_grad():
+                out[fused] = m(mel).clone()
+            torch.cuda.synchronize()
+    finally:
+        _native.set_option("fused_inference_attention", 1)
+    ref = O.encoder_forward(O.to_torch_state(state, torch.float64), mel.cpu().double(), 1).numpy()
+    for fused in (1, 0):
+        assert _cos(out[fused].cpu().numpy().astype(np.float64), ref).min() >= 0.9999, fused
+    torch.testing.assert_close(out[1], out[0], atol=4e-3, rtol=0)
