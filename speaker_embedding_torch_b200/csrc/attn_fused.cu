@@ -19,13 +19,19 @@
 
 namespace spk {
 
+__device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2: ~2 ulp, plenty for bf16 probabilities
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int AF_KV_ROWS = 256;               // max keys (T <= 256)
-constexpr int AF_SQ = 0;                      // 128 x 128 B
-constexpr int AF_SK = 16384;                  // 256 x 128 B
+constexpr int AF_STAGE = 16384 + 32768 + 32768;   // Q 128 x 128 B | K 256 x 128 B | V 256 x 128 B, double-buffered
+constexpr int AF_SK = 16384;
 constexpr int AF_SV = AF_SK + 32768;
-constexpr int AF_SP = AF_SV + 32768;          // 4 k-blocks x (128 rows x 128 B)
+constexpr int AF_SP = 2 * AF_STAGE;               // 4 k-blocks x (128 rows x 128 B)
 constexpr int AF_BAR = AF_SP + 65536;
-constexpr int AF_SMEM = AF_BAR + 128 + 1024;  // + alignment slack
+constexpr int AF_SMEM = AF_BAR + 128 + 1024;      // + alignment slack (230 528 B <= 227 KB)
 
 struct AttnFusedArgs {
   CUtensorMap q_map, k_map, v_map;
@@ -37,16 +43,16 @@ struct AttnFusedArgs {
 __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_constant__ AttnFusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = sbase + AF_SQ, sK = sbase + AF_SK, sV = sbase + AF_SV, sP = sbase + AF_SP;
-  const uint32_t bar_load = sbase + AF_BAR, bar_s = bar_load + 8, bar_p = bar_load + 16, bar_o = bar_load + 24;
-  const uint32_t tmem_slot = bar_load + 32;
+  const uint32_t sP = sbase + AF_SP;
+  const uint32_t bar_load = sbase + AF_BAR /* [2] */, bar_s = bar_load + 16, bar_p = bar_load + 24, bar_o = bar_load + 32;
+  const uint32_t tmem_slot = bar_load + 40;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.q_map); tma_prefetch_desc(&a.k_map); tma_prefetch_desc(&a.v_map);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_load, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_load, 1); mbar_init(bar_load + 8, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -62,31 +68,39 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
+      // operand stages are double-buffered: the loads of item i+1 go out as soon as PV of item i-1 has retired
       int it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int mt = item % a.mtiles, bh = item / a.mtiles, h = bh % a.H, b = bh / a.H;
-        if (it > 0) mbar_wait(bar_o, (it - 1) & 1, 0x500u);     // PV of the previous item done: operands free
-        mbar_arrive_expect_tx(bar_load, load_bytes);
-        tma_load_4d(sQ, &a.q_map, bar_load, 0, mt * 128, h, b);
-        tma_load_4d(sK, &a.k_map, bar_load, 0, 0, h, b);
-        tma_load_4d(sV, &a.v_map, bar_load, 0, 0, h, b);
+        const int s = it & 1;
+        const uint32_t sQ = sbase + s * AF_STAGE, sK = sQ + AF_SK, sV = sQ + AF_SV, bl = bar_load + 8 * s;
+        if (it >= 2) mbar_wait(bar_o, (it - 2) & 1, 0x500u);    // PV of item it-2 (same stage) done
+        mbar_arrive_expect_tx(bl, load_bytes);
+        tma_load_4d(sQ, &a.q_map, bl, 0, mt * 128, h, b);
+        tma_load_4d(sK, &a.k_map, bl, 0, 0, h, b);
+        tma_load_4d(sV, &a.v_map, bl, 0, 0, h, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, a.Tk16, false, false);
       const uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-      int it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        const uint32_t ph = it & 1;
-        mbar_wait(bar_load, ph, 0x510u);
+      auto issue_s = [&](int it) {
+        const int s = it & 1;
+        const uint32_t sQ = sbase + s * AF_STAGE, sK = sQ + AF_SK;
+        mbar_wait(bar_load + 8 * s, (it >> 1) & 1, 0x510u);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem_S, umma_smem_desc(sQ + k * 32, 16, 1024), umma_smem_desc(sK + k * 32, 16, 1024), idesc_s,
                     k > 0 ? 1u : 0u);
         umma_commit(bar_s);
-        mbar_wait(bar_p, ph, 0x520u);
+      };
+      int it = 0;
+      if (blockIdx.x < items) issue_s(0);
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const uint32_t sV = sbase + (it & 1) * AF_STAGE + AF_SV;
+        mbar_wait(bar_p, it & 1, 0x520u);           // P(it) in shared memory, S(it) fully read
         tc_fence_after();
         uint32_t acc = 0;
         for (int kb = 0; kb < a.Tk64 / 64; ++kb) {
@@ -98,6 +112,7 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
           }
         }
         umma_commit(bar_o);
+        if (item + static_cast<int>(gridDim.x) < items) issue_s(it + 1);   // scores of the next item during this epilogue
       }
     }
   } else if (warp >= 4) {
@@ -109,7 +124,11 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const int mt = item % a.mtiles, bh = item / a.mtiles, h = bh % a.H, b = bh / a.H;
-      mbar_wait(bar_s, ph, 0x530u);
+      mbar_wait(bar_s, ph, 0x530u);        // also keeps idle warps in lock-step with the barrier phases
+      if (mt * 128 + w * 32 >= a.T) {      // warp-uniform: all 32 query rows of this warp lie past T -> nothing to do
+        mbar_arrive(bar_p);
+        continue;
+      }
       tc_fence_after();
       uint32_t sreg[32];
       // pass 1: row max over the valid keys
@@ -122,6 +141,7 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
           if (c * 32 + i < a.T) mx = fmaxf(mx, __uint_as_float(sreg[i]));
       }
       // pass 2: unnormalised probabilities -> bf16 -> swizzled shared memory; row sum in fp32
+      const float mxs = mx * sc;
       float sum = 0.f;
       for (int c = 0; c * 32 < a.Tk64; ++c) {
         tmem_ld_32x32(tmem_S + t_lane + c * 32, sreg);
@@ -133,8 +153,8 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int key = c * 32 + g * 8 + 2 * j;
-            const float e0 = key < a.T ? exp2f((__uint_as_float(sreg[g * 8 + 2 * j]) - mx) * sc) : 0.f;
-            const float e1 = key + 1 < a.T ? exp2f((__uint_as_float(sreg[g * 8 + 2 * j + 1]) - mx) * sc) : 0.f;
+            const float e0 = key < a.T ? fast_exp2(__uint_as_float(sreg[g * 8 + 2 * j]) * sc - mxs) : 0.f;
+            const float e1 = key + 1 < a.T ? fast_exp2(__uint_as_float(sreg[g * 8 + 2 * j + 1]) * sc - mxs) : 0.f;
             sum += e0 + e1;
             pk[j] = pack_bf16x2(e0, e1);
           }
