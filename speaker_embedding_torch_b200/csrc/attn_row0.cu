@@ -39,7 +39,19 @@ __device__ __forceinline__ float keep_of(const DropCfg& d, uint32_t site, uint64
   return k8[idx & 7];
 }
 
-// one warp per (slice b, head h); lane owns head dims 2*lane, 2*lane+1
+// One warp per (slice b, head h).  Lane (g = lane >> 3, d8 = lane & 7): key group g handles keys t = 4 i + g,
+// d8 selects 8 consecutive head dims (one 16-byte load per plane), so a warp instruction moves 4 keys x 128 B
+// and the per-key reduction is 3 shuffles inside an 8-lane group.
+__device__ __forceinline__ void load8f(const __nv_bfloat16* base, int64_t ps, int planes, int64_t off, float (&v)[8]) {
+  load8_split(base, ps, planes, off, v);
+}
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
 __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
     const __nv_bfloat16* __restrict__ q0, int64_t q_ps, const __nv_bfloat16* __restrict__ kv, int64_t kv_ps, int planes,
     __nv_bfloat16* __restrict__ att0, int64_t a_ps, float* __restrict__ p0, float* __restrict__ pd0, DropCfg drop,
@@ -49,13 +61,22 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
   const int64_t bh = static_cast<int64_t>(blockIdx.x) * R0_WARPS + warp;
   if (bh >= static_cast<int64_t>(B) * H) return;
   const int b = static_cast<int>(bh / H), h = static_cast<int>(bh % H);
+  const int g = lane >> 3, d8 = lane & 7;
   float* sc = sm + warp * Tp;
-  const float2 q = load2_split(q0, q_ps, planes, static_cast<int64_t>(b) * 256 + h * 64 + 2 * lane);
-  const int64_t kv_row0 = static_cast<int64_t>(b) * T * 512 + h * 64 + 2 * lane;
-  for (int t = 0; t < T; ++t) {
-    const float2 k = load2_split(kv, kv_ps, planes, kv_row0 + static_cast<int64_t>(t) * 512);
-    const float s = warp_sum(q.x * k.x + q.y * k.y);
-    if (lane == 0) sc[t] = s * 0.125f;
+  float q[8];
+  load8f(q0, q_ps, planes, static_cast<int64_t>(b) * 256 + h * 64 + d8 * 8, q);
+  const int64_t kv_row0 = static_cast<int64_t>(b) * T * 512 + h * 64 + d8 * 8;
+  // scores
+#pragma unroll 2
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    const int t = min(t0 + g, T - 1);
+    float k[8];
+    load8f(kv, kv_ps, planes, kv_row0 + static_cast<int64_t>(t) * 512, k);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(q[i], k[i], s);
+    s = group8_sum(s);
+    if (d8 == 0 && t0 + g < T) sc[t0 + g] = s * 0.125f;
   }
   __syncwarp();
   float mx = -INFINITY;
@@ -81,14 +102,25 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
     }
   }
   __syncwarp();
-  float2 o = make_float2(0.f, 0.f);
-  for (int t = 0; t < T; ++t) {
-    const float2 v = load2_split(kv, kv_ps, planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512);
-    const float pd = sc[t];
-    o.x = fmaf(pd, v.x, o.x);
-    o.y = fmaf(pd, v.y, o.y);
+  // o = sum_t pd_t V_t : each key group accumulates its keys, then the four groups are combined
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    const int t = t0 + g;
+    if (t < T) {
+      float v[8];
+      load8f(kv, kv_ps, planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512, v);
+      const float pd = sc[t];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(pd, v[i], o[i]);
+    }
   }
-  store2_split(att0, a_ps, planes, static_cast<int64_t>(b) * 256 + h * 64 + 2 * lane, o.x, o.y);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+  }
+  if (g == 0) store8_split(att0, a_ps, planes, static_cast<int64_t>(b) * 256 + h * 64 + d8 * 8, o);
 }
 
 int attn_row0_fwd(const void* q0, int64_t q_ps, const void* kv, int64_t kv_ps, int planes, void* att0, int64_t a_ps,
@@ -115,23 +147,40 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
   const int64_t bh = static_cast<int64_t>(blockIdx.x) * R0_WARPS + warp;
   if (bh >= static_cast<int64_t>(B) * H) return;
   const int b = static_cast<int>(bh / H), h = static_cast<int>(bh % H);
+  const int g = lane >> 3, d8 = lane & 7;
   float* ds = sm + warp * Tp;
-  const int64_t col = h * 64 + 2 * lane;
-  const float2 dout = load2_split(datt0, da_ps, g_planes, static_cast<int64_t>(b) * 256 + col);
-  const float2 q = load2_split(q0, q_ps, planes, static_cast<int64_t>(b) * 256 + col);
+  const int64_t col = h * 64 + d8 * 8;
+  float dout[8], q[8];
+  load8f(datt0, da_ps, g_planes, static_cast<int64_t>(b) * 256 + col, dout);
+  load8f(q0, q_ps, planes, static_cast<int64_t>(b) * 256 + col, q);
   const int64_t kv_row0 = static_cast<int64_t>(b) * T * 512 + col;
   const float* p = p0 + bh * Tp;
   const float* pd = pd0 + bh * Tp;
   // dV rows and dp_t = dO . V_t
   float pd_sum = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float2 v = load2_split(kv, kv_ps, planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512);
-    const float dp = warp_sum(dout.x * v.x + dout.y * v.y);
-    const float pdt = pd[t];
-    if (lane == 0) ds[t] = dp;
-    pd_sum += pdt;
-    store2_split(dkv, dkv_ps, g_planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512, pdt * dout.x, pdt * dout.y);
+#pragma unroll 2
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    const int t = t0 + g;
+    const int tc = min(t, T - 1);
+    float v[8];
+    load8f(kv, kv_ps, planes, kv_row0 + 256 + static_cast<int64_t>(tc) * 512, v);
+    float dp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dp = fmaf(dout[i], v[i], dp);
+    dp = group8_sum(dp);
+    if (t < T) {
+      const float pdt = pd[t];
+      if (d8 == 0) ds[t] = dp;
+      pd_sum += pdt;
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = pdt * dout[i];
+      store8_split(dkv, dkv_ps, g_planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512, w);
+    }
   }
+  // pd_sum currently holds this key group's share: combine the four groups
+  pd_sum += __shfl_xor_sync(0xffffffffu, pd_sum, 8);
+  pd_sum += __shfl_xor_sync(0xffffffffu, pd_sum, 16);
   __syncwarp();
   float dot = 0.f;
   for (int t = lane; t < T; t += 32) dot += pd[t] * ds[t];
@@ -144,21 +193,33 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
   }
   ds_sum = warp_sum(ds_sum);
   __syncwarp();
-  float2 dq = make_float2(0.f, 0.f);
-  for (int t = 0; t < T; ++t) {
-    const float2 k = load2_split(kv, kv_ps, planes, kv_row0 + static_cast<int64_t>(t) * 512);
-    const float d = ds[t];
-    dq.x = fmaf(d, k.x, dq.x);
-    dq.y = fmaf(d, k.y, dq.y);
-    store2_split(dkv, dkv_ps, g_planes, kv_row0 + static_cast<int64_t>(t) * 512, d * q.x, d * q.y);
+  float dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    const int t = t0 + g;
+    if (t < T) {
+      float k[8], w[8];
+      load8f(kv, kv_ps, planes, kv_row0 + static_cast<int64_t>(t) * 512, k);
+      const float d = ds[t];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dq[i] = fmaf(d, k[i], dq[i]); w[i] = d * q[i]; }
+      store8_split(dkv, dkv_ps, g_planes, kv_row0 + static_cast<int64_t>(t) * 512, w);
+    }
   }
-  store2_split(dq0, dq_ps, g_planes, static_cast<int64_t>(b) * 256 + col, dq.x, dq.y);
-  atomicAdd(dbias + col, dq.x);
-  atomicAdd(dbias + col + 1, dq.y);
-  atomicAdd(dbias + 256 + col, ds_sum * q.x);
-  atomicAdd(dbias + 256 + col + 1, ds_sum * q.y);
-  atomicAdd(dbias + 512 + col, pd_sum * dout.x);
-  atomicAdd(dbias + 512 + col + 1, pd_sum * dout.y);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dq[i] += __shfl_xor_sync(0xffffffffu, dq[i], 8);
+    dq[i] += __shfl_xor_sync(0xffffffffu, dq[i], 16);
+  }
+  if (g == 0) {
+    store8_split(dq0, dq_ps, g_planes, static_cast<int64_t>(b) * 256 + col, dq);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(dbias + col + i, dq[i]);
+      atomicAdd(dbias + 256 + col + i, ds_sum * q[i]);
+      atomicAdd(dbias + 512 + col + i, pd_sum * dout[i]);
+    }
+  }
 }
 
 int attn_row0_bwd(const void* datt0, int64_t da_ps, int g_planes, const void* q0, int64_t q_ps, const void* kv,
