@@ -255,11 +255,14 @@ __device__ __forceinline__ void colsum_tile(uint32_t stage, int lane, float* col
   }
 }
 
+// CT: compile-time superset of the flags that can be set for this launch -- everything outside CT is dead code, which
+// keeps the common forward epilogues (bias / ReLU only) short (the epilogue is instruction-issue bound).
+template <uint32_t CT>
 __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage, int lane, int M, int N,
                                            int64_t row0, int64_t batch, int64_t out_boff, const CoopIO& io_out,
                                            const CoopIO& io_res, const CoopIO& io_gate, int64_t cs_boff, int col0,
                                            const uint32_t (&acc)[32], float pe_alpha) {
-  const uint32_t f = e.flags;
+  const uint32_t f = e.flags & CT;
   const int64_t row = row0 + lane;
   const bool row_ok = row < M;
   float v[32];
@@ -356,6 +359,30 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
     else store_f32_tile<false>(stage, lane, reinterpret_cast<float*>(e.out), e.out_ld, out_boff, row0, col0, M, N, v);
   } else {
     store_split_tile(stage, lane, e.out, e.out_plane_stride, e.out_planes, io_out, col0, N, v);
+  }
+}
+
+// All 32-column chunks of one accumulator tile that belong to this warp.
+template <uint32_t CT, int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t stage_buf, int lane, int cgroup,
+                                              uint32_t t_row, int M, int N, int64_t row0, int64_t batch, int64_t out_boff,
+                                              int64_t res_boff, int64_t cs_boff, int tn, float pe_alpha) {
+  const CoopIO io_out = make_coop(lane, out_boff, row0, e.out_ld, M, (e.flags & EPI_OUT_F32) ? 4 : 8);
+  CoopIO io_res = io_out, io_gate = io_out;
+  if constexpr ((CT & (EPI_RES | EPI_ACC_GATES_AUX)) != 0) {
+    if (e.flags & (EPI_RES | EPI_ACC_GATES_AUX)) io_res = make_coop(lane, res_boff, row0, e.res_ld, M, 8);
+  }
+  if constexpr ((CT & EPI_GATE_POS) != 0) {
+    if (e.flags & EPI_GATE_POS) io_gate = make_coop(lane, 0, row0, e.gate_ld, M, 8);
+  }
+#pragma unroll 1
+  for (int c = cgroup; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
+    const int col0 = tn * BLOCK_N + c * 32;
+    if (col0 >= N) break;             // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c * 32, r);
+    tmem_ld_wait();
+    epilogue32<CT>(e, stage_buf, lane, M, N, row0, batch, out_boff, io_out, io_res, io_gate, cs_boff, col0, r, pe_alpha);
   }
 }
 
@@ -519,24 +546,21 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
       const int64_t row0 = static_cast<int64_t>(tm) * BLOCK_M + w * 32;
       const int64_t out_boff = i0 * e.out_sb0 + i1 * e.out_sb1;
       const int64_t res_boff = i0 * e.res_sb0 + i1 * e.res_sb1;
-      const CoopIO io_out = make_coop(lane, out_boff, row0, e.out_ld, args.M, (e.flags & EPI_OUT_F32) ? 4 : 8);
-      CoopIO io_res = io_out, io_gate = io_out;
-      if (e.flags & (EPI_RES | EPI_ACC_GATES_AUX)) io_res = make_coop(lane, res_boff, row0, e.res_ld, args.M, 8);
-      if (e.flags & EPI_GATE_POS) io_gate = make_coop(lane, 0, row0, e.gate_ld, args.M, 8);
-      const int64_t cs_boff = i0 * e.colsum_sb0;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BLOCK_N;
       const uint32_t stage_buf = epi_stage_base + (warp - 4) * EPI_STAGE_BYTES;
-      const bool warp_rows_ok = row0 < args.M;     // warp-uniform
-#pragma unroll 1
-      for (int c = cgroup; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
-        const int col0 = tn * BLOCK_N + c * 32;
-        if (col0 >= args.N) break;             // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        tmem_ld_wait();
-        if (warp_rows_ok)
-          epilogue32(e, stage_buf, lane, args.M, args.N, row0, t, out_boff, io_out, io_res, io_gate, cs_boff, col0, r,
-                     pe_alpha);
+      const int64_t cs_boff = i0 * e.colsum_sb0;
+      if (row0 < args.M) {   // warp-uniform
+        constexpr uint32_t CT_LEAN = EPI_BIAS | EPI_RELU | EPI_OUT_F32;
+        constexpr uint32_t CT_FWD = CT_LEAN | EPI_PE | EPI_DROPOUT | EPI_RES;
+        if ((e.flags & ~CT_LEAN) == 0)
+          epilogue_tile<CT_LEAN, BLOCK_N>(e, stage_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
+                                          cs_boff, tn, pe_alpha);
+        else if ((e.flags & ~CT_FWD) == 0)
+          epilogue_tile<CT_FWD, BLOCK_N>(e, stage_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
+                                         cs_boff, tn, pe_alpha);
+        else
+          epilogue_tile<0xFFFFFFFFu, BLOCK_N>(e, stage_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff,
+                                              res_boff, cs_boff, tn, pe_alpha);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
