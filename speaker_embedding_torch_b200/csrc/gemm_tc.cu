@@ -649,15 +649,48 @@ int encode_map_4d(CUtensorMap* map, const void* base, const int64_t dims[4], con
   return 0;
 }
 
+// Opt in to the dynamic shared memory size and make the kernel resident (CUDA loads kernels lazily: a first launch of
+// a new instantiation inside a timed region -- a new frame length picks another BLOCK_N -- would pay for the load).
+template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
+static int configure() {
+  using Cfg = TileCfg<PLANES, BLOCK_N>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, PLANES, BLOCK_N>;
+  SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  cudaFuncAttributes fa;
+  SPK_CUDA(cudaFuncGetAttributes(&fa, kern));
+  return 0;
+}
+template <bool A_MN, bool B_MN, int PLANES>
+static int configure_bn() {
+  SPK_TRY((configure<A_MN, B_MN, PLANES, 64>()));
+  SPK_TRY((configure<A_MN, B_MN, PLANES, 128>()));
+  if constexpr (PLANES < 3) {
+    SPK_TRY((configure<A_MN, B_MN, PLANES, 192>()));
+    SPK_TRY((configure<A_MN, B_MN, PLANES, 256>()));
+  }
+  return 0;
+}
+template <int PLANES>
+static int configure_planes() {
+  SPK_TRY((configure_bn<false, false, PLANES>()));
+  SPK_TRY((configure_bn<false, true, PLANES>()));
+  SPK_TRY((configure_bn<true, true, PLANES>()));
+  return 0;
+}
+static int configure_all() {
+  static bool done = false;
+  if (done) return 0;
+  SPK_TRY(configure_planes<1>());
+  SPK_TRY(configure_planes<2>());
+  SPK_TRY(configure_planes<3>());
+  done = true;
+  return 0;
+}
+
 template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
 static int launch(const GemmKernelArgs& args, int grid, cudaStream_t stream) {
   using Cfg = TileCfg<PLANES, BLOCK_N>;
   auto kern = gemm_tc_kernel<A_MN, B_MN, PLANES, BLOCK_N>;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
-    SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
   kern<<<grid, 128 + 32 * NUM_EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(args);
   SPK_CUDA(cudaGetLastError());
   return 0;
@@ -702,6 +735,8 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
   else SPK_CHECK(p.A.rows == p.K && p.A.cols <= p.M, "gemm: A is not [K, <=M]");
   if (!p.b_mn) SPK_CHECK(p.B.rows <= p.N && p.B.cols == p.K, "gemm: B is not [<=N, K]");
   else SPK_CHECK(p.B.rows == p.K && p.B.cols <= p.N, "gemm: B is not [K, <=N]");
+
+  SPK_TRY(configure_all());
 
   int bn = p.block_n;
   if (bn == 0) bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : (p.N <= 192 ? 192 : 256));
