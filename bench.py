@@ -59,16 +59,60 @@ def min_flops_fwd(T):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: an NVML polling thread (5 ms period; the timed region of a
+    default run is only ~130 ms, too short for `nvidia-smi -lms`), falling back to nvidia-smi when NVML is missing."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
+
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.stop = threading.Event()
+        self.nvml = None
+
+    def _handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(self.index)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
+
+    def _poll(self, pynvml, h):
+        try:
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        while not self.stop.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(mx) if mx else None, int(mask)))
+            except Exception:
+                pass
+            self.stop.wait(0.005)
 
     def __enter__(self):
+        try:
+            pynvml, h = self._handle()
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, args=(pynvml, h), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -78,29 +122,36 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            c = [x.strip() for x in line.split(",")]
+            try:
+                mask = 0
+                for (n, bit), v in zip(self.REASONS, c[3:7]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((float(c[0]), float(c[1]), mask))
+            except (ValueError, IndexError):
+                continue
 
     def __exit__(self, *a):
-        if self.proc is not None:
+        if self.nvml is not None:
+            self.stop.set()
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
             time.sleep(0.25)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows if r[1]]
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(n for n, bit in self.REASONS if mask & bit), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -256,10 +307,11 @@ def run_native(args):
 
     # ---- end to end through the public API: pinned host batch -> H2D -> step -> loss D2H
     host = [synth_mel(gen, batch, T, dev).cpu().pin_memory() for T in lengths[W + K:W + 2 * K]]
+    from speaker_embedding_torch_b200.Prefetch import Device_Prefetcher
+    feeder = Device_Prefetcher(host, dev, reserve_bytes=batch * 80 * T_MAX * 4)     # buffers sized for Frame_Length.Max
     barrier()
     e0.record()
-    for i in range(K):
-        mel = host[i].to(dev, non_blocking=True)
+    for mel in feeder:                           # batch i+1 crosses PCIe on a side stream while batch i is computed
         lv = step(mel).item()
     e1.record()
     barrier()
@@ -297,6 +349,13 @@ def run_native(args):
                 "peak_source": pk["src"] + (" sustained bf16" if tensor_bound else " copy"),
                 "launch_ms": per_launch_ms, "share_of_step": r["ms"] / tot_ms,
                 "alg_flops_per_launch": r["flops"] / r["launches"], "alg_bytes_per_launch": r["bytes"] / r["launches"]}
+        try:      # DRAM bytes per launch of the same kernel at the same frame count, from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tr.get("frames") == Tp and tag in tr:
+                roof["traffic"] = tr[tag]["read"] + tr[tag]["write"]
+                roof["traffic_source"] = "profiles/r01_gemm_traffic.csv (ncu dram__bytes_read+write, T=%d)" % Tp
+        except (OSError, ValueError, KeyError):
+            pass
         roof["frac"] = roof["achieved"] / roof["peak"]
         breakdown = {k: {"ms_per_step": round(v["ms"] / prof_steps, 4), "launches": v["launches"] // prof_steps,
                          "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else 0.0,

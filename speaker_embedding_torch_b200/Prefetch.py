@@ -1,0 +1,87 @@
+"""Host -> device batch prefetch for the training loop.
+
+The reference moves each batch with ``features.to(device, non_blocking=True)`` right before the step
+(Train.py:143 / 202), i.e. the copy sits on the compute stream in front of the forward pass.  With a 13 ms step and a
+50 MB mel batch (~1 ms over PCIe) that copy is worth hiding: ``Device_Prefetcher`` issues the copy of batch i+1 on a
+side stream while batch i is being computed, into ``depth + 1`` rotating device buffers it owns (no allocator traffic
+in steady state), and hands the tensors over with the proper stream dependencies in both directions.
+
+    for features in Device_Prefetcher(loader, device):     # loader yields pinned CPU tensors (pin_memory=True)
+        loss = criterion(model(features), utts); ...
+
+A yielded tensor is valid until ``depth`` further batches have been requested (it is a view of a rotating buffer).
+``reserve_bytes`` sizes the buffers up front (the largest batch, e.g. Frame_Length.Max): growing one later costs a
+cudaMalloc, which was measured at up to 67 ms on a B200 with a multi-GB workspace cached.
+"""
+import torch
+
+
+class Device_Prefetcher:
+    def __init__(self, iterable, device, depth: int = 1, reserve_bytes: int = 0):
+        self.iterable = iterable
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("Device_Prefetcher needs a CUDA device (there is no CPU path)")
+        self.depth = max(1, int(depth))
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._slots = [dict() for _ in range(self.depth + 1)]      # leaf index -> byte buffer
+        self._free_evt = [None] * (self.depth + 1)                # consumer finished reading slot k
+        self.reserve_bytes = int(reserve_bytes)
+        if self.reserve_bytes > 0:
+            for slot in self._slots:
+                slot[1] = torch.empty(self.reserve_bytes, dtype=torch.uint8, device=self.device)
+
+    def _leaf(self, slot, index, src):
+        nbytes = src.numel() * src.element_size()
+        buf = self._slots[slot].get(index)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes + nbytes // 4, self.reserve_bytes, 16), dtype=torch.uint8, device=self.device)
+            self._slots[slot][index] = buf
+        dst = buf[:nbytes].view(src.dtype).view(src.shape)
+        dst.copy_(src, non_blocking=True)
+        return dst
+
+    def _move(self, slot, obj, counter):
+        if torch.is_tensor(obj):
+            counter[0] += 1
+            return self._leaf(slot, counter[0], obj.contiguous())
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._move(slot, o, counter) for o in obj)
+        if isinstance(obj, dict):
+            return {k: self._move(slot, v, counter) for k, v in obj.items()}
+        return obj
+
+    def _issue(self, slot, batch):
+        with torch.cuda.stream(self.stream):
+            if self._free_evt[slot] is not None:
+                self.stream.wait_event(self._free_evt[slot])       # do not overwrite a buffer the step still reads
+            moved = self._move(slot, batch, [0])
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        return moved, ready, slot
+
+    def __iter__(self):
+        it = iter(self.iterable)
+        queue, nxt = [], 0
+        try:
+            while len(queue) < self.depth:
+                queue.append(self._issue(nxt, next(it)))
+                nxt = (nxt + 1) % (self.depth + 1)
+        except StopIteration:
+            pass
+        prev_slot = None
+        while queue:
+            moved, ready, slot = queue.pop(0)
+            cur = torch.cuda.current_stream(self.device)
+            if prev_slot is not None:          # everything enqueued so far (the previous step) is done with prev_slot
+                evt = torch.cuda.Event()
+                evt.record(cur)
+                self._free_evt[prev_slot] = evt
+            cur.wait_event(ready)
+            try:
+                queue.append(self._issue(nxt, next(it)))
+                nxt = (nxt + 1) % (self.depth + 1)
+            except StopIteration:
+                pass
+            prev_slot = slot
+            yield moved

@@ -288,7 +288,8 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* _
       if (col < Tp) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[c][i] *= inv;
-        store8_split(p, ps, planes, r * Tp + col, v[c]);
+        // with dropout the un-dropped P is only read by the (two-plane) backward pass: skip its third plane
+        store8_split(p, ps, (p_drop != nullptr && planes > 2) ? 2 : planes, r * Tp + col, v[c]);
         if (p_drop != nullptr) {
           float k8[8];
           const uint64_t idx = static_cast<uint64_t>(r) * Tp + col;
