@@ -84,4 +84,6 @@ class Device_Prefetcher:
             except StopIteration:
                 pass
             prev_slot = slot
+            for buf in self._slots[slot].values():
+                buf.record_stream(cur)     # the buffers were allocated under the copy stream; the step reads them here
             yield moved
