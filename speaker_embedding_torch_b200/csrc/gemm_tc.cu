@@ -29,7 +29,9 @@ constexpr int UMMA_K = 16;
 constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in limit per CTA
 constexpr int BAR_BYTES = 256;
 constexpr int NUM_EPI_WARPS = 8;         // two warps per TMEM lane quarter, alternating 32-column chunks
-constexpr int EPI_SMEM = NUM_EPI_WARPS * 2176;
+constexpr int EPI_STAGE_BYTES = 2176;    // per warp: bf16 tile 32 x 32 (2 KB) or fp32 tile 32 x 17
+constexpr int EPI_BIAS_BYTES = 512;      // per warp: the bias of its (up to four) 32-column chunks of the current tile
+constexpr int EPI_SMEM = NUM_EPI_WARPS * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
 
 struct GemmKernelArgs {
   CUtensorMap a_map[3];
@@ -59,8 +61,6 @@ struct TileCfg {
 // a per-warp shared-memory tile (32 rows x 64 B, 16-B chunks XOR-swizzled so that both the "lane owns a
 // row" and the "8 lanes cover 2 rows x 64 B" access patterns are bank-conflict free), so each warp
 // memory instruction touches 8 rows x 64 contiguous bytes (full 32-B sectors).
-constexpr int EPI_STAGE_BYTES = 2176;    // per warp: bf16 tile 32 x 32 (2 KB) or fp32 tile 32 x 17
-
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
@@ -258,7 +258,7 @@ __device__ __forceinline__ void colsum_tile(uint32_t stage, int lane, float* col
 // CT: compile-time superset of the flags that can be set for this launch -- everything outside CT is dead code, which
 // keeps the common forward epilogues (bias / ReLU only) short (the epilogue is instruction-issue bound).
 template <uint32_t CT>
-__device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage, int lane, int M, int N,
+__device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage, uint32_t bias_s, int lane, int M, int N,
                                            int64_t row0, int64_t batch, int64_t out_boff, const CoopIO& io_out,
                                            const CoopIO& io_res, const CoopIO& io_gate, int64_t cs_boff, int col0,
                                            const uint32_t (&acc)[32], float pe_alpha) {
@@ -273,22 +273,12 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
   }
-  if (f & EPI_BIAS) {
-    const float4* bp = reinterpret_cast<const float4*>(e.bias + col0);
-    if (col0 + 32 <= N) {          // warp-uniform: whole chunk inside the matrix
+  if (f & EPI_BIAS) {   // staged in shared memory before the accumulator wait (zeros past N); same address in all lanes
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b = __ldg(bp + i);
-        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (col0 + 4 * i < N) {
-          const float4 b = __ldg(bp + i);
-          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-        }
-      }
+    for (int i = 0; i < 8; ++i) {
+      float4 b;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_s + i * 16));
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
     }
   }
   if (f & EPI_RELU) {
@@ -364,7 +354,7 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
 
 // All 32-column chunks of one accumulator tile that belong to this warp.
 template <uint32_t CT, int BLOCK_N>
-__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t stage_buf, int lane, int cgroup,
+__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t stage_buf, uint32_t bias_buf, int lane, int cgroup,
                                               uint32_t t_row, int M, int N, int64_t row0, int64_t batch, int64_t out_boff,
                                               int64_t res_boff, int64_t cs_boff, int tn, float pe_alpha) {
   const CoopIO io_out = make_coop(lane, out_boff, row0, e.out_ld, M, (e.flags & EPI_OUT_F32) ? 4 : 8);
@@ -382,7 +372,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t st
     uint32_t r[32];
     tmem_ld_32x32(t_row + c * 32, r);
     tmem_ld_wait();
-    epilogue32<CT>(e, stage_buf, lane, M, N, row0, batch, out_boff, io_out, io_res, io_gate, cs_boff, col0, r, pe_alpha);
+    epilogue32<CT>(e, stage_buf, bias_buf + (c >> 1) * 128, lane, M, N, row0, batch, out_boff, io_out, io_res, io_gate,
+                   cs_boff, col0, r, pe_alpha);
   }
 }
 
@@ -532,6 +523,8 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
     const int cgroup = (warp - 4) >> 2;    // this warp handles the 32-column chunks with (c & 1) == cgroup
     const GemmEpilogue& e = args.epi;
     const float pe_alpha = (e.flags & EPI_PE) ? __ldg(e.pe_alpha) : 0.f;
+    const uint32_t stage_buf = epi_stage_base + (warp - 4) * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
+    const uint32_t bias_buf = stage_buf + EPI_STAGE_BYTES;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int t = tile;
@@ -541,25 +534,33 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
       const int i0 = t % args.nb0, i1 = t / args.nb0;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      if (e.flags & EPI_BIAS) {   // bias of this warp's chunks (cgroup + 2 j) -> shared memory, before the accumulator is due
+        const int j = lane >> 3;
+        const int cloc = cgroup * 32 + j * 64;
+        const int col = tn * BLOCK_N + cloc + (lane & 7) * 4;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cloc < BLOCK_N && col < args.N) b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_buf + lane * 16), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+        __syncwarp();
+      }
       mbar_wait(tfull_bar(acc), acc_phase, 0x400u + acc);
       tc_fence_after();
       const int64_t row0 = static_cast<int64_t>(tm) * BLOCK_M + w * 32;
       const int64_t out_boff = i0 * e.out_sb0 + i1 * e.out_sb1;
       const int64_t res_boff = i0 * e.res_sb0 + i1 * e.res_sb1;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BLOCK_N;
-      const uint32_t stage_buf = epi_stage_base + (warp - 4) * EPI_STAGE_BYTES;
       const int64_t cs_boff = i0 * e.colsum_sb0;
       if (row0 < args.M) {   // warp-uniform
         constexpr uint32_t CT_LEAN = EPI_BIAS | EPI_RELU | EPI_OUT_F32;
         constexpr uint32_t CT_FWD = CT_LEAN | EPI_PE | EPI_DROPOUT | EPI_RES;
         if ((e.flags & ~CT_LEAN) == 0)
-          epilogue_tile<CT_LEAN, BLOCK_N>(e, stage_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
+          epilogue_tile<CT_LEAN, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
                                           cs_boff, tn, pe_alpha);
         else if ((e.flags & ~CT_FWD) == 0)
-          epilogue_tile<CT_FWD, BLOCK_N>(e, stage_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
+          epilogue_tile<CT_FWD, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
                                          cs_boff, tn, pe_alpha);
         else
-          epilogue_tile<0xFFFFFFFFu, BLOCK_N>(e, stage_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff,
+          epilogue_tile<0xFFFFFFFFu, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff,
                                               res_boff, cs_boff, tn, pe_alpha);
       }
       tc_fence_before();
