@@ -136,40 +136,49 @@ __device__ __forceinline__ void load_aux_tile(uint32_t stage, int lane, const vo
   }
 }
 
-// out[row0 + lane][col0 .. col0+31] = v (split planes), coalesced through the staging tile
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 w;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(addr) : "memory");
+  return w;
+}
+
+// out[row0 + lane][col0 .. col0+31] = v (split planes), coalesced through the staging tile.
+// All 16 packed words / all four 16-byte rows live in distinct registers, so the four shared stores, the four shared
+// loads and the four global stores of a plane issue back to back (ncu r01: with re-used registers every STS / LDS
+// waited for the previous one to release its operands).
 __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void* base_v, int64_t ps, int planes,
                                                  const CoopIO& io, int col0, int N, float (&v)[32]) {
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(base_v) + io.off0 + col0;
   const bool col_ok = col0 + (lane & 3) * 8 < N;
+  const uint32_t own = stage + lane * 64, sw = ((lane >> 1) & 3) << 4;   // own + ((cc << 4) ^ sw) == stage_off(lane, cc)
+  const uint32_t coop = stage + stage_off(lane >> 2, lane & 3);          // + it * 512: the swizzle term does not depend on it
   for (int p = 0; p < planes; ++p) {
     const bool more = p + 1 < planes;   // the residual is only needed if another plane follows
+    uint32_t w[16];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      uint32_t w[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 q = __floats2bfloat162_rn(v[cc * 8 + 2 * i], v[cc * 8 + 2 * i + 1]);
-        w[i] = *reinterpret_cast<uint32_t*>(&q);
-        if (more) {
-          v[cc * 8 + 2 * i] -= bf16lo_to_f(w[i]);
-          v[cc * 8 + 2 * i + 1] -= bf16hi_to_f(w[i]);
-        }
-      }
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(lane, cc)), "r"(w[0]),
-                   "r"(w[1]), "r"(w[2]), "r"(w[3])
-                   : "memory");
+    for (int i = 0; i < 16; ++i) {
+      __nv_bfloat162 q = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&q);
     }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) sts128(own + ((cc << 4) ^ sw), w[4 * cc], w[4 * cc + 1], w[4 * cc + 2], w[4 * cc + 3]);
     __syncwarp();
+    uint4 o[4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      uint32_t w0, w1, w2, w3;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                   : "r"(stage + stage_off(it * 8 + (lane >> 2), lane & 3))
-                   : "memory");
-      if (col_ok && ((io.rowmask >> it) & 1u))
-        *reinterpret_cast<uint4*>(base + p * ps + it * io.ld8) = make_uint4(w0, w1, w2, w3);
+    for (int it = 0; it < 4; ++it) o[it] = lds128(coop + it * 512);
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[2 * i] -= bf16lo_to_f(w[i]);
+        v[2 * i + 1] -= bf16hi_to_f(w[i]);
+      }
     }
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+      if (col_ok && ((io.rowmask >> it) & 1u)) *reinterpret_cast<uint4*>(base + p * ps + it * io.ld8) = o[it];
     __syncwarp();
   }
 }
@@ -180,26 +189,22 @@ __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void*
 __device__ __forceinline__ void store_f32_tile_plain(uint32_t stage, int lane, float* base_f, const CoopIO& io, int col0,
                                                      int N, const float (&v)[32]) {
   float* base = base_f + io.off0 + col0;
+  const uint32_t own = stage + lane * 64, sw = ((lane >> 1) & 3) << 4;
+  const uint32_t coop = stage + stage_off(lane >> 2, lane & 3);
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_off(lane, cc)),
-                   "r"(__float_as_uint(v[h * 16 + cc * 4])), "r"(__float_as_uint(v[h * 16 + cc * 4 + 1])),
-                   "r"(__float_as_uint(v[h * 16 + cc * 4 + 2])), "r"(__float_as_uint(v[h * 16 + cc * 4 + 3]))
-                   : "memory");
+      sts128(own + ((cc << 4) ^ sw), __float_as_uint(v[h * 16 + cc * 4]), __float_as_uint(v[h * 16 + cc * 4 + 1]),
+             __float_as_uint(v[h * 16 + cc * 4 + 2]), __float_as_uint(v[h * 16 + cc * 4 + 3]));
     __syncwarp();
     const bool col_ok = col0 + h * 16 + (lane & 3) * 4 < N;
+    uint4 o[4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      uint32_t w0, w1, w2, w3;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                   : "r"(stage + stage_off(it * 8 + (lane >> 2), lane & 3))
-                   : "memory");
-      if (col_ok && ((io.rowmask >> it) & 1u))
-        *reinterpret_cast<uint4*>(base + h * 16 + it * io.ld8) = make_uint4(w0, w1, w2, w3);
-    }
+    for (int it = 0; it < 4; ++it) o[it] = lds128(coop + it * 512);
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+      if (col_ok && ((io.rowmask >> it) & 1u)) *reinterpret_cast<uint4*>(base + h * 16 + it * io.ld8) = o[it];
     __syncwarp();
   }
 }
