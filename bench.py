@@ -69,6 +69,7 @@ class ClockSampler:
         self.index, self.rows, self.proc, self.thread = index, [], None, None
         self.stop = threading.Event()
         self.nvml = None
+        self.err = None
 
     def _handle(self):
         import pynvml
@@ -81,32 +82,39 @@ class ClockSampler:
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
         return pynvml, h
 
-    def _poll(self, pynvml, h):
+    def sample(self):
+        """One NVML reading now (also called from the main thread while the GPU is still busy with the timed steps, so a
+        starved polling thread cannot leave the line without clocks)."""
+        if self.nvml is None:
+            return
+        pynvml, h = self.nvml, self.h
         try:
-            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            mx = None
-        while not self.stop.is_set():
+            if self.mx is None:
+                self.mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
             try:
-                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                try:
-                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append((float(sm), float(mx) if mx else None, int(mask)))
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
             except Exception:
-                pass
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append((float(sm), float(self.mx) if self.mx else None, int(mask)))
+        except Exception as ex:      # keep polling; the summary reports the last error if nothing was sampled
+            self.err = repr(ex)
+
+    def _poll(self):
+        while not self.stop.is_set():
+            self.sample()
             self.stop.wait(0.005)
 
     def __enter__(self):
         try:
             pynvml, h = self._handle()
-            self.nvml = pynvml
-            self.thread = threading.Thread(target=self._poll, args=(pynvml, h), daemon=True)
+            self.nvml, self.h, self.mx = pynvml, h, None
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
             return self
-        except Exception:
+        except Exception as ex:
             self.nvml = None
+            self.err = repr(ex)
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -143,7 +151,7 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": self.err}
         sm = [r[0] for r in self.rows]
         mx = [r[1] for r in self.rows if r[1]]
         mask = 0
@@ -295,6 +303,7 @@ def run_native(args):
         for i in range(K):
             loss = step(dev_mels[W + i])
         e1.record()
+        clk.sample()                        # the queue is still draining: a reading inside the timed region
         barrier()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device=dev)
@@ -461,7 +470,6 @@ def run_infer(args):
     windows = synth_mel(gen, utt, S * (F - O) + O, dev)                      # [utt, 80, 192]
     # the collater's overlapping slices (stride F - O), utterance-major rows
     chunk = torch.stack([windows[:, :, i * (F - O):i * (F - O) + F] for i in range(S)], dim=1).reshape(utt * S, MEL, F).contiguous()
-    host = chunk.cpu().pin_memory()
 
     def barrier():
         if world > 1:
@@ -477,17 +485,27 @@ def run_infer(args):
             for _ in range(K):
                 out = model(chunk, S)
             e1.record()
+            clk.sample()
             barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        # end to end: the un-sliced 192-frame windows cross PCIe (pinned host -> Device_Prefetcher, next chunk in flight
+        # while this one is embedded), the collater's overlapping slices are cut on the device, d-vectors come back
+        from speaker_embedding_torch_b200.Modules import Overlapped_Slices
+        from speaker_embedding_torch_b200.Prefetch import Device_Prefetcher
+        host_windows = windows.cpu().pin_memory()
+        assert torch.equal(Overlapped_Slices(windows, F, O), chunk)
+        feeder = Device_Prefetcher([host_windows] * K, dev, reserve_bytes=host_windows.numel() * 4)
+        host_out = [torch.empty(utt, 256).pin_memory() for _ in range(K)]       # d-vectors land here, no per-step sync
         barrier()
         e0.record()
-        for _ in range(K):
-            o = model(host.to(dev, non_blocking=True), S).cpu()
+        for i, w in enumerate(feeder):
+            host_out[i].copy_(model(Overlapped_Slices(w, F, O), S), non_blocking=True)
         e1.record()
         barrier()
+        assert abs(float(host_out[-1].sum()) - float(out.float().sum().item())) < 1e-2 * utt
         t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
@@ -503,7 +521,7 @@ def run_infer(args):
                        "parallelism": "dp%d (utterance shards, no collective)" % world},
             "clocks": clk.summary(),
             "e2e": {"value": world * K * utt / (float(t2.item()) * 1e-3), "unit": "utterances/s",
-                    "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": utt * 256 * 4},
+                    "h2d_bytes_per_step": host_windows.numel() * 4, "d2h_bytes_per_step": utt * 256 * 4},
             "extra": {"tensor_frac_of_sustained": flops * K / (ms * 1e-3) / 1e12 / pk["tf_sus"],
                       "dvec_checksum": float(out.float().sum().item())},
         }))

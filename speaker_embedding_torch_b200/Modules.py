@@ -286,6 +286,24 @@ def _names_for(layers):
 # ------------------------------------------------------------------------------------------------
 # loss
 
+def Overlapped_Slices(windows: torch.Tensor, frame_length: int, overlap_length: int) -> torch.Tensor:
+    """Device-side form of the inference collater's slicing (Inference.py:95-115): ``windows`` is
+    ``[Utterances, Mel_Dim, samples * (frame_length - overlap_length) + overlap_length]`` (what ``Correction``
+    produces), the result is ``[Utterances * samples, Mel_Dim, frame_length]`` in utterance-major order, ready for
+    ``GE2E.forward(features, samples)``.  Sending the un-sliced windows over PCIe and slicing here moves
+    ``required_length`` instead of ``samples * frame_length`` frames per utterance (192 instead of 320 for the
+    reference's 5 x 64 / 32 configuration)."""
+    if windows.dim() != 3:
+        raise RuntimeError("windows must be [Utterances, Mel_Dim, Time], got %s" % (tuple(windows.shape),))
+    hop = frame_length - overlap_length
+    if hop <= 0 or windows.size(2) < frame_length:
+        raise RuntimeError("invalid slicing: frame_length %d, overlap_length %d, window %d"
+                           % (frame_length, overlap_length, windows.size(2)))
+    samples = (windows.size(2) - overlap_length) // hop
+    sl = windows.unfold(2, frame_length, hop)[:, :, :samples]            # [U, Mel, samples, frame_length] (view)
+    return sl.permute(0, 2, 1, 3).reshape(windows.size(0) * samples, windows.size(1), frame_length)
+
+
 class _GE2ELossFunction(torch.autograd.Function):
     """Loss and gradients from ONE fused kernel launch (spk_ge2e_loss); backward only rescales."""
 

@@ -119,3 +119,21 @@ def test_arg_parser_contract():
     from speaker_embedding_torch_b200.Arg_Parser import Recursive_Parse
     hp = Recursive_Parse({"A": {"B": {"C": 3}}, "D": [1, 2], "E": "x"})
     assert hp.A.B.C == 3 and hp.D == [1, 2] and hp.E == "x"
+
+
+def test_overlapped_slices_match_the_collater():
+    """Device-side slicing == the reference collater's np.stack of strided windows (Inference.py:103-110)."""
+    import numpy as np
+    import torch
+    from speaker_embedding_torch_b200.Modules import Overlapped_Slices
+    rs = np.random.RandomState(0)
+    frame, overlap, samples = 64, 32, 5
+    required = samples * (frame - overlap) + overlap
+    feats = [rs.randn(80, required).astype(np.float32) for _ in range(3)]
+    ref = np.vstack([np.stack([f[:, i:i + frame] for i in range(0, required - overlap, frame - overlap)]) for f in feats])
+    got = Overlapped_Slices(torch.from_numpy(np.stack(feats)), frame, overlap)
+    assert got.shape == (3 * samples, 80, frame)
+    assert np.array_equal(got.numpy(), ref)
+    import pytest
+    with pytest.raises(RuntimeError):
+        Overlapped_Slices(torch.zeros(2, 80, 32), 64, 32)
