@@ -495,17 +495,20 @@ def run_infer(args):
         # while this one is embedded), the collater's overlapping slices are cut on the device, d-vectors come back
         from speaker_embedding_torch_b200.Modules import Overlapped_Slices
         from speaker_embedding_torch_b200.Prefetch import Device_Prefetcher
-        host_windows = windows.cpu().pin_memory()
+        # patterns travel as the reference stores them (fp16, Pattern_Generator.py:123); slicing and the upcast happen
+        # inside the prenet's input load (GE2E.embed_windows -> spk_encoder_forward_view)
+        host_windows = windows.half().cpu().pin_memory()
         assert torch.equal(Overlapped_Slices(windows, F, O), chunk)
-        feeder = Device_Prefetcher([host_windows] * K, dev, reserve_bytes=host_windows.numel() * 4)
+        feeder = Device_Prefetcher([host_windows] * K, dev, reserve_bytes=host_windows.numel() * 2)
         host_out = [torch.empty(utt, 256).pin_memory() for _ in range(K)]       # d-vectors land here, no per-step sync
+        model.embed_windows(windows.half(), F, O)                               # warm-up of the fp16 load
         barrier()
         e0.record()
         for i, w in enumerate(feeder):
-            host_out[i].copy_(model(Overlapped_Slices(w, F, O), S), non_blocking=True)
+            host_out[i].copy_(model.embed_windows(w, F, O), non_blocking=True)
         e1.record()
         barrier()
-        assert abs(float(host_out[-1].sum()) - float(out.float().sum().item())) < 1e-2 * utt
+        assert abs(float(host_out[-1].sum()) - float(out.float().sum().item())) < 2e-2 * utt   # fp16 patterns
         t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
@@ -521,7 +524,7 @@ def run_infer(args):
                        "parallelism": "dp%d (utterance shards, no collective)" % world},
             "clocks": clk.summary(),
             "e2e": {"value": world * K * utt / (float(t2.item()) * 1e-3), "unit": "utterances/s",
-                    "h2d_bytes_per_step": host_windows.numel() * 4, "d2h_bytes_per_step": utt * 256 * 4},
+                    "h2d_bytes_per_step": host_windows.numel() * 2, "d2h_bytes_per_step": utt * 256 * 4},
             "extra": {"tensor_frac_of_sustained": flops * K / (ms * 1e-3) / 1e12 / pk["tf_sus"],
                       "dvec_checksum": float(out.float().sum().item())},
         }))

@@ -84,6 +84,23 @@ int spk_encoder_forward(const spk_encoder_config* cfg, const spk_encoder_params*
                         int batch, int frames, int samples, int precision, int training, uint64_t seed,
                         float* dvec, void* workspace, size_t workspace_bytes, int keep_stash, void* stream);
 
+/* The same forward over a strided view of the input, so that the inference collater's work (Inference.py:95-115:
+ * five overlapping 64-frame slices cut from a 192-frame window, fp16 patterns upcast to fp32) happens inside the
+ * prenet's input load instead of on the host and on PCIe:
+ *   slice b = (window u = b / slices_per_window, s = b % slices_per_window) is frames [s*hop, s*hop + frames) of
+ *   window u; data is [batch / slices_per_window, mel_dim, window_frames] in `dtype` (0 = fp32, 1 = fp16).
+ * slices_per_window == 1, hop == 0, window_frames == frames describes the plain [batch, mel_dim, frames] input. */
+typedef struct spk_mel_view {
+  const void* data;
+  int32_t dtype;             /* 0 = fp32, 1 = fp16 */
+  int32_t window_frames;     /* frames per window (row stride of a mel channel) */
+  int32_t hop;               /* frames between consecutive slices of a window */
+  int32_t slices_per_window; /* >= 1; batch must be a multiple of it */
+} spk_mel_view;
+int spk_encoder_forward_view(const spk_encoder_config* cfg, const spk_encoder_params* weights, const spk_mel_view* mel,
+                             int batch, int frames, int samples, int precision, int training, uint64_t seed,
+                             float* dvec, void* workspace, size_t workspace_bytes, int keep_stash, void* stream);
+
 /* Backward of the call above (same cfg/shape/precision/training/seed/workspace).  Accumulates
  * (+=) into `grads`, which the caller zero-initialises; replaces autograd through Modules.py:46-59. */
 int spk_encoder_backward(const spk_encoder_config* cfg, const spk_encoder_params* weights,

@@ -115,15 +115,28 @@ def _aligned_ptr(ws):
     return ctypes.c_void_p((base + 255) // 256 * 256)
 
 
-def _run_forward(cfg, names, params, pe, features, samples, precision, training, seed, keep):
+def _run_forward(cfg, names, params, pe, features, samples, precision, training, seed, keep, slicing=None):
+    """One spk_encoder_forward_view call.  ``features`` is ``[Batch*Samples, Mel_Dim, Time]`` (fp32 or fp16: the
+    reference stores its patterns as fp16, the upcast happens in the prenet load), or -- with
+    ``slicing = (frame_length, hop, slices_per_window)`` -- un-sliced windows ``[Utterances, Mel_Dim, L]`` whose
+    overlapping slices are cut by the same load."""
     N.require_cuda(features, "features")
-    if features.dtype != torch.float32:
+    if features.dtype not in (torch.float32, torch.float16):
         features = features.float()
     features = features.contiguous()
     if features.dim() != 3 or features.size(1) != cfg.mel_dim:
         raise RuntimeError("features must be [Batch*Samples, Mel_Dim=%d, Time], got %s"
                            % (cfg.mel_dim, tuple(features.shape)))
-    batch, _, frames = features.shape
+    if slicing is None:
+        batch, _, frames = features.shape
+        window, hop, spw = frames, 0, 1
+    else:
+        frames, hop, spw = (int(v) for v in slicing)
+        window = features.size(2)
+        batch = features.size(0) * spw
+        if spw < 1 or hop < 0 or (spw - 1) * hop + frames > window:
+            raise RuntimeError("invalid slicing: %d slices of %d frames at hop %d from a %d-frame window"
+                               % (spw, frames, hop, window))
     if samples < 1 or batch % samples != 0:
         raise RuntimeError("shape '[-1, %d, ...]' is invalid for a batch of %d slices" % (samples, batch))
     tensors = {}
@@ -136,10 +149,12 @@ def _run_forward(cfg, names, params, pe, features, samples, precision, training,
         weights = _fill_params(N.EncoderParams(), tensors, pe, cfg.layers)
         ws, nbytes = _workspace(cfg, batch, frames, samples, precision, int(keep), features.device)
         dvec = torch.empty((batch // samples, cfg.emb), dtype=torch.float32, device=features.device)
-        N.check(N.lib().spk_encoder_forward(ctypes.byref(cfg), ctypes.byref(weights), N.ptr(features), batch, frames,
-                                            samples, precision, int(training), ctypes.c_uint64(seed), N.ptr(dvec),
-                                            _aligned_ptr(ws), nbytes, int(keep), N.stream_ptr(features.device)),
-                "spk_encoder_forward")
+        view = N.MelView(features.data_ptr(), 1 if features.dtype == torch.float16 else 0, window, hop, spw)
+        N.check(N.lib().spk_encoder_forward_view(ctypes.byref(cfg), ctypes.byref(weights), ctypes.byref(view), batch,
+                                                 frames, samples, precision, int(training), ctypes.c_uint64(seed),
+                                                 N.ptr(dvec), _aligned_ptr(ws), nbytes, int(keep),
+                                                 N.stream_ptr(features.device)),
+                "spk_encoder_forward_view")
     return dvec, ws, nbytes, (batch, frames)
 
 
@@ -249,6 +264,30 @@ class GE2E(torch.nn.Module):
                                               samples, self.eval_precision, self.max_slices_per_call,
                                               self._cfg.mel_dim, self._cfg.emb, self._cfg.heads, self._cfg.layers,
                                               self._cfg.max_pos)
+
+
+    def embed_windows(self, windows, frame_length, overlap_length):
+        """Multi-slice d-vectors straight from un-sliced windows (the device-side form of Inference.py:95-115 +
+        157-159): ``windows`` is ``[Utterances, Mel_Dim, samples*(frame_length-overlap_length)+overlap_length]``,
+        fp32 or fp16; the overlapping slices are cut inside the prenet's input load (no sliced copy exists) and
+        their embeddings are averaged per utterance.  Returns ``[Utterances, Emb_dim]``.  eval() only."""
+        if self.training:
+            raise RuntimeError("GE2E.embed_windows is an inference entry point; call eval()")
+        hop = int(frame_length) - int(overlap_length)
+        if windows.dim() != 3 or hop <= 0 or windows.size(2) < frame_length:
+            raise RuntimeError("invalid slicing: frame_length %d, overlap_length %d, windows %s"
+                               % (frame_length, overlap_length, tuple(windows.shape)))
+        spw = (windows.size(2) - int(overlap_length)) // hop
+        params = [p.detach() for p in self.parameters()]
+        pe = self.positional_encoding.pe
+        per_call = max(1, self.max_slices_per_call // spw)
+        outs = []
+        with torch.no_grad():
+            for u in range(0, windows.size(0), per_call):
+                outs.append(_run_forward(self._cfg, self._param_names, params, pe, windows[u:u + per_call], spw,
+                                         self.eval_precision, False, 0, keep=False,
+                                         slicing=(int(frame_length), hop, spw))[0])
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
 
 @torch.library.custom_op("spkemb::encoder_infer", mutates_args=())

@@ -22,10 +22,16 @@ EXPORTS = (
     "spk_abi_version", "spk_last_error", "spk_encoder_workspace_bytes", "spk_encoder_forward",
     "spk_encoder_backward", "spk_ge2e_workspace_bytes", "spk_ge2e_loss", "spk_optim_step",
     "spk_gemm", "spk_split_pack", "spk_device_info", "spk_prof_enable", "spk_prof_report",
-    "spk_encoder_debug_layout", "spk_set_option",
+    "spk_encoder_debug_layout", "spk_set_option", "spk_encoder_forward_view",
 )
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
+
+
+class MelView(ctypes.Structure):
+    """spk_mel_view: strided / fp16 view of the mel input (overlapping inference slices cut inside the prenet load)."""
+    _fields_ = [("data", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("window_frames", ctypes.c_int32),
+                ("hop", ctypes.c_int32), ("slices_per_window", ctypes.c_int32)]
 
 
 class EncoderConfig(ctypes.Structure):
@@ -110,6 +116,10 @@ def lib():
         L.spk_encoder_forward.restype = i32
         L.spk_encoder_forward.argtypes = [ctypes.POINTER(EncoderConfig), ctypes.POINTER(EncoderParams), vp,
                                           i32, i32, i32, i32, i32, u64, vp, vp, sz, i32, vp]
+        L.spk_encoder_forward_view.restype = i32
+        L.spk_encoder_forward_view.argtypes = [ctypes.POINTER(EncoderConfig), ctypes.POINTER(EncoderParams),
+                                               ctypes.POINTER(MelView), i32, i32, i32, i32, i32, u64, vp, vp, sz,
+                                               i32, vp]
         L.spk_encoder_backward.restype = i32
         L.spk_encoder_backward.argtypes = [ctypes.POINTER(EncoderConfig), ctypes.POINTER(EncoderParams),
                                            ctypes.POINTER(EncoderParams), vp, i32, i32, i32, i32, i32, u64,

@@ -25,7 +25,17 @@ int spk_encoder_forward(const spk_encoder_config* cfg, const spk_encoder_params*
                         int frames, int samples, int precision, int training, uint64_t seed, float* dvec,
                         void* workspace, size_t workspace_bytes, int keep_stash, void* stream) {
   SPK_CHECK(cfg && weights && mel && dvec && workspace, "spk_encoder_forward: null argument");
-  return encoder_forward(*cfg, *weights, mel, batch, frames, samples, precision, training, seed, dvec, workspace,
+  spk_mel_view view;
+  view.data = mel; view.dtype = 0; view.window_frames = frames; view.hop = 0; view.slices_per_window = 1;
+  return encoder_forward(*cfg, *weights, view, batch, frames, samples, precision, training, seed, dvec, workspace,
+                         workspace_bytes, keep_stash, as_stream(stream));
+}
+
+int spk_encoder_forward_view(const spk_encoder_config* cfg, const spk_encoder_params* weights, const spk_mel_view* mel,
+                             int batch, int frames, int samples, int precision, int training, uint64_t seed,
+                             float* dvec, void* workspace, size_t workspace_bytes, int keep_stash, void* stream) {
+  SPK_CHECK(cfg && weights && mel && mel->data && dvec && workspace, "spk_encoder_forward_view: null argument");
+  return encoder_forward(*cfg, *weights, *mel, batch, frames, samples, precision, training, seed, dvec, workspace,
                          workspace_bytes, keep_stash, as_stream(stream));
 }
 

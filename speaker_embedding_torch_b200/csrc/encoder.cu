@@ -395,7 +395,7 @@ static void fill_pack_table(const Plan& pl, const spk_encoder_params& w, PackTab
   tab.count = n;
 }
 
-int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, const float* mel, int B, int T, int S,
+int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, const spk_mel_view& mel, int B, int T, int S,
                     int P, int training, uint64_t seed, float* dvec, void* ws_v, size_t ws_bytes, int keep,
                     cudaStream_t st) {
   Plan pl;

@@ -3,6 +3,8 @@
 // reductions; rows of the 256-wide model dimension are handled one warp per row (8 elements / lane).
 #include "rowops.h"
 
+#include <cuda_fp16.h>
+
 namespace spk {
 
 // ------------------------------------------------------------------------------------------------
@@ -24,17 +26,19 @@ int pack_weights(const PackTable& tab, void* dst, int64_t plane_stride, int plan
 }
 
 // ------------------------------------------------------------------------------------------------
-// mel [B, C, T] fp32 (frames contiguous)  ->  token-major split tensor [B*T, C]   (C % 8 == 0)
-template <int C>
-__global__ void mel_pack_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ out, int64_t plane_stride,
-                                int planes, int T) {
+// mel view -> token-major split tensor [B*T, C]   (C % 8 == 0).  Slice b = window b / spw, frames
+// [ (b % spw) * hop, + T ) of a [windows, C, L] tensor in fp32 or fp16 (frames contiguous): the overlapping-slice
+// collation and the fp16 -> fp32 upcast of the reference's inference collater happen in this load.
+template <int C, typename TIn>
+__global__ void mel_pack_kernel(const TIn* __restrict__ mel, __nv_bfloat16* __restrict__ out, int64_t plane_stride,
+                                int planes, int T, int L, int hop, int spw) {
   __shared__ float tile[C][33];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 32;
-  const float* src = mel + static_cast<int64_t>(b) * C * T;
+  const TIn* src = mel + static_cast<int64_t>(b / spw) * C * L + static_cast<int64_t>(b % spw) * hop;
   for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
     const int c = i >> 5, tl = i & 31;
-    tile[c][tl] = (t0 + tl < T) ? __ldg(src + static_cast<int64_t>(c) * T + t0 + tl) : 0.f;
+    tile[c][tl] = (t0 + tl < T) ? static_cast<float>(__ldg(src + static_cast<int64_t>(c) * L + t0 + tl)) : 0.f;
   }
   __syncthreads();
   constexpr int G = C / 8;
@@ -47,11 +51,24 @@ __global__ void mel_pack_kernel(const float* __restrict__ mel, __nv_bfloat16* __
     store8_split(out, plane_stride, planes, (static_cast<int64_t>(b) * T + t0 + tl) * C + g * 8, v);
   }
 }
-int mel_pack(const float* mel, void* out, int64_t plane_stride, int planes, int B, int C, int T, cudaStream_t st) {
-  ProfScope prof("mel_pack", 0, 1.0 * B * C * T * (4.0 + 2.0 * planes), st);
+int mel_pack(const spk_mel_view& mel, void* out, int64_t plane_stride, int planes, int B, int C, int T, cudaStream_t st) {
+  const double in_b = mel.dtype == 1 ? 2.0 : 4.0;
+  ProfScope prof("mel_pack", 0, 1.0 * B * C * T * (in_b + 2.0 * planes), st);
   SPK_CHECK(C == 80, "mel_pack: Mel_Dim %d not supported by this build (80)", C);
+  SPK_CHECK(mel.data != nullptr && (mel.dtype == 0 || mel.dtype == 1), "mel view: dtype must be 0 (fp32) or 1 (fp16)");
+  SPK_CHECK(mel.slices_per_window >= 1 && B % mel.slices_per_window == 0 && mel.hop >= 0,
+            "mel view: batch %d is not a multiple of slices_per_window %d", B, mel.slices_per_window);
+  SPK_CHECK(static_cast<int64_t>(mel.slices_per_window - 1) * mel.hop + T <= mel.window_frames,
+            "mel view: %d slices of %d frames at hop %d do not fit a %d-frame window", mel.slices_per_window, T, mel.hop,
+            mel.window_frames);
   dim3 grid((T + 31) / 32, B);
-  mel_pack_kernel<80><<<grid, 256, 0, st>>>(mel, reinterpret_cast<__nv_bfloat16*>(out), plane_stride, planes, T);
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (mel.dtype == 0)
+    mel_pack_kernel<80, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(mel.data), o, plane_stride, planes, T,
+                                                     mel.window_frames, mel.hop, mel.slices_per_window);
+  else
+    mel_pack_kernel<80, __half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(mel.data), o, plane_stride, planes,
+                                                      T, mel.window_frames, mel.hop, mel.slices_per_window);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,6 +1,7 @@
 // Bandwidth-bound building blocks of the encoder (see rowops.cu).
 #pragma once
 #include <algorithm>
+#include "../../include/spkemb.h"
 #include "common.cuh"
 
 namespace spk {
@@ -16,7 +17,8 @@ struct PackTable {
 };
 
 int pack_weights(const PackTable& tab, void* dst, int64_t plane_stride, int planes, cudaStream_t st);
-int mel_pack(const float* mel, void* out, int64_t plane_stride, int planes, int B, int C, int T, cudaStream_t st);
+// mel view (include/spkemb.h spk_mel_view) -> token-major split tensor [B*T, C]
+int mel_pack(const spk_mel_view& mel, void* out, int64_t plane_stride, int planes, int B, int C, int T, cudaStream_t st);
 int pe_transpose(const float* pe, float* pe_t, int D, int max_pos, int T, cudaStream_t st);
 
 // y[r] = LN(z[r * z_row_step]) over 256 columns; stats[r] = (mean, rstd) (may be null)

@@ -253,3 +253,52 @@ def test_fused_inference_attention_matches_unfused_and_oracle(frames):
     for fused in (1, 0):
         assert _cos(out[fused].cpu().numpy().astype(np.float64), ref).min() >= 0.9999, fused
     torch.testing.assert_close(out[1], out[0], atol=4e-3, rtol=0)
+
+
+def test_embed_windows_equals_host_sliced_forward():
+    """Overlapping slices cut inside the prenet load (spk_mel_view) == the reference collater's slices
+    (Inference.py:103-110) fed through forward(features, samples): bit-identical d-vectors, fp32 and fp16 windows,
+    several utterance counts (including one that is chunked by max_slices_per_call)."""
+    from speaker_embedding_torch_b200.Modules import Overlapped_Slices
+    m, _ = _model(11)
+    m.eval()
+    frame, overlap, samples = 64, 32, 5
+    required = samples * (frame - overlap) + overlap
+    for utts in (1, 7, 33):
+        windows = torch.as_tensor(synth.make_mel(300 + utts, utts, required)).cuda()
+        with torch.no_grad():
+            ref = m(Overlapped_Slices(windows, frame, overlap), samples)
+            got = m.embed_windows(windows, frame, overlap)
+            assert got.shape == (utts, 256)
+            assert torch.equal(got, ref)
+            half = windows.half()
+            ref16 = m(Overlapped_Slices(half.float(), frame, overlap), samples)
+            assert torch.equal(m.embed_windows(half, frame, overlap), ref16)
+    m.max_slices_per_call = 10                      # two utterances per call
+    with torch.no_grad():
+        assert torch.equal(m.embed_windows(windows, frame, overlap), ref)
+    with pytest.raises(RuntimeError):
+        m.embed_windows(windows[:, :, :40], frame, overlap)
+    m.train()
+    with pytest.raises(RuntimeError):
+        m.embed_windows(windows, frame, overlap)
+
+
+def test_fp16_patterns_are_upcast_in_the_prenet_load():
+    """The reference stores patterns as fp16 (Pattern_Generator.py:123) and upcasts on the host (Datasets.py:84);
+    here fp16 features go to the device as they are: same d-vectors and gradients as the host-upcast input."""
+    from speaker_embedding_torch_b200 import GE2E_Loss
+    m, _ = _model(12)
+    mel16 = torch.as_tensor(synth.make_mel(120, 4 * 3, 50)).cuda().half()
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(mel16), m(mel16.float()))
+    crit = GE2E_Loss().cuda()
+    grads = []
+    for x in (mel16, mel16.float()):
+        m.zero_grad(set_to_none=True)
+        crit(m(x), 3).backward()
+        grads.append(torch.cat([p.grad.flatten() for p in m.parameters()]).clone())
+    # same inputs after the upcast; the split-K weight gradients use fp32 atomics, so not bit-for-bit
+    rel = float((grads[0] - grads[1]).norm() / grads[1].norm())
+    assert rel < 1e-5, rel
