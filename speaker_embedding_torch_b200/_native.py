@@ -148,6 +148,9 @@ def lib():
                                                ctypes.c_char_p, sz]
         if L.spk_abi_version() != ABI_VERSION:
             raise RuntimeError("libspkemb.so ABI %d != binding ABI %d" % (L.spk_abi_version(), ABI_VERSION))
+        for name, env in (("gemm_cta_pairs", "SPKEMB_GEMM_CTA_PAIRS"),):      # A/B switches for the benchmarks
+            if env in os.environ:
+                L.spk_set_option(name.encode(), int(os.environ[env]))
         _lib = L
     return _lib
 

@@ -74,6 +74,7 @@ struct GemmProblem {
 int gemm_run(const GemmProblem& p, cudaStream_t stream);
 
 int device_sm_count();
+void gemm_set_cta_pairs(int on);   // route eligible multi-plane GEMMs through the cta_group::2 kernel
 
 // bf16 4-D tiled tensor map {dims[0] (contiguous), dims[1], dims[2], dims[3]} with element strides for dims 1..3,
 // box {64, box_rows, 1, 1}, 128-byte swizzle, out-of-bounds elements read as zero.

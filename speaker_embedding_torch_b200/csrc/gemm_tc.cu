@@ -582,6 +582,234 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05.mma.cta_group::2): two CTAs of a cluster work on one 256 x BLOCK_N tile.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile (BLOCK_N / 2 rows), the leader (cluster rank 0) issues the
+// MMAs for both tensor cores, each CTA's accumulator half (its 128 rows x BLOCK_N columns) lands in its own TMEM and
+// is drained by its own epilogue warps.  Per SM the UMMA operand reads drop from 128 / 96 B/clk (BLOCK_N = 128 / 256
+// single-CTA tiles) to 64 B/clk, which leaves shared-memory bandwidth for the epilogue's staging round trips
+// (profiles/r01_gemm_epilogue.md), and a three-plane ring fits BLOCK_N = 256.
+//   full[s]      local TMA completion of stage s                     (each CTA, its own loads)
+//   peer_full[s] leader only: the peer's stage s is loaded           (remote arrive by the peer's relay lane)
+//   empty[s]     both CTAs, signalled by the leader's commit (multicast)
+//   tfull[a]     both CTAs, leader's commit (multicast): accumulator a complete
+//   tempty[a]    leader only: 2 x 256 epilogue threads (local + remote arrives)
+template <int PLANES, int BLOCK_N>
+struct PairCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int RAW_STAGES = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_SMEM) / STAGE_BYTES;
+  static constexpr int STAGES = RAW_STAGES > 6 ? 6 : RAW_STAGES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_SMEM;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(STAGES >= 2, "operand ring does not fit shared memory");
+  static_assert(2 * BLOCK_N <= 512 && BLOCK_N % 128 == 0, "pair tile N");
+};
+
+template <bool B_MN, int PLANES, int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1)
+    gemm_pair_kernel(const __grid_constant__ GemmKernelArgs args) {
+  using Cfg = PairCfg<PLANES, BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int HALF_N = BLOCK_N / 2;
+  constexpr uint32_t IDESC = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N, false, B_MN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+  const uint32_t epi_stage_base = bar_base + BAR_BYTES;
+  auto sA = [&](int s, int p) { return smem_base + s * Cfg::STAGE_BYTES + p * Cfg::A_BYTES; };
+  auto sB = [&](int s, int p) { return smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES + p * Cfg::B_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = static_cast<int>(cluster_id_x());
+  const int npairs = static_cast<int>(cluster_count_x());
+
+  if (warp == 0 && lane == 0) {
+#pragma unroll
+    for (int p = 0; p < PLANES; ++p) {
+      tma_prefetch_desc(&args.a_map[p]);
+      tma_prefetch_desc(&args.b_map[p]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(pfull_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * 32 * NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                      // barriers of both CTAs exist before any remote arrive / multicast commit
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles_per_batch = args.tiles_m * args.tiles_n;       // tiles_m counts 256-row tiles here
+  const int total_tiles = args.nb0 * args.nb1 * tiles_per_batch;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        int t = tile;
+        const int tn = t % args.tiles_n; t /= args.tiles_n;
+        const int tm = t % args.tiles_m; t /= args.tiles_m;
+        const int i0 = t % args.nb0, i1 = t / args.nb0;
+        const int a0 = args.a_batched ? i0 : 0, a1 = args.a_batched ? i1 : 0;
+        const int b0 = args.b_batched ? i0 : 0, b1 = args.b_batched ? i1 : 0;
+        const int arow = tm * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+        const int brow = tn * BLOCK_N + static_cast<int>(rank) * HALF_N;
+        for (int kb = 0; kb < args.kb_total; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 0x900u + stage);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int p = 0; p < PLANES; ++p) {
+            tma_load_4d(sA(stage, p), &args.a_map[p], full_bar(stage), kb * BLOCK_K, arow, a0, a1);
+            if (!B_MN) {
+              tma_load_4d(sB(stage, p), &args.b_map[p], full_bar(stage), kb * BLOCK_K, brow, b0, b1);
+            } else {
+#pragma unroll
+              for (int c = 0; c < HALF_N / 64; ++c)
+                tma_load_4d(sB(stage, p) + c * (BLOCK_K * 128), &args.b_map[p], full_bar(stage), brow + c * 64,
+                            kb * BLOCK_K, b0, b1);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      if (rank != 0) {
+        // =================================================================== peer: relay "my stage is loaded"
+        for (int tile = pair; tile < total_tiles; tile += npairs) {
+          for (int kb = 0; kb < args.kb_total; ++kb) {
+            mbar_wait(full_bar(stage), phase, 0xA00u + stage);
+            mbar_arrive_cluster(mapa_shared(pfull_bar(stage), 0));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else {
+        // =================================================================== leader: MMA issuer for the pair
+        int it = 0;
+        for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, 0xB00u + acc);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          uint32_t accumulate = 0;
+          for (int kb = 0; kb < args.kb_total; ++kb) {
+            mbar_wait(full_bar(stage), phase, 0xC00u + stage);
+            mbar_wait_cluster(pfull_bar(stage), phase, 0xD00u + stage);
+            tc_fence_after();
+#pragma unroll
+            for (int combo = 0; combo < (PLANES == 1 ? 1 : (PLANES == 2 ? 3 : 6)); ++combo) {
+              constexpr int PA2[3] = {1, 0, 0}, PB2[3] = {0, 1, 0};
+              constexpr int PA3[6] = {1, 0, 2, 0, 1, 0}, PB3[6] = {1, 2, 0, 1, 0, 0};
+              const int pa = (PLANES == 1) ? 0 : (PLANES == 2 ? PA2[combo % 3] : PA3[combo]);
+              const int pb = (PLANES == 1) ? 0 : (PLANES == 2 ? PB2[combo % 3] : PB3[combo]);
+              const uint32_t a_base = sA(stage, pa), b_base = sB(stage, pb);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t da = umma_smem_desc(a_base + k * (UMMA_K * 2), 16, 1024);
+                const uint64_t db = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                         : umma_smem_desc(b_base + k * (UMMA_K * 2), 16, 1024);
+                umma_bf16_pair(d_tmem, da, db, IDESC, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit_pair(empty_bar(stage));       // frees the slot in both CTAs when these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit_pair(tfull_bar(acc));           // both halves of the accumulator are complete
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (both CTAs, own rows)
+    const int w = (warp - 4) & 3;
+    const int cgroup = (warp - 4) >> 2;
+    const GemmEpilogue& e = args.epi;
+    const float pe_alpha = (e.flags & EPI_PE) ? __ldg(e.pe_alpha) : 0.f;
+    const uint32_t stage_buf = epi_stage_base + (warp - 4) * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
+    const uint32_t bias_buf = stage_buf + EPI_STAGE_BYTES;
+    const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0), tempty_leader1 = mapa_shared(tempty_bar(1), 0);
+    int it = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+      int t = tile;
+      const int tn = t % args.tiles_n; t /= args.tiles_n;
+      const int tm = t % args.tiles_m; t /= args.tiles_m;
+      const int i0 = t % args.nb0, i1 = t / args.nb0;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (e.flags & EPI_BIAS) {
+        const int j = lane >> 3;
+        const int cloc = cgroup * 32 + j * 64;
+        const int col = tn * BLOCK_N + cloc + (lane & 7) * 4;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cloc < BLOCK_N && col < args.N) b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_buf + lane * 16), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+        __syncwarp();
+      }
+      mbar_wait(tfull_bar(acc), acc_phase, 0xE00u + acc);
+      tc_fence_after();
+      const int64_t row0 = static_cast<int64_t>(tm) * 2 * BLOCK_M + static_cast<int64_t>(rank) * BLOCK_M + w * 32;
+      const int64_t out_boff = i0 * e.out_sb0 + i1 * e.out_sb1;
+      const int64_t res_boff = i0 * e.res_sb0 + i1 * e.res_sb1;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BLOCK_N;
+      const int64_t cs_boff = i0 * e.colsum_sb0;
+      if (row0 < args.M) {   // warp-uniform
+        constexpr uint32_t CT_LEAN = EPI_BIAS | EPI_RELU | EPI_OUT_F32;
+        constexpr uint32_t CT_FWD = CT_LEAN | EPI_PE | EPI_DROPOUT | EPI_RES;
+        if ((e.flags & ~CT_LEAN) == 0)
+          epilogue_tile<CT_LEAN, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
+                                          cs_boff, tn, pe_alpha);
+        else if ((e.flags & ~CT_FWD) == 0)
+          epilogue_tile<CT_FWD, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
+                                         cs_boff, tn, pe_alpha);
+        else
+          epilogue_tile<0xFFFFFFFFu, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff,
+                                              res_boff, cs_boff, tn, pe_alpha);
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                      // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -702,6 +930,23 @@ static int launch(const GemmKernelArgs& args, int grid, cudaStream_t stream) {
   return 0;
 }
 
+static int g_cta_pairs = 1;            // spk_set_option("gemm_cta_pairs", 0/1)
+void gemm_set_cta_pairs(int on) { g_cta_pairs = on; }
+
+template <bool B_MN, int PLANES, int BLOCK_N>
+static int launch_pair(const GemmKernelArgs& args, int pairs, cudaStream_t stream) {
+  using Cfg = PairCfg<PLANES, BLOCK_N>;
+  auto kern = gemm_pair_kernel<B_MN, PLANES, BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  kern<<<2 * pairs, 128 + 32 * NUM_EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(args);   // __cluster_dims__(2,1,1)
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <bool A_MN, bool B_MN, int PLANES>
 static int launch_bn(int block_n, const GemmKernelArgs& args, int grid, cudaStream_t stream) {
   if constexpr (PLANES == 3) {   // three planes of A and B only fit a double-buffered ring up to N = 128
@@ -743,6 +988,42 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
   else SPK_CHECK(p.B.rows == p.K && p.B.cols <= p.N, "gemm: B is not [K, <=N]");
 
   SPK_TRY(configure_all());
+
+  // CTA-pair path: K-major A, two or three planes, no split-K, 256-wide N tiles
+  if (g_cta_pairs && !p.a_mn && p.planes >= 2 && p.ksplit <= 1 && p.block_n == 0 && p.N % 128 == 0 && p.M >= 256) {
+    constexpr int BN = 256;
+    GemmKernelArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int pl = 0; pl < p.planes; ++pl) {
+      SPK_TRY(make_map(&a.a_map[pl], p.A, pl, p.nb0, p.nb1, BLOCK_M));
+      SPK_TRY(make_map(&a.b_map[pl], p.B, pl, p.nb0, p.nb1, p.b_mn ? BLOCK_K : BN / 2));
+    }
+    a.M = p.M; a.N = p.N; a.K = p.K;
+    a.tiles_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    a.tiles_n = (p.N + BN - 1) / BN;
+    a.nb0 = p.nb0; a.nb1 = p.nb1;
+    a.kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+    a.kb_per_split = a.kb_total; a.ksplit = 1;
+    a.a_batched = (p.A.sb0 != 0 || p.A.sb1 != 0);
+    a.b_batched = (p.B.sb0 != 0 || p.B.sb1 != 0);
+    a.epi = p.epi;
+    const long long total = 1LL * a.nb0 * a.nb1 * a.tiles_m * a.tiles_n;
+    SPK_CHECK(total < (1LL << 30), "gemm: too many tiles");
+    const int max_pairs = device_sm_count() / 2;
+    const int pairs = static_cast<int>(total < max_pairs ? total : max_pairs);
+    const double nb = 1.0 * p.nb0 * p.nb1, esz = 2.0 * p.planes;
+    const double out_b = (p.epi.flags & (EPI_OUT_F32 | EPI_OUT_ATOMIC)) ? 4.0 : esz;
+    double bytes = nb * (1.0 * p.M * p.K * esz + 1.0 * p.M * p.N * out_b) + (a.b_batched ? nb : 1.0) * p.N * p.K * esz;
+    if (p.epi.flags & (EPI_RES | EPI_ACC_GATES_AUX)) bytes += nb * p.M * p.N * 2.0 * p.epi.res_planes;
+    if (p.epi.flags & EPI_GATE_POS) bytes += nb * p.M * p.N * 2.0 * p.epi.gate_planes;
+    ProfScope prof(p.tag, 2.0 * nb * p.M * p.N * p.K, bytes, stream);
+    if (p.planes == 3) {
+      if (p.b_mn) return launch_pair<true, 3, BN>(a, pairs, stream);
+      return launch_pair<false, 3, BN>(a, pairs, stream);
+    }
+    if (p.b_mn) return launch_pair<true, 2, BN>(a, pairs, stream);
+    return launch_pair<false, 2, BN>(a, pairs, stream);
+  }
 
   int bn = p.block_n;
   if (bn == 0) bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : (p.N <= 192 ? 192 : 256));

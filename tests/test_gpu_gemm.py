@@ -79,3 +79,31 @@ def test_gemm_rejects_bad_arguments():
         N.gemm(a, a, 1, 64, 64, 64, ksplit=2)
     with pytest.raises(RuntimeError, match="CUDA"):
         N.gemm(a.cpu(), a, 1, 64, 64, 64)
+
+
+@pytest.mark.parametrize("planes,m,n,k,b_mn,bias,relu,out_f32", [
+    (3, 512, 256, 256, 0, 0, 0, 0),
+    (3, 1000, 768, 256, 0, 1, 0, 0),           # ragged M: the peer CTA's rows run past M
+    (3, 300, 384, 320, 0, 1, 1, 0),            # N = 1.5 pair tiles (the peer's half of the last tile is empty)
+    (2, 777, 1024, 256, 1, 0, 0, 1),           # MN-major B (dgrad), fp32 out
+    (2, 2048, 128, 192, 1, 0, 0, 0),           # N = 128: only the leader's half of B exists
+    (3, 40000, 1024, 256, 0, 1, 1, 0),         # many tiles per pair (TMEM double buffer, ring wrap-around)
+])
+def test_cta_pair_kernel_is_bit_identical_to_single_cta(planes, m, n, k, b_mn, bias, relu, out_f32):
+    """tcgen05.mma.cta_group::2 path (two CTAs per 256 x 256 tile, each stages half of B) against the single-CTA
+    kernel: same MMAs in the same order per accumulator element, so the outputs must match bit for bit."""
+    from speaker_embedding_torch_b200 import _native as N
+    torch.manual_seed(m + n + k)
+    a = N.split_pack(torch.randn(m, k, device="cuda"), planes)
+    b = N.split_pack(torch.randn(k, n, device="cuda") if b_mn else torch.randn(n, k, device="cuda"), planes)
+    bv = torch.randn(n, device="cuda") if bias else None
+    outs = []
+    try:
+        for mode in (0, 1):
+            N.set_option("gemm_cta_pairs", mode)
+            outs.append(N.gemm(a, b, planes, m, n, k, b_mn=bool(b_mn), bias=bv, relu=bool(relu),
+                               out_f32=bool(out_f32)).clone())
+    finally:
+        N.set_option("gemm_cta_pairs", 1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
