@@ -32,6 +32,9 @@ constexpr int NUM_EPI_WARPS = 8;         // two warps per TMEM lane quarter, alt
 constexpr int EPI_STAGE_BYTES = 2176;    // per warp: bf16 tile 32 x 32 (2 KB) or fp32 tile 32 x 17
 constexpr int EPI_BIAS_BYTES = 512;      // per warp: the bias of its (up to four) 32-column chunks of the current tile
 constexpr int EPI_SMEM = NUM_EPI_WARPS * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
+// setmaxnreg: the CTA's register pool is its launch allocation, 384 x 168 >= 128 x 48 + 256 x 224 (a larger request
+// spins forever): warps 0-3 (TMA / MMA / TMEM / idle) keep 48 registers, the epilogue warps get 224.
+constexpr int LAUNCH_REGS = 168, CTRL_REGS = 48, EPI_REGS = 224;
 
 struct GemmKernelArgs {
   CUtensorMap a_map[3];
@@ -436,94 +439,98 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
   const int tiles_per_batch = args.ksplit * args.tiles_m * args.tiles_n;
   const int total_tiles = args.nb0 * args.nb1 * tiles_per_batch;
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int tn = t % args.tiles_n; t /= args.tiles_n;
-        const int tm = t % args.tiles_m; t /= args.tiles_m;
-        const int ks = t % args.ksplit;  t /= args.ksplit;
-        const int i0 = t % args.nb0, i1 = t / args.nb0;
-        const int a0 = args.a_batched ? i0 : 0, a1 = args.a_batched ? i1 : 0;
-        const int b0 = args.b_batched ? i0 : 0, b1 = args.b_batched ? i1 : 0;
-        const int kb_begin = ks * args.kb_per_split;
-        const int kb_end = min(kb_begin + args.kb_per_split, args.kb_total);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, 0x100u + stage);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+  if (warp < 4) {
+    setmaxnreg_dec<CTRL_REGS>();
+    if (warp == 0) {
+      // ===================================================================== TMA producer
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          int t = tile;
+          const int tn = t % args.tiles_n; t /= args.tiles_n;
+          const int tm = t % args.tiles_m; t /= args.tiles_m;
+          const int ks = t % args.ksplit;  t /= args.ksplit;
+          const int i0 = t % args.nb0, i1 = t / args.nb0;
+          const int a0 = args.a_batched ? i0 : 0, a1 = args.a_batched ? i1 : 0;
+          const int b0 = args.b_batched ? i0 : 0, b1 = args.b_batched ? i1 : 0;
+          const int kb_begin = ks * args.kb_per_split;
+          const int kb_end = min(kb_begin + args.kb_per_split, args.kb_total);
+          for (int kb = kb_begin; kb < kb_end; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, 0x100u + stage);
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
 #pragma unroll
-          for (int p = 0; p < PLANES; ++p) {
-            if (!A_MN) {
-              tma_load_4d(sA(stage, p), &args.a_map[p], full_bar(stage), kb * BLOCK_K, tm * BLOCK_M, a0, a1);
-            } else {
+            for (int p = 0; p < PLANES; ++p) {
+              if (!A_MN) {
+                tma_load_4d(sA(stage, p), &args.a_map[p], full_bar(stage), kb * BLOCK_K, tm * BLOCK_M, a0, a1);
+              } else {
 #pragma unroll
-              for (int c = 0; c < BLOCK_M / 64; ++c)
-                tma_load_4d(sA(stage, p) + c * (BLOCK_K * 128), &args.a_map[p], full_bar(stage),
-                            tm * BLOCK_M + c * 64, kb * BLOCK_K, a0, a1);
+                for (int c = 0; c < BLOCK_M / 64; ++c)
+                  tma_load_4d(sA(stage, p) + c * (BLOCK_K * 128), &args.a_map[p], full_bar(stage),
+                              tm * BLOCK_M + c * 64, kb * BLOCK_K, a0, a1);
+              }
+              if (!B_MN) {
+                tma_load_4d(sB(stage, p), &args.b_map[p], full_bar(stage), kb * BLOCK_K, tn * BLOCK_N, b0, b1);
+              } else {
+#pragma unroll
+                for (int c = 0; c < BLOCK_N / 64; ++c)
+                  tma_load_4d(sB(stage, p) + c * (BLOCK_K * 128), &args.b_map[p], full_bar(stage),
+                              tn * BLOCK_N + c * 64, kb * BLOCK_K, b0, b1);
+              }
             }
-            if (!B_MN) {
-              tma_load_4d(sB(stage, p), &args.b_map[p], full_bar(stage), kb * BLOCK_K, tn * BLOCK_N, b0, b1);
-            } else {
-#pragma unroll
-              for (int c = 0; c < BLOCK_N / 64; ++c)
-                tma_load_4d(sB(stage, p) + c * (BLOCK_K * 128), &args.b_map[p], full_bar(stage),
-                            tn * BLOCK_N + c * 64, kb * BLOCK_K, b0, b1);
-            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        int t = tile / (args.tiles_n * args.tiles_m);
-        const int ks = t % args.ksplit;
-        const int kb_begin = ks * args.kb_per_split;
-        const int kb_end = min(kb_begin + args.kb_per_split, args.kb_total);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x200u + acc);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        uint32_t accumulate = 0;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(full_bar(stage), phase, 0x300u + stage);
+    } else if (warp == 1) {
+      // ===================================================================== MMA issuer
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+          int t = tile / (args.tiles_n * args.tiles_m);
+          const int ks = t % args.ksplit;
+          const int kb_begin = ks * args.kb_per_split;
+          const int kb_end = min(kb_begin + args.kb_per_split, args.kb_total);
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x200u + acc);
           tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          uint32_t accumulate = 0;
+          for (int kb = kb_begin; kb < kb_end; ++kb) {
+            mbar_wait(full_bar(stage), phase, 0x300u + stage);
+            tc_fence_after();
 #pragma unroll
-          for (int combo = 0; combo < (PLANES == 1 ? 1 : (PLANES == 2 ? 3 : 6)); ++combo) {
-            // plane products, smallest terms first (plane 0 = hi, 1 = mid/lo, 2 = lo):
-            //   2 planes: a1*b0, a0*b1, a0*b0           3 planes: a1*b1, a0*b2, a2*b0, a0*b1, a1*b0, a0*b0
-            constexpr int PA2[3] = {1, 0, 0}, PB2[3] = {0, 1, 0};
-            constexpr int PA3[6] = {1, 0, 2, 0, 1, 0}, PB3[6] = {1, 2, 0, 1, 0, 0};
-            const int pa = (PLANES == 1) ? 0 : (PLANES == 2 ? PA2[combo % 3] : PA3[combo]);
-            const int pb = (PLANES == 1) ? 0 : (PLANES == 2 ? PB2[combo % 3] : PB3[combo]);
-            const uint32_t a_base = sA(stage, pa), b_base = sB(stage, pb);
+            for (int combo = 0; combo < (PLANES == 1 ? 1 : (PLANES == 2 ? 3 : 6)); ++combo) {
+              // plane products, smallest terms first (plane 0 = hi, 1 = mid/lo, 2 = lo):
+              //   2 planes: a1*b0, a0*b1, a0*b0           3 planes: a1*b1, a0*b2, a2*b0, a0*b1, a1*b0, a0*b0
+              constexpr int PA2[3] = {1, 0, 0}, PB2[3] = {0, 1, 0};
+              constexpr int PA3[6] = {1, 0, 2, 0, 1, 0}, PB3[6] = {1, 2, 0, 1, 0, 0};
+              const int pa = (PLANES == 1) ? 0 : (PLANES == 2 ? PA2[combo % 3] : PA3[combo]);
+              const int pb = (PLANES == 1) ? 0 : (PLANES == 2 ? PB2[combo % 3] : PB3[combo]);
+              const uint32_t a_base = sA(stage, pa), b_base = sB(stage, pb);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t da = A_MN ? umma_smem_desc(a_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                       : umma_smem_desc(a_base + k * (UMMA_K * 2), 16, 1024);
-              const uint64_t db = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                       : umma_smem_desc(b_base + k * (UMMA_K * 2), 16, 1024);
-              umma_bf16(d_tmem, da, db, IDESC, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t da = A_MN ? umma_smem_desc(a_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                         : umma_smem_desc(a_base + k * (UMMA_K * 2), 16, 1024);
+                const uint64_t db = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                         : umma_smem_desc(b_base + k * (UMMA_K * 2), 16, 1024);
+                umma_bf16(d_tmem, da, db, IDESC, accumulate);
+                accumulate = 1;
+              }
             }
+            umma_commit(empty_bar(stage));        // frees the smem slot when these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(empty_bar(stage));        // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          umma_commit(tfull_bar(acc));            // accumulator ready for the epilogue
         }
-        umma_commit(tfull_bar(acc));            // accumulator ready for the epilogue
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ===================================================================== epilogue
+    setmaxnreg_inc<EPI_REGS>();
     const int w = (warp - 4) & 3;          // TMEM lane quarter (warp % 4) -> accumulator rows 32w .. 32w+31
     const int cgroup = (warp - 4) >> 2;    // this warp handles the 32-column chunks with (c & 1) == cgroup
     const GemmEpilogue& e = args.epi;
@@ -666,91 +673,95 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
   const int tiles_per_batch = args.tiles_m * args.tiles_n;       // tiles_m counts 256-row tiles here
   const int total_tiles = args.nb0 * args.nb1 * tiles_per_batch;
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += npairs) {
-        int t = tile;
-        const int tn = t % args.tiles_n; t /= args.tiles_n;
-        const int tm = t % args.tiles_m; t /= args.tiles_m;
-        const int i0 = t % args.nb0, i1 = t / args.nb0;
-        const int a0 = args.a_batched ? i0 : 0, a1 = args.a_batched ? i1 : 0;
-        const int b0 = args.b_batched ? i0 : 0, b1 = args.b_batched ? i1 : 0;
-        const int arow = tm * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
-        const int brow = tn * BLOCK_N + static_cast<int>(rank) * HALF_N;
-        for (int kb = 0; kb < args.kb_total; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, 0x900u + stage);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-#pragma unroll
-          for (int p = 0; p < PLANES; ++p) {
-            tma_load_4d(sA(stage, p), &args.a_map[p], full_bar(stage), kb * BLOCK_K, arow, a0, a1);
-            if (!B_MN) {
-              tma_load_4d(sB(stage, p), &args.b_map[p], full_bar(stage), kb * BLOCK_K, brow, b0, b1);
-            } else {
-#pragma unroll
-              for (int c = 0; c < HALF_N / 64; ++c)
-                tma_load_4d(sB(stage, p) + c * (BLOCK_K * 128), &args.b_map[p], full_bar(stage), brow + c * 64,
-                            kb * BLOCK_K, b0, b1);
-            }
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      if (rank != 0) {
-        // =================================================================== peer: relay "my stage is loaded"
+  if (warp < 4) {
+    setmaxnreg_dec<CTRL_REGS>();
+    if (warp == 0) {
+      // ===================================================================== TMA producer (both CTAs)
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
         for (int tile = pair; tile < total_tiles; tile += npairs) {
+          int t = tile;
+          const int tn = t % args.tiles_n; t /= args.tiles_n;
+          const int tm = t % args.tiles_m; t /= args.tiles_m;
+          const int i0 = t % args.nb0, i1 = t / args.nb0;
+          const int a0 = args.a_batched ? i0 : 0, a1 = args.a_batched ? i1 : 0;
+          const int b0 = args.b_batched ? i0 : 0, b1 = args.b_batched ? i1 : 0;
+          const int arow = tm * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+          const int brow = tn * BLOCK_N + static_cast<int>(rank) * HALF_N;
           for (int kb = 0; kb < args.kb_total; ++kb) {
-            mbar_wait(full_bar(stage), phase, 0xA00u + stage);
-            mbar_arrive_cluster(mapa_shared(pfull_bar(stage), 0));
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          }
-        }
-      } else {
-        // =================================================================== leader: MMA issuer for the pair
-        int it = 0;
-        for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
-          const int acc = it & 1;
-          const uint32_t acc_phase = (it >> 1) & 1;
-          mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, 0xB00u + acc);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-          uint32_t accumulate = 0;
-          for (int kb = 0; kb < args.kb_total; ++kb) {
-            mbar_wait(full_bar(stage), phase, 0xC00u + stage);
-            mbar_wait_cluster(pfull_bar(stage), phase, 0xD00u + stage);
-            tc_fence_after();
+            mbar_wait(empty_bar(stage), phase ^ 1u, 0x900u + stage);
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
 #pragma unroll
-            for (int combo = 0; combo < (PLANES == 1 ? 1 : (PLANES == 2 ? 3 : 6)); ++combo) {
-              constexpr int PA2[3] = {1, 0, 0}, PB2[3] = {0, 1, 0};
-              constexpr int PA3[6] = {1, 0, 2, 0, 1, 0}, PB3[6] = {1, 2, 0, 1, 0, 0};
-              const int pa = (PLANES == 1) ? 0 : (PLANES == 2 ? PA2[combo % 3] : PA3[combo]);
-              const int pb = (PLANES == 1) ? 0 : (PLANES == 2 ? PB2[combo % 3] : PB3[combo]);
-              const uint32_t a_base = sA(stage, pa), b_base = sB(stage, pb);
+            for (int p = 0; p < PLANES; ++p) {
+              tma_load_4d(sA(stage, p), &args.a_map[p], full_bar(stage), kb * BLOCK_K, arow, a0, a1);
+              if (!B_MN) {
+                tma_load_4d(sB(stage, p), &args.b_map[p], full_bar(stage), kb * BLOCK_K, brow, b0, b1);
+              } else {
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                const uint64_t da = umma_smem_desc(a_base + k * (UMMA_K * 2), 16, 1024);
-                const uint64_t db = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                         : umma_smem_desc(b_base + k * (UMMA_K * 2), 16, 1024);
-                umma_bf16_pair(d_tmem, da, db, IDESC, accumulate);
-                accumulate = 1;
+                for (int c = 0; c < HALF_N / 64; ++c)
+                  tma_load_4d(sB(stage, p) + c * (BLOCK_K * 128), &args.b_map[p], full_bar(stage), brow + c * 64,
+                              kb * BLOCK_K, b0, b1);
               }
             }
-            umma_commit_pair(empty_bar(stage));       // frees the slot in both CTAs when these MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          umma_commit_pair(tfull_bar(acc));           // both halves of the accumulator are complete
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        if (rank != 0) {
+          // =================================================================== peer: relay "my stage is loaded"
+          for (int tile = pair; tile < total_tiles; tile += npairs) {
+            for (int kb = 0; kb < args.kb_total; ++kb) {
+              mbar_wait(full_bar(stage), phase, 0xA00u + stage);
+              mbar_arrive_cluster(mapa_shared(pfull_bar(stage), 0));
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        } else {
+          // =================================================================== leader: MMA issuer for the pair
+          int it = 0;
+          for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, 0xB00u + acc);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            uint32_t accumulate = 0;
+            for (int kb = 0; kb < args.kb_total; ++kb) {
+              mbar_wait(full_bar(stage), phase, 0xC00u + stage);
+              mbar_wait_cluster(pfull_bar(stage), phase, 0xD00u + stage);
+              tc_fence_after();
+#pragma unroll
+              for (int combo = 0; combo < (PLANES == 1 ? 1 : (PLANES == 2 ? 3 : 6)); ++combo) {
+                constexpr int PA2[3] = {1, 0, 0}, PB2[3] = {0, 1, 0};
+                constexpr int PA3[6] = {1, 0, 2, 0, 1, 0}, PB3[6] = {1, 2, 0, 1, 0, 0};
+                const int pa = (PLANES == 1) ? 0 : (PLANES == 2 ? PA2[combo % 3] : PA3[combo]);
+                const int pb = (PLANES == 1) ? 0 : (PLANES == 2 ? PB2[combo % 3] : PB3[combo]);
+                const uint32_t a_base = sA(stage, pa), b_base = sB(stage, pb);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  const uint64_t da = umma_smem_desc(a_base + k * (UMMA_K * 2), 16, 1024);
+                  const uint64_t db = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                           : umma_smem_desc(b_base + k * (UMMA_K * 2), 16, 1024);
+                  umma_bf16_pair(d_tmem, da, db, IDESC, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit_pair(empty_bar(stage));       // frees the slot in both CTAs when these MMAs retire
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit_pair(tfull_bar(acc));           // both halves of the accumulator are complete
+          }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ===================================================================== epilogue (both CTAs, own rows)
+    setmaxnreg_inc<EPI_REGS>();
     const int w = (warp - 4) & 3;
     const int cgroup = (warp - 4) >> 2;
     const GemmEpilogue& e = args.epi;
@@ -892,6 +903,9 @@ static int configure() {
   SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   cudaFuncAttributes fa;
   SPK_CUDA(cudaFuncGetAttributes(&fa, kern));
+  // setmaxnreg re-partitions the launch allocation; another launch register count would dead-lock the epilogue warps
+  SPK_CHECK(fa.numRegs == LAUNCH_REGS, "gemm kernel was built with %d registers/thread, expected %d", fa.numRegs,
+            LAUNCH_REGS);
   return 0;
 }
 template <bool A_MN, bool B_MN, int PLANES>
@@ -940,6 +954,10 @@ static int launch_pair(const GemmKernelArgs& args, int pairs, cudaStream_t strea
   static bool configured = false;
   if (!configured) {
     SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cudaFuncAttributes fa;
+    SPK_CUDA(cudaFuncGetAttributes(&fa, kern));
+    SPK_CHECK(fa.numRegs == LAUNCH_REGS, "gemm pair kernel was built with %d registers/thread, expected %d", fa.numRegs,
+              LAUNCH_REGS);
     configured = true;
   }
   kern<<<2 * pairs, 128 + 32 * NUM_EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(args);   // __cluster_dims__(2,1,1)
