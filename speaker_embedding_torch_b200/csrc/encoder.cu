@@ -31,6 +31,7 @@ struct Split {
 struct LayerBufs {
   Split qkv, p, pd, att, z1, h1, f, z2, hout;
   size_t st1 = 0, st2 = 0;
+  size_t fbits = 0;   // ReLU mask of the FFN hidden activation, one bit per element ([F/32, Mt] words), for the backward
 };
 
 // Last layer, t = 0 rows only (see attn_row0.cu): compact [B, .] buffers + K|V for every frame.
@@ -116,6 +117,7 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
     b.st1 = take_f32(cur, Mt * 2);
     b.h1 = take_split(cur, Mt * D, P);
     b.f = take_split(cur, Mt * F, P);
+    b.fbits = take_f32(cur, Mt * (F / 32));
     b.z2 = take_split(cur, Mt * D, P);
     b.st2 = take_f32(cur, Mt * 2);
     b.hout = keep ? take_split(cur, Mt * D, P) : pl.h0;
@@ -492,6 +494,10 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       g.planes = P; g.M = (int)Mt; g.N = (int)F; g.K = (int)D;
       g.epi.flags = EPI_BIAS | EPI_RELU | (drop.thresh ? EPI_DROPOUT : 0);
       g.epi.bias = lw.linear1_b; g.epi.drop = drop; g.epi.drop_site = 3 + 4 * l;
+      if (keep) {   // the backward's ReLU gate reads one bit per element instead of a whole plane of f
+        g.epi.flags |= EPI_EMIT_BITS;
+        g.epi.gate_bits = reinterpret_cast<uint32_t*>(c.f32(b.fbits));
+      }
       c.out(g.epi, b.f, 0, F);
       SPK_TRY(gemm_run(g, st));
     }
@@ -737,10 +743,9 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.B = c.mat(pl.wpack, pl.w_l2[l], D, F, F);
       g.b_mn = true;
       g.planes = P; g.M = (int)Mt; g.N = (int)F; g.K = (int)D;
-      g.epi.flags = EPI_GATE_POS | EPI_COLSUM;
+      g.epi.flags = EPI_GATE_BITS | EPI_COLSUM;
       g.epi.colsum = lg.linear1_b;
-      g.epi.gate = c.ptr(b.f); g.epi.gate_plane_stride = b.f.ps; g.epi.gate_ld = F;
-      g.epi.gate_planes = 1;   // f >= 0 and bf16(f) > 0 <=> f > 0: the hi plane alone decides the ReLU gate
+      g.epi.gate_bits = reinterpret_cast<uint32_t*>(c.f32(b.fbits));   // written by the forward FFN1 epilogue
       g.epi.gate_scale = drop.inv_keep;
       c.out(g.epi, pl.df, 0, F);
       SPK_TRY(gemm_run(g, st));

@@ -28,7 +28,9 @@ enum : uint32_t {
   EPI_ACC_GATES_AUX = 1u << 6,  // v = (v > 0) ? res[row, col] * dropout_keep : 0  (prenet backward by recompute)
   EPI_COLSUM = 1u << 7,     // colsum[col] += sum_rows(v)  (bias gradient fused into the producing GEMM)
   EPI_OUT_F32 = 1u << 8,    // plain fp32 store instead of split planes
-  EPI_OUT_ATOMIC = 1u << 9  // fp32 atomicAdd (split-K weight gradients)
+  EPI_OUT_ATOMIC = 1u << 9,  // fp32 atomicAdd (split-K weight gradients)
+  EPI_EMIT_BITS = 1u << 10,  // gate_bits[col/32, row]: bit i set iff v[col0 + i] > 0   (forward: ReLU mask for the backward)
+  EPI_GATE_BITS = 1u << 11   // v = bit ? v * gate_scale : 0 from gate_bits (ReLU backward, 1 bit per element)
 };
 
 struct GemmEpilogue {
@@ -49,6 +51,7 @@ struct GemmEpilogue {
   int64_t gate_plane_stride = 0, gate_ld = 0;
   int gate_planes = 1;
   float gate_scale = 1.f;
+  uint32_t* gate_bits = nullptr;   // [N / 32, M] words, chunk-major (N % 32 == 0, unbatched): EPI_EMIT_BITS writes, EPI_GATE_BITS reads
   // fused column sums (fp32, atomically accumulated); colsum_sb0: elements per batch index i0
   float* colsum = nullptr;
   int64_t colsum_sb0 = 0;

@@ -269,7 +269,7 @@ template <uint32_t CT>
 __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage, uint32_t bias_s, int lane, int M, int N,
                                            int64_t row0, int64_t batch, int64_t out_boff, const CoopIO& io_out,
                                            const CoopIO& io_res, const CoopIO& io_gate, int64_t cs_boff, int col0,
-                                           const uint32_t (&acc)[32], float pe_alpha) {
+                                           const uint32_t (&acc)[32], float pe_alpha, uint32_t gate_word) {
   const uint32_t f = e.flags & CT;
   const int64_t row = row0 + lane;
   const bool row_ok = row < M;
@@ -315,6 +315,16 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
         for (int i = 0; i < 8; ++i) v[q * 8 + i] *= k8[i];
       }
     }
+  }
+  if (f & EPI_EMIT_BITS) {          // ReLU mask of the final (post-dropout) activation, 1 bit per element
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f) ? (1u << i) : 0u;
+    if (row_ok) e.gate_bits[static_cast<int64_t>(col0 >> 5) * M + row] = m;   // chunk-major: a warp writes 128 contiguous bytes
+  }
+  if (f & EPI_GATE_BITS) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((gate_word >> i) & 1u) ? v[i] * e.gate_scale : 0.f;
   }
   if (f & (EPI_RES | EPI_ACC_GATES_AUX)) {
     float r[32];
@@ -373,15 +383,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t st
   if constexpr ((CT & EPI_GATE_POS) != 0) {
     if (e.flags & EPI_GATE_POS) io_gate = make_coop(lane, 0, row0, e.gate_ld, M, 8);
   }
+  // ReLU-mask words (EPI_GATE_BITS), layout [N / 32][M] (chunk-major: the 32 lanes of a warp = consecutive rows read 128
+  // contiguous bytes); the word of chunk c + 2 is loaded while chunk c is processed
+  const bool use_bits = (CT & EPI_GATE_BITS) != 0 && (e.flags & EPI_GATE_BITS) != 0 && row0 + lane < M;
+  const uint32_t* bits_row = use_bits ? e.gate_bits + static_cast<int64_t>(tn) * (BLOCK_N / 32) * M + row0 + lane : nullptr;
+  uint32_t next_word = (use_bits && tn * BLOCK_N + cgroup * 32 < N) ? __ldg(bits_row + static_cast<int64_t>(cgroup) * M) : 0u;
 #pragma unroll 1
   for (int c = cgroup; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
     const int col0 = tn * BLOCK_N + c * 32;
     if (col0 >= N) break;             // warp-uniform
     uint32_t r[32];
     tmem_ld_32x32(t_row + c * 32, r);
+    const uint32_t word = next_word;
+    const int cn = c + NUM_EPI_WARPS / 4;
+    if (use_bits && cn < BLOCK_N / 32 && tn * BLOCK_N + cn * 32 < N) next_word = __ldg(bits_row + static_cast<int64_t>(cn) * M);
     tmem_ld_wait();
     epilogue32<CT>(e, stage_buf, bias_buf + (c >> 1) * 128, lane, M, N, row0, batch, out_boff, io_out, io_res, io_gate,
-                   cs_boff, col0, r, pe_alpha);
+                   cs_boff, col0, r, pe_alpha, word);
   }
 }
 
@@ -564,13 +582,18 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
       const int64_t cs_boff = i0 * e.colsum_sb0;
       if (row0 < args.M) {   // warp-uniform
         constexpr uint32_t CT_LEAN = EPI_BIAS | EPI_RELU | EPI_OUT_F32;
-        constexpr uint32_t CT_FWD = CT_LEAN | EPI_PE | EPI_DROPOUT | EPI_RES;
+        // the bit-mask classes only exist in the multi-plane kernels: the one-plane (inference) kernels stay small
+        constexpr uint32_t CT_FWD = CT_LEAN | EPI_PE | EPI_DROPOUT | EPI_RES | (PLANES >= 2 ? EPI_EMIT_BITS : 0u);
+        constexpr uint32_t CT_BWD = EPI_GATE_BITS | EPI_COLSUM | EPI_RES | EPI_OUT_F32;   // data gradients
         if ((e.flags & ~CT_LEAN) == 0)
           epilogue_tile<CT_LEAN, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
                                           cs_boff, tn, pe_alpha);
         else if ((e.flags & ~CT_FWD) == 0)
           epilogue_tile<CT_FWD, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
                                          cs_boff, tn, pe_alpha);
+        else if (PLANES >= 2 && (e.flags & ~CT_BWD) == 0)
+          epilogue_tile<(PLANES >= 2 ? CT_BWD : 0xFFFFFFFFu), BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0,
+                                                                       t, out_boff, res_boff, cs_boff, tn, pe_alpha);
         else
           epilogue_tile<0xFFFFFFFFu, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff,
                                               res_boff, cs_boff, tn, pe_alpha);
@@ -795,13 +818,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
       const int64_t cs_boff = i0 * e.colsum_sb0;
       if (row0 < args.M) {   // warp-uniform
         constexpr uint32_t CT_LEAN = EPI_BIAS | EPI_RELU | EPI_OUT_F32;
-        constexpr uint32_t CT_FWD = CT_LEAN | EPI_PE | EPI_DROPOUT | EPI_RES;
+        // the bit-mask classes only exist in the multi-plane kernels: the one-plane (inference) kernels stay small
+        constexpr uint32_t CT_FWD = CT_LEAN | EPI_PE | EPI_DROPOUT | EPI_RES | (PLANES >= 2 ? EPI_EMIT_BITS : 0u);
+        constexpr uint32_t CT_BWD = EPI_GATE_BITS | EPI_COLSUM | EPI_RES | EPI_OUT_F32;   // data gradients
         if ((e.flags & ~CT_LEAN) == 0)
           epilogue_tile<CT_LEAN, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
                                           cs_boff, tn, pe_alpha);
         else if ((e.flags & ~CT_FWD) == 0)
           epilogue_tile<CT_FWD, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
                                          cs_boff, tn, pe_alpha);
+        else if (PLANES >= 2 && (e.flags & ~CT_BWD) == 0)
+          epilogue_tile<(PLANES >= 2 ? CT_BWD : 0xFFFFFFFFu), BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0,
+                                                                       t, out_boff, res_boff, cs_boff, tn, pe_alpha);
         else
           epilogue_tile<0xFFFFFFFFu, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff,
                                               res_boff, cs_boff, tn, pe_alpha);
@@ -999,6 +1027,9 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
   SPK_CHECK(p.N % 8 == 0, "gemm: N (%d) must be a multiple of 8", p.N);
   SPK_CHECK(p.epi.out != nullptr, "gemm: no output");
   SPK_CHECK(p.ksplit == 1 || (p.epi.flags & EPI_OUT_ATOMIC), "gemm: split-K needs the atomic epilogue");
+  if (p.epi.flags & (EPI_EMIT_BITS | EPI_GATE_BITS))
+    SPK_CHECK(p.epi.gate_bits != nullptr && p.N % 32 == 0 && p.nb0 * p.nb1 == 1,
+              "gemm: the ReLU bit mask needs N %% 32 == 0 and an unbatched problem");
   // the non-contraction extent of an operand may be smaller than M / N: TMA zero-fills the rest
   if (!p.a_mn) SPK_CHECK(p.A.rows <= p.M && p.A.cols == p.K, "gemm: A is not [<=M, K]");
   else SPK_CHECK(p.A.rows == p.K && p.A.cols <= p.M, "gemm: A is not [K, <=M]");
