@@ -153,8 +153,12 @@ int spk_split_pack(const float* src, void* dst, int64_t plane_stride, int planes
 
 int spk_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* Library options.  "prune_last_layer" (default 1): run the last encoder layer only for the t = 0 query row
- * the d-vector head consumes (exact; K and V are still projected for every frame). */
+/* Library options (all default 1):
+ *   "prune_last_layer"           run the last encoder layer only for the t = 0 query row the d-vector head consumes
+ *                                (exact; K and V are still projected for every frame);
+ *   "fused_inference_attention"  one tcgen05 kernel for QK^T / softmax / PV in the one-plane inference path (T <= 256);
+ *   "gemm_cta_pairs"             multi-plane GEMMs on CTA pairs (tcgen05.mma.cta_group::2); 0 = single-CTA kernel
+ *                                (bit-identical results, used by the tests as the cross-check). */
 int spk_set_option(const char* name, int value);
 
 /* Launch profiler (used by bench.py for the per-kernel roofline): when enabled every launcher brackets

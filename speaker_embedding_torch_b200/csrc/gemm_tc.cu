@@ -8,10 +8,12 @@
 // * one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16 in, fp32 accumulate in
 //   TMEM); with two planes it issues Ah*Bh + Ah*Bl + Al*Bh into the same accumulator, with three
 //   planes the six products down to 2^-16 (fp32-equivalent operands);
-// * the accumulator is double-buffered in TMEM so the 4 epilogue warps (tcgen05.ld -> registers
+// * the accumulator is double-buffered in TMEM so the 8 epilogue warps (tcgen05.ld -> registers
 //   -> fused bias / ReLU / positional term / dropout / residual / gate -> global) drain tile i
 //   while the MMA warp works on tile i+1;
-// * grid = min(#tiles, #SMs); tiles are assigned round-robin (persistent CTAs).
+// * grid = min(#tiles, #SMs); tiles are assigned round-robin (persistent CTAs);
+// * multi-plane problems with a K-major A and M >= 256 run on CTA pairs instead (gemm_pair_kernel below:
+//   tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA stages half of B).
 //
 // Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
 // 4..11 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31 == accumulator rows; warps 4-7 take the even
