@@ -624,7 +624,9 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
 //   peer_full[s] leader only: the peer's stage s is loaded           (remote arrive by the peer's relay lane)
 //   empty[s]     both CTAs, signalled by the leader's commit (multicast)
 //   tfull[a]     both CTAs, leader's commit (multicast): accumulator a complete
-//   tempty[a]    leader only: 2 x 256 epilogue threads (local + remote arrives)
+//   tlocal[a]    each CTA: its 256 epilogue threads have drained accumulator a (CTA-scope arrives: a cluster-scope
+//                release from every epilogue thread would wait for its outstanding global stores)
+//   tempty[a]    leader only: one remote arrive per CTA, forwarded by the idle warp 3 once tlocal[a] completes
 template <int PLANES, int BLOCK_N>
 struct PairCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -654,7 +656,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
   auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+  auto tlocal_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 4 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 6);
   const uint32_t epi_stage_base = bar_base + BAR_BYTES;
   auto sA = [&](int s, int p) { return smem_base + s * Cfg::STAGE_BYTES + p * Cfg::A_BYTES; };
   auto sB = [&](int s, int p) { return smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES + p * Cfg::B_BYTES; };
@@ -680,7 +683,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 2 * 32 * NUM_EPI_WARPS);
+      mbar_init(tempty_bar(a), 2);                       // one arrive per CTA, from its relay lane
+      mbar_init(tlocal_bar(a), 32 * NUM_EPI_WARPS);      // this CTA's epilogue threads
     }
     fence_mbar_init();
   }
@@ -783,6 +787,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
           }
         }
       }
+    } else if (warp == 3) {
+      // =================================================================== both CTAs: forward "accumulator drained"
+      if (lane == 0) {
+        const uint32_t te0 = mapa_shared(tempty_bar(0), 0), te1 = mapa_shared(tempty_bar(1), 0);
+        int it = 0;
+        for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+          const int acc = it & 1;
+          mbar_wait(tlocal_bar(acc), (it >> 1) & 1, 0xF00u + acc);
+          mbar_arrive_cluster(acc ? te1 : te0);
+        }
+      }
     }
   } else {
     // ===================================================================== epilogue (both CTAs, own rows)
@@ -793,7 +808,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
     const float pe_alpha = (e.flags & EPI_PE) ? __ldg(e.pe_alpha) : 0.f;
     const uint32_t stage_buf = epi_stage_base + (warp - 4) * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
     const uint32_t bias_buf = stage_buf + EPI_STAGE_BYTES;
-    const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0), tempty_leader1 = mapa_shared(tempty_bar(1), 0);
     int it = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
       int t = tile;
@@ -837,7 +851,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
                                               res_boff, cs_boff, tn, pe_alpha);
       }
       tc_fence_before();
-      mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+      mbar_arrive(tlocal_bar(acc));
     }
   }
 
