@@ -458,6 +458,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       g.epi.alpha = 0.125f;
       c.out(g.epi, pl.scr, 0, Tp, (int64_t)T * Tp, (int64_t)H * T * Tp);
       if (P >= 2) g.epi.flags |= EPI_OUT_F32;   // multi-plane modes keep the scores in fp32 (cheaper epilogue, 4 B instead of 2P B)
+      if (P >= 2) g.block_n = 64;   // K = 64 is one k-block per tile: 64-wide tiles keep a two-stage ring and finer work items
       SPK_TRY(gemm_run(g, st));
     }
     SPK_TRY(softmax_fwd(c.ptr(pl.scr), P >= 2 ? reinterpret_cast<const float*>(c.ptr(pl.scr)) : nullptr, pl.scr.ps, P,
@@ -801,6 +802,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.planes = P; g.M = T; g.N = Tp; g.K = 64; g.nb0 = H; g.nb1 = B;
       c.out(g.epi, pl.scr, 0, Tp, sP0, sP1);
       if (P >= 2) g.epi.flags |= EPI_OUT_F32;
+      if (P >= 2) g.block_n = 64;   // as for QK^T
       SPK_TRY(gemm_run(g, st));
     }
     SPK_TRY(softmax_bwd(c.ptr(b.p), c.ptr(pl.scr), P >= 2 ? reinterpret_cast<const float*>(c.ptr(pl.scr)) : nullptr,
