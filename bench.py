@@ -2,7 +2,7 @@
 """bench.py -- GE2E train steps/sec (and d-vectors/sec) on N B200s, one process per GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework (CUDA, sm_100a)
-    python bench.py --impl reference [--steps K] [--warmup W]       # reference CPU path (oracle port)
+    python bench.py --impl reference [--steps K] [--warmup W]       # the unmodified reference on the host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W      # N > 1
 
@@ -163,12 +163,73 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port of the reference's CPU path (Device -1)
+# reference arm / CPU baseline: the UNMODIFIED reference (baseline/_ref, staged by __graft_entry__.build()) on the
+# host cores -- its `Device: '-1'` path (Train.py:34-35, README.md:56-58).  Falls back to the oracle port when the
+# staged copy is missing.
 
-def cpu_train_step_rate(steps, warmup, budget_s=150.0):
-    """Times the oracle's restatement of the reference train step (fwd + GE2E + bwd + clip + RAdam,
-    dropout on) on the host cores, on a bounded sample: `spk` speakers x 15 utterances x 160 frames.
-    Returns steps/s scaled to the full 64-speaker batch, and a description of the sample."""
+REF_COPY = os.path.join(ROOT, "baseline", "_ref")
+
+
+def step_lengths(count):
+    """One frame count per step (Datasets.py:77-84), the same sequence for every arm and every rank."""
+    rs = np.random.RandomState(0)
+    return [int(rs.randint(T_MIN, T_MAX + 1)) for _ in range(count)]
+
+
+class ReferenceTrainer:
+    """Trainer.Train_Step (Train.py:140-168) with the published optimiser pair (RAdam + Modified_Noam_Scheduler,
+    SURVEY.md D4) driving the reference's own GE2E / GE2E_Loss / RAdam / scheduler classes, unmodified, on CPU."""
+
+    def __init__(self):
+        import yaml
+        if REF_COPY not in sys.path:
+            sys.path.insert(0, REF_COPY)
+        import warnings
+        warnings.filterwarnings("ignore")
+        from Modules import GE2E, GE2E_Loss                      # baseline/_ref/Modules.py
+        from Radam import RAdam                                  # baseline/_ref/Radam.py
+        from Noam_Scheduler import Modified_Noam_Scheduler       # baseline/_ref/Noam_Scheduler.py
+        from Arg_Parser import Recursive_Parse
+        import Modules
+        assert os.path.dirname(os.path.abspath(Modules.__file__)) == REF_COPY, Modules.__file__
+        hp = Recursive_Parse(yaml.load(open(os.path.join(REF_COPY, "Hyper_Parameters.yaml")), Loader=yaml.Loader))
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        torch.manual_seed(0)
+        self.model = GE2E(hp).train()
+        self.criterion = GE2E_Loss()
+        self.optimizer = RAdam(self.model.parameters(), lr=2e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0)
+        self.scheduler = Modified_Noam_Scheduler(self.optimizer, base=4000)
+        self.gen = torch.Generator().manual_seed(1234)
+
+    def step(self, speakers, frames):
+        features = synth_mel(self.gen, speakers * UTTS, frames, "cpu")
+        embeddings = self.model(features)
+        loss = self.criterion(embeddings, UTTS)
+        self.optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(parameters=self.model.parameters(), max_norm=1.0)
+        self.optimizer.step()
+        self.scheduler.step()
+        return loss.item()
+
+
+def reference_train_step_rate(steps, warmup, lengths):
+    """steps/s of the full 64 x 15 batch on the host cores; every step is timed on the whole batch."""
+    tr = ReferenceTrainer()
+    tr.step(2, 32)                                     # thread pool / allocator warm-up, not a benchmark step
+    for i in range(warmup):
+        tr.step(SPEAKERS, lengths[i])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        tr.step(SPEAKERS, lengths[warmup + i])
+    dt = (time.perf_counter() - t0) / steps
+    sample = "full batch: 64 speakers x 15 utt x T~U[140,180] per step, %d timed step(s), dropout on" % steps
+    return 1.0 / dt, dt * 1e3, tr.cores, sample, "reference"
+
+
+def port_train_step_rate(steps, warmup, lengths):
+    """Fallback when baseline/_ref is absent: the oracle's restatement of the same step."""
     from oracle import ge2e_oracle as O
     from oracle import synth
     cores = os.cpu_count() or 1
@@ -181,8 +242,8 @@ def cpu_train_step_rate(steps, warmup, budget_s=150.0):
     m = [torch.zeros_like(p) for p in params]
     v = [torch.zeros_like(p) for p in params]
 
-    def one_step(spk, step):
-        mel = torch.as_tensor(synth.make_mel(step, spk * UTTS, 160))
+    def one_step(spk, frames, step):
+        mel = torch.as_tensor(synth.make_mel(step, spk * UTTS, frames))
         for p in params:
             p.grad = None
         d = O.encoder_forward(state, mel, 1, dropout_p=0.1, gen=gen)
@@ -195,22 +256,23 @@ def cpu_train_step_rate(steps, warmup, budget_s=150.0):
             for p, mi, vi in zip(params, m, v):
                 O.radam_step(p.detach().numpy(), (p.grad * coef).numpy(), mi.numpy(), vi.numpy(), step + 1, lr,
                              eps=1e-6)
-        return float(loss)
+        return float(loss.detach())
 
-    t0 = time.perf_counter()
-    one_step(2, 0)                                   # probe (also warms the allocator / threads)
-    per_spk = (time.perf_counter() - t0) / 2.0
-    spk = int(max(2, min(SPEAKERS, budget_s / max(per_spk * (steps + warmup), 1e-9))))
+    one_step(2, 32, 0)
     for i in range(warmup):
-        one_step(spk, i)
+        one_step(SPEAKERS, lengths[i], i)
     t0 = time.perf_counter()
     for i in range(steps):
-        one_step(spk, warmup + i)
+        one_step(SPEAKERS, lengths[warmup + i], warmup + i)
     dt = (time.perf_counter() - t0) / steps
-    rate = 1.0 / (dt * SPEAKERS / spk)
-    sample = "%d of 64 speakers x 15 utt x 160 frames per step, %d step(s), scaled x%.1f" % (
-        spk, steps, SPEAKERS / spk)
-    return rate, dt * 1e3 * SPEAKERS / spk, cores, sample
+    sample = "full batch: 64 speakers x 15 utt x T~U[140,180] per step, %d timed step(s), dropout on" % steps
+    return 1.0 / dt, dt * 1e3, cores, sample, "port"
+
+
+def cpu_train_step_rate(steps, warmup, lengths):
+    if os.path.exists(os.path.join(REF_COPY, "Modules.py")):
+        return reference_train_step_rate(steps, warmup, lengths)
+    return port_train_step_rate(steps, warmup, lengths)
 
 
 def run_reference(args):
@@ -218,14 +280,18 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    rate, ms, cores, sample = cpu_train_step_rate(steps, warmup)
+    lengths = step_lengths(max(3, warmup) + steps)[max(3, warmup) - warmup:]     # the native arm's timed lengths
+    rate, ms, cores, sample, kind = cpu_train_step_rate(steps, warmup, lengths)
     line = {
         "impl": "reference", "metric": "GE2E train steps/sec (64 spk x 15 utt, fwd+bwd+clip+RAdam/Noam)",
         "value": rate, "unit": "steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "ge2e_train_step_64x15_T140-180", "device": "cpu (reference Device -1 path)"},
-        "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "ge2e_train_step_64x15_T140-180", "speakers_per_gpu": SPEAKERS,
+                   "utterances_per_speaker": UTTS, "frames": "one T~U[140,180] per step", "mel": MEL,
+                   "optimizer": "reference RAdam lr2e-3 eps1e-6 + Modified_Noam(4000), clip 1.0", "dropout": 0.1,
+                   "device": "cpu (reference Device -1 path), %d threads" % cores},
+        "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -268,8 +334,7 @@ def run_native(args):
     opt = RAdam(model.parameters(), lr=2e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=1.0)
     sched = Modified_Noam_Scheduler(opt, base=4000)
 
-    rs = np.random.RandomState(0)
-    lengths = [int(rs.randint(T_MIN, T_MAX + 1)) for _ in range(W + 2 * K + 4)]
+    lengths = step_lengths(W + K + 4)
     # the warm-up covers the longest and the shortest slice, so that every kernel instantiation (CUDA loads kernels
     # lazily) and the largest workspace exist before the timed region, as they do after the first minutes of training
     lengths[0], lengths[1] = T_MAX, T_MIN
@@ -315,7 +380,8 @@ def run_native(args):
     del dev_mels
 
     # ---- end to end through the public API: pinned host batch -> H2D -> step -> loss D2H
-    host = [synth_mel(gen, batch, T, dev).cpu().pin_memory() for T in lengths[W + K:W + 2 * K]]
+    # (the same frame counts as the device-resident pass, so that `e2e` and `value` time the same work)
+    host = [synth_mel(gen, batch, T, dev).cpu().pin_memory() for T in lengths[W:W + K]]
     from speaker_embedding_torch_b200.Prefetch import Device_Prefetcher
     feeder = Device_Prefetcher(host, dev, reserve_bytes=batch * 80 * T_MAX * 4)     # buffers sized for Frame_Length.Max
     barrier()
@@ -331,107 +397,102 @@ def run_native(args):
     h2d = int(np.mean([h.numel() * 4 for h in host]))
     del host
 
-    # ---- per-kernel profile (events around every launch; separate pass so it does not perturb `value`)
+    # ---- per-kernel profile (events around every launch; separate pass so it does not perturb `value`), at a FIXED
+    # frame count (160, the centre of the range) so that the committed ncu DRAM-traffic capture describes the same launch
     line_extra = {}
     # every rank runs the profiled steps (backward contains the gradient all-reduce); rank 0 reports
+    prof_steps, Tprof = 2, 160
+    mel_prof = synth_mel(gen, batch, Tprof, dev)
+    step(mel_prof)                               # allocator / lazy-load warm-up at this frame count
+    torch.cuda.synchronize()
     _native.prof_enable(True)
-    prof_steps = 2
-    Tp = lengths[W]
     for i in range(prof_steps):
-        step(synth_mel(gen, batch, Tp, dev))
+        step(mel_prof)
     torch.cuda.synchronize()
     rep = _native.prof_report()
     _native.prof_enable(False)
+    del mel_prof
     barrier()
+
+    def is_contraction(tag):
+        return tag.startswith("gemm.") or tag.startswith("attn_fused") or tag.startswith("attn_train")
+
     if rank == 0:
         launches_per_step = sum(r["launches"] for r in rep.values()) // prof_steps
         tot_ms = sum(r["ms"] for r in rep.values())
-        top = max(rep.items(), key=lambda kv: kv[1]["ms"])
-        tag, r = top
+        tag, r = max(rep.items(), key=lambda kv: kv[1]["ms"])
         per_launch_ms = r["ms"] / r["launches"]
         tflops = r["flops"] / r["launches"] / (per_launch_ms * 1e-3) / 1e12
         gbs = r["bytes"] / r["launches"] / (per_launch_ms * 1e-3) / 1e9
-        tensor_bound = r["flops"] > 0 and (r["flops"] / pk["tf_sus"] / 1e12) > (r["bytes"] / pk["hbm"] / 1e9)
+        # every dense contraction of the encoder is charged against the sustained bf16 tensor peak with its
+        # bf16 dense FLOP count (the extra MMAs of the split-plane products are not credited); row kernels against HBM
+        tensor_bound = is_contraction(tag) and r["flops"] > 0
         roof = {"kernel": tag, "bound": "tensor" if tensor_bound else "hbm",
                 "achieved": tflops if tensor_bound else gbs, "peak": pk["tf_sus"] if tensor_bound else pk["hbm"],
                 "unit": "TFLOP/s" if tensor_bound else "GB/s", "traffic": None,
                 "peak_source": pk["src"] + (" sustained bf16" if tensor_bound else " copy"),
-                "launch_ms": per_launch_ms, "share_of_step": r["ms"] / tot_ms,
+                "launch_ms": per_launch_ms, "share_of_step": r["ms"] / tot_ms, "frames": Tprof,
                 "alg_flops_per_launch": r["flops"] / r["launches"], "alg_bytes_per_launch": r["bytes"] / r["launches"]}
         try:      # DRAM bytes per launch of the same kernel at the same frame count, from the committed ncu capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tr.get("frames") == Tp and tag in tr:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if tr.get("frames") == Tprof and tag in tr:
                 roof["traffic"] = tr[tag]["read"] + tr[tag]["write"]
-                roof["traffic_source"] = "profiles/r01_gemm_traffic.csv (ncu dram__bytes_read+write, T=%d)" % Tp
+                roof["traffic_source"] = tr.get("source", "profiles/r02_traffic.json")
         except (OSError, ValueError, KeyError):
             pass
         roof["frac"] = roof["achieved"] / roof["peak"]
+        # the whole step against the same peak: F_min FLOPs of forward + backward (3 x forward) at the mean frame count of
+        # the timed steps / measured step time
+        mean_fl = float(np.mean([min_flops_fwd(T) for T in lengths[W:W + K]]))
+        step_tf = 3 * batch * mean_fl * (value / world) / 1e12
+        roof["step"] = {"achieved": step_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": step_tf / pk["tf_sus"],
+                        "alg_flops_per_step": 3 * batch * mean_fl,
+                        "accounting": "3 x F_min(T) x 960 slices, SURVEY.md 8(d); extra split-plane MMAs not credited"}
         breakdown = {k: {"ms_per_step": round(v["ms"] / prof_steps, 4), "launches": v["launches"] // prof_steps,
                          "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else 0.0,
                          "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)}
                      for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
         line_extra = {"roofline": roof, "gpu_launches": launches_per_step * K, "breakdown": breakdown,
-                      "profiled_step_ms": tot_ms / prof_steps, "profiled_T": Tp}
+                      "profiled_step_ms": tot_ms / prof_steps, "profiled_T": Tprof}
 
-        # ---- d-vectors/sec, 160-frame slices, eval (BASELINE metric part 1)
-        model.eval()
-        mel160 = synth_mel(gen, batch, 160, dev)
-        with torch.no_grad():
-            for _ in range(3):
-                model(mel160)
-            torch.cuda.synchronize()
-            e0.record()
-            reps = 10
-            for _ in range(reps):
-                model(mel160)
-            e1.record()
-            torch.cuda.synchronize()
-        dv_ms = e0.elapsed_time(e1) / reps
+    # ---- inference metrics of BASELINE.json on every rank (utterance shards, no collective; max over ranks):
+    #      d-vectors/s on 160-frame slices and config 3 (5 x 64-frame slices, 32 overlap) incl. its end-to-end path
+    infer = run_infer_shard(model, gen, dev, world, rank, barrier, dist)
+    if rank == 0:
+        dv_ms = infer.pop("_dv_ms")
         _native.prof_enable(True)
+        model.eval()
         with torch.no_grad():
-            model(mel160)
+            model(synth_mel(gen, batch, 160, dev))
         torch.cuda.synchronize()
         irep = _native.prof_report()
         _native.prof_enable(False)
+        model.train()
+        line_extra["infer"] = infer
         line_extra["infer_breakdown"] = {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                                              "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else 0.0,
                                              "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)}
                                          for k, v in sorted(irep.items(), key=lambda kv: -kv[1]["ms"])}
-        # config 3 shape: multi-slice inference, 5 x 64-frame slices per utterance (Inference.py:95-115)
-        utt = 4000
-        mel564 = synth_mel(gen, utt * 5, 64, dev)
-        with torch.no_grad():
-            model(mel564, 5)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(3):
-                model(mel564, 5)
-            e1.record()
-            torch.cuda.synchronize()
-        ms564 = e0.elapsed_time(e1) / 3
-        del mel564
-        model.train()
-        line_extra["extra"] = {"multislice_utt_per_sec_5x64_1gpu": utt / (ms564 * 1e-3),"dvectors_per_sec_160f_1gpu": batch / (dv_ms * 1e-3), "infer_ms_per_960x160_batch": dv_ms,
-                               "flop_accounting": "F_min (last layer pruned to the t=0 query), bf16 dense count, extra split-plane MMAs not credited",
+        line_extra["extra"] = {"flop_accounting": "F_min (last layer pruned to the t=0 query), bf16 dense count, extra split-plane MMAs not credited",
                                "infer_tensor_frac_of_sustained": batch * min_flops_fwd(160) / (dv_ms * 1e-3) / 1e12 / pk["tf_sus"],
-                               "train_tensor_frac_of_sustained": 3 * batch * min_flops_fwd(160) * value / world / 1e12 / pk["tf_sus"],
-                               "last_loss": last_loss}
+                               "train_precision": int(model.train_precision), "last_loss": last_loss}
 
     barrier()
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            try:
-                rate, cms, cores, sample = cpu_train_step_rate(1, 0, budget_s=25.0)
-                cpu = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+            try:   # bounded sample: two full-batch steps of the reference on the host cores (~15-20 s)
+                rate, cms, cores, sample, kind = cpu_train_step_rate(2, 0, lengths[W:W + 2])
+                cpu = {"value": rate, "unit": "steps/s", "cores": cores, "kind": kind, "sample": sample}
             except Exception as exc:  # the baseline must never take the GPU number down with it
-                cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+                cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "reference",
                        "sample": "failed: %r" % (exc,)}
         line = {
             "metric": "GE2E train steps/sec (64 spk x 15 utt, fwd+bwd+clip+RAdam/Noam)",
             "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 (split-bf16 hi+lo operands, fp32 accumulate)", "data": "synthetic",
+            "dtype": "bf16 (split into %d planes per operand forward / 2 backward, fp32 accumulate)" % int(model.train_precision),
+            "data": "synthetic",
             "config": {"workload": "ge2e_train_step_64x15_T140-180", "speakers_per_gpu": SPEAKERS,
                        "utterances_per_speaker": UTTS, "frames": "one T~U[140,180] per step", "mel": MEL,
                        "optimizer": "fused RAdam lr2e-3 eps1e-6 + Modified_Noam(4000), clip 1.0",
@@ -445,6 +506,75 @@ def run_native(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_infer_shard(model, gen, dev, world, rank, barrier, dist, utt=4000, reps=5):
+    """BASELINE config 3 on this rank's shard: `utt` utterances per step, 5 x 64-frame slices at 32 overlap
+    (Inference.py:95-115), `reps` timed steps; plus the 160-frame single-slice d-vector rate.  Returns rank-0 dict
+    with whole-job numbers (time = max over ranks; utterances are independent, there is no collective)."""
+    from speaker_embedding_torch_b200.Prefetch import Device_Prefetcher
+    pk = peaks()
+    batch = SPEAKERS * UTTS
+    S, F, O = 5, 64, 32
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def max_ms(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    model.eval()
+    with torch.no_grad():
+        mel160 = synth_mel(gen, batch, 160, dev)
+        for _ in range(3):
+            model(mel160)
+        barrier()
+        e0.record()
+        for _ in range(10):
+            model(mel160)
+        e1.record()
+        barrier()
+        dv_ms = max_ms(e0.elapsed_time(e1)) / 10
+        del mel160
+        windows = synth_mel(gen, utt, S * (F - O) + O, dev)                      # [utt, 80, 192]
+        for _ in range(3):
+            model.embed_windows(windows, F, O)
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            out = model.embed_windows(windows, F, O)
+        e1.record()
+        barrier()
+        ms = max_ms(e0.elapsed_time(e1))
+        # end to end: fp16 192-frame windows (as the reference stores its patterns, Pattern_Generator.py:123) cross PCIe
+        # through Device_Prefetcher, slices are cut and upcast inside the prenet load, d-vectors are read back
+        host_windows = windows.half().cpu().pin_memory()
+        feeder = Device_Prefetcher([host_windows] * reps, dev, reserve_bytes=host_windows.numel() * 2)
+        host_out = [torch.empty(utt, 256).pin_memory() for _ in range(reps)]
+        model.embed_windows(windows.half(), F, O)
+        barrier()
+        e0.record()
+        for i, w in enumerate(feeder):
+            host_out[i].copy_(model.embed_windows(w, F, O), non_blocking=True)
+        e1.record()
+        barrier()
+        ms_e2e = max_ms(e0.elapsed_time(e1))
+        checksum = float(out.float().sum().item())
+    model.train()
+    if rank != 0:
+        return {}
+    flops = utt * S * min_flops_fwd(F)
+    return {"_dv_ms": dv_ms,
+            "dvectors_per_sec_160f": world * batch / (dv_ms * 1e-3), "ms_per_960x160_batch": dv_ms,
+            "config3": {"metric": "utterances/sec, multi-slice extraction 5 x 64 frames / 32 overlap",
+                        "value": world * reps * utt / (ms * 1e-3), "unit": "utterances/s",
+                        "utterances_per_step_per_gpu": utt, "steps": reps, "ms_per_step": ms / reps, "n_gpus": world,
+                        "sharding": "utterance shards, no collective",
+                        "e2e": {"value": world * reps * utt / (ms_e2e * 1e-3), "unit": "utterances/s",
+                                "h2d_bytes_per_step": host_windows.numel() * 2, "d2h_bytes_per_step": utt * 256 * 4},
+                        "tensor_frac_of_sustained": flops * reps / (ms * 1e-3) / 1e12 / pk["tf_sus"],
+                        "dvec_checksum": checksum}}
 
 
 def run_infer(args):

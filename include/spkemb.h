@@ -30,6 +30,10 @@ extern "C" {
 #define SPK_ENOMEM (-12)
 #define SPK_EIO (-5)
 #define SPK_MAX_LAYERS 8
+#define SPK_PLAN_EXPLICIT (1 << 8)          /* the bits below are valid */
+#define SPK_PLAN_PRUNE (1 << 9)             /* "prune_last_layer" */
+#define SPK_PLAN_FUSED_INFER_ATTN (1 << 10) /* "fused_inference_attention" */
+#define SPK_PLAN_FUSED_TRAIN_ATTN (1 << 11) /* "fused_training_attention" */
 
 int spk_abi_version(void);
 const char* spk_last_error(void);
@@ -72,8 +76,11 @@ typedef struct spk_encoder_params {
   float* proj_b;     /* [emb] */
 } spk_encoder_params;
 
-/* precision: 1 = bf16 operands (inference), 2 = split-bf16 hi+lo (3 MMAs per product), 3 = hi+mid+lo
+/* precision (low 8 bits): 1 = bf16 operands (inference), 2 = split-bf16 hi+lo (3 MMAs per product), 3 = hi+mid+lo
  * (6 MMAs, fp32-equivalent forward; the backward pass then reads two of the three planes).
+ * Upper bits: the library options that shape the workspace (SPK_PLAN_*).  A caller that wants its backward call to
+ * be immune to spk_set_option() between forward and backward passes `precision | spk_plan_flags()` to
+ * workspace_bytes / forward / backward alike; without SPK_PLAN_EXPLICIT the process-wide options apply.
  * keep_stash: 1 when spk_encoder_backward will follow (activations of every layer are kept). */
 size_t spk_encoder_workspace_bytes(const spk_encoder_config* cfg, int batch, int frames, int samples,
                                    int precision, int keep_stash);
@@ -111,6 +118,15 @@ int spk_encoder_backward(const spk_encoder_config* cfg, const spk_encoder_params
 /* Test aid: text table "name byte_offset plane_stride" of the workspace buffers (returns bytes written). */
 int spk_encoder_debug_layout(const spk_encoder_config* cfg, int batch, int frames, int samples, int precision,
                              int keep_stash, char* buf, size_t cap);
+
+/* Test aid: the dropout keep-scale (0 or 1 / (1 - p_q), p_q = round(p * 2^16) / 2^16) of elements
+ * [8 * idx8_begin, 8 * (idx8_begin + n8)) of dropout site `site` under `seed` -- the pure function of
+ * (seed, site, element) that the forward and backward kernels evaluate.  Sites: 0 = positional encoding
+ * (Modules.py:103; element = token * emb + channel); layer l: 1 + 4l attention probabilities (element = ((slice *
+ * heads + head) * frames + query) * frames_padded_to_8 + key; pruned last layer: (slice * heads + head) *
+ * frames_padded_to_8 + key), 2 + 4l dropout1, 3 + 4l FFN inner (element = token * ffn + unit), 4 + 4l dropout2
+ * (torch TransformerEncoderLayer; element = token * emb + channel; in the pruned last layer `token` = slice). */
+int spk_dropout_keep(uint64_t seed, float p, uint32_t site, uint64_t idx8_begin, int64_t n8, float* out, void* stream);
 
 /* GE2E_Loss.forward + backward (Modules.py:121-156) as one fused kernel.
  * emb [speakers*per_speaker, dim] fp32, speaker-major rows; weight/bias: device pointers to the
@@ -160,6 +176,8 @@ int spk_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   "gemm_cta_pairs"             multi-plane GEMMs on CTA pairs (tcgen05.mma.cta_group::2); 0 = single-CTA kernel
  *                                (bit-identical results, used by the tests as the cross-check). */
 int spk_set_option(const char* name, int value);
+/* Snapshot of the options above as SPK_PLAN_* bits (SPK_PLAN_EXPLICIT set), to be OR-ed into `precision`. */
+int spk_plan_flags(void);
 
 /* Launch profiler (used by bench.py for the per-kernel roofline): when enabled every launcher brackets
  * its kernel with CUDA events on the launching stream.  spk_prof_report synchronises those events,

@@ -46,7 +46,9 @@ def _layer_norm(x, w, b):
     return xc / torch.sqrt(var + LN_EPS) * w + b
 
 
-def _dropout(x, p, gen):
+def _dropout(x, p, gen, scale=None):
+    if scale is not None:           # explicit keep-scales (0 or 1/(1-p)), e.g. the masks the CUDA kernels used
+        return x * scale.to(x.dtype)
     if p <= 0.0:
         return x
     keep = (torch.rand(x.shape, generator=gen, dtype=torch.float32) >= p).to(x.dtype)
@@ -54,14 +56,18 @@ def _dropout(x, p, gen):
 
 
 def encoder_forward(state, mel, samples=1, heads=4, layers=3, dropout_p=0.0, gen=None,
-                    return_intermediates=False):
+                    return_intermediates=False, drop_scales=None):
     """d-vectors [B/samples, D] from mel [B, mel_dim, T]  (Modules.py:46-59).
 
     ``state`` is a dict of torch tensors with the reference's state_dict names.
     Token-major restatement: h is [B, T, D]; every k=1 conv / linear is h @ W^T + b.
     ``dropout_p`` > 0 reproduces the reference's 13 train-mode dropout sites
-    statistically (the RNG stream differs).
+    statistically (the RNG stream differs; SURVEY.md D9).  ``drop_scales`` = {site: keep-scale tensor}
+    replaces the random masks by given ones (sites numbered as in include/spkemb.h: 0 positional encoding,
+    1 + 4l attention probabilities [B, H, T, T], 2 + 4l dropout1, 3 + 4l FFN inner [B, T, 4D], 4 + 4l dropout2),
+    which is how the tests check that the CUDA forward and backward apply one and the same mask per site.
     """
+    ds = drop_scales or {}
     x = mel.transpose(1, 2)                                   # [B, T, mel]
     B, T, _ = x.shape
     w_pre = state["prenet.weight"][:, :, 0]                   # [D, mel]
@@ -69,7 +75,7 @@ def encoder_forward(state, mel, samples=1, heads=4, layers=3, dropout_p=0.0, gen
     D = h.shape[-1]
     pe = state["positional_encoding.pe"][0, :, :T].t()        # [T, D]  (Modules.py:107-109)
     h = h + state["positional_encoding.alpha"] * pe           # Modules.py:102
-    h = _dropout(h, dropout_p, gen)                           # Modules.py:103
+    h = _dropout(h, dropout_p, gen, ds.get(0))                # Modules.py:103
     dh = D // heads
     inter = {"embed": h}
     for l in range(layers):
@@ -82,14 +88,16 @@ def encoder_forward(state, mel, samples=1, heads=4, layers=3, dropout_p=0.0, gen
         v = v.reshape(B, T, heads, dh).transpose(1, 2)
         s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)         # SDPA scale 1/sqrt(64)
         pr = torch.softmax(s, dim=-1)
-        pr = _dropout(pr, dropout_p, gen)                     # attention-prob dropout
+        pr = _dropout(pr, dropout_p, gen, ds.get(1 + 4 * l))  # attention-prob dropout
         a = (pr @ v).transpose(1, 2).reshape(B, T, D)
         a = a @ state[p + "self_attn.out_proj.weight"].t() + state[p + "self_attn.out_proj.bias"]
-        h = _layer_norm(h + _dropout(a, dropout_p, gen), state[p + "norm1.weight"], state[p + "norm1.bias"])
+        h = _layer_norm(h + _dropout(a, dropout_p, gen, ds.get(2 + 4 * l)), state[p + "norm1.weight"],
+                        state[p + "norm1.bias"])
         f = torch.relu(h @ state[p + "linear1.weight"].t() + state[p + "linear1.bias"])
-        f = _dropout(f, dropout_p, gen)
+        f = _dropout(f, dropout_p, gen, ds.get(3 + 4 * l))
         f = f @ state[p + "linear2.weight"].t() + state[p + "linear2.bias"]
-        h = _layer_norm(h + _dropout(f, dropout_p, gen), state[p + "norm2.weight"], state[p + "norm2.bias"])
+        h = _layer_norm(h + _dropout(f, dropout_p, gen, ds.get(4 + 4 * l)), state[p + "norm2.weight"],
+                        state[p + "norm2.bias"])
         inter["layer%d" % l] = h
     h0 = _layer_norm(h[:, 0, :], state["transformer.norm.weight"], state["transformer.norm.bias"])  # Modules.py:33-35,54
     e = h0.reshape(-1, samples, D).mean(dim=1)                # Modules.py:55
@@ -156,13 +164,53 @@ def ge2e_loss_and_grads_closed_form(emb, per_speaker, weight=10.0, bias=-5.0):
     return loss, dE, dw, db
 
 
+def ge2e_closed_form_chunked(emb, per_speaker, weight=10.0, bias=-5.0, rows_per_chunk=4096):
+    """The closed form above evaluated in row chunks, so that N = 4096 (a 61 440 x 4 096 logit matrix, 2 GB in
+    fp64) never exists at once.  Same results as ``ge2e_loss_and_grads_closed_form`` (checked in the CPU tests)."""
+    E = np.asarray(emb, dtype=np.float64)
+    NM, D = E.shape
+    M = per_speaker
+    N = NM // M
+    c = E.reshape(N, M, D).mean(axis=1)
+    ne = np.maximum(np.linalg.norm(E, axis=1, keepdims=True), COS_EPS)
+    nc = np.maximum(np.linalg.norm(c, axis=1, keepdims=True), COS_EPS)
+    eh, ch = E / ne, c / nc
+    lab = np.repeat(np.arange(N), M)
+    loss = 0.0
+    dw = 0.0
+    db = 0.0
+    de_h = np.empty_like(E)
+    dc_h = np.zeros_like(c)
+    for r0 in range(0, NM, rows_per_chunk):
+        r1 = min(NM, r0 + rows_per_chunk)
+        S = eh[r0:r1] @ ch.T
+        z = weight * S - bias
+        zmax = z.max(axis=1, keepdims=True)
+        ex = np.exp(z - zmax)
+        den = ex.sum(axis=1, keepdims=True)
+        rows = np.arange(r1 - r0)
+        loss += float(np.sum(np.log(den[:, 0]) + zmax[:, 0] - z[rows, lab[r0:r1]]))
+        pm = ex / den
+        pm[rows, lab[r0:r1]] -= 1.0
+        pm /= NM
+        dw += float((pm * S).sum())
+        db += float(-pm.sum())
+        G = weight * pm
+        de_h[r0:r1] = G @ ch
+        dc_h += G.T @ eh[r0:r1]
+    dE = (de_h - (de_h * eh).sum(1, keepdims=True) * eh) / ne
+    dc = (dc_h - (dc_h * ch).sum(1, keepdims=True) * ch) / nc
+    dE = dE + np.repeat(dc, M, axis=0) / M
+    return loss / NM, dE, dw, db
+
+
 def train_step_grads(state_np, mel_np, per_speaker, weight=10.0, bias=-5.0, dtype=torch.float64,
-                     samples=1):
+                     samples=1, drop_scales=None):
     """Loss, d-vectors and every parameter gradient via autograd through the restatement."""
     st = to_torch_state(state_np, dtype=dtype, requires_grad=True)
     w = torch.tensor(weight, dtype=dtype, requires_grad=True)
     b = torch.tensor(bias, dtype=dtype, requires_grad=True)
-    d = encoder_forward(st, torch.as_tensor(mel_np).to(dtype), samples=samples)
+    d = encoder_forward(st, torch.as_tensor(mel_np).to(dtype), samples=samples, drop_scales=drop_scales)
     loss = ge2e_loss(d, per_speaker, w, b)
     loss.backward()
     grads = {k: v.grad.detach().numpy() for k, v in st.items() if v.requires_grad}

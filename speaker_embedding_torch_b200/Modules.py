@@ -145,6 +145,8 @@ def _run_forward(cfg, names, params, pe, features, samples, precision, training,
         if p.dtype != torch.float32 or not p.is_contiguous():
             raise RuntimeError("parameter %s must be contiguous fp32" % n)
         tensors[n] = p
+    if precision < 256:
+        precision |= N.plan_flags()          # the backward call receives the same bits through ctx.meta
     with torch.cuda.device(features.device):
         weights = _fill_params(N.EncoderParams(), tensors, pe, cfg.layers)
         ws, nbytes = _workspace(cfg, batch, frames, samples, precision, int(keep), features.device)
@@ -155,7 +157,7 @@ def _run_forward(cfg, names, params, pe, features, samples, precision, training,
                                                  N.ptr(dvec), _aligned_ptr(ws), nbytes, int(keep),
                                                  N.stream_ptr(features.device)),
                 "spk_encoder_forward_view")
-    return dvec, ws, nbytes, (batch, frames)
+    return dvec, ws, nbytes, (batch, frames, precision)
 
 
 class _EncoderFunction(torch.autograd.Function):
@@ -167,8 +169,9 @@ class _EncoderFunction(torch.autograd.Function):
         names = module._param_names
         cfg = module._cfg
         pe = module.positional_encoding.pe
-        dvec, ws, nbytes, (batch, frames) = _run_forward(cfg, names, [p.detach() for p in params], pe, features,
-                                                         samples, precision, training, seed, keep=True)
+        dvec, ws, nbytes, (batch, frames, precision) = _run_forward(cfg, names, [p.detach() for p in params], pe,
+                                                                    features, samples, precision, training, seed,
+                                                                    keep=True)
         ctx.module, ctx.ws, ctx.nbytes = module, ws, nbytes
         ctx.meta = (batch, frames, samples, precision, training, seed)
         ctx.save_for_backward(*params)
@@ -188,7 +191,7 @@ class _EncoderFunction(torch.autograd.Function):
         for s in sizes:
             offsets.append(total)
             total += (s + 3) // 4 * 4          # keep every view 16-byte aligned
-        arena = module._grad_arena(total, device)
+        arena = module._grad_arena(total, device, params)
         views = [arena[o:o + s].view_as(p) for o, s, p in zip(offsets, sizes, params)]
         with torch.cuda.device(device):
             weights = _fill_params(N.EncoderParams(), dict(zip(names, [p.detach() for p in params])), ctx.pe,
@@ -244,9 +247,23 @@ class GE2E(torch.nn.Module):
 
     # flat fp32 gradient arena: every parameter gradient is a view of it, so the data-parallel
     # allreduce (distributed.apply_gradient_allreduce) is one in-place collective with no copies.
-    def _grad_arena(self, numel, device):
-        arena = torch.zeros(numel, dtype=torch.float32, device=device)
-        self._arena = arena
+    # The arena is persistent (re-zeroed, not re-allocated, every backward) and carries four spare floats behind the
+    # gradients: element `numel` is where distributed.allreduce_gradients parks the step's loss so that the logging
+    # mean of Train.py:166-168 rides on the gradient collective.  If a caller still holds .grad tensors
+    # that alias the arena (zero_grad(set_to_none=False)), autograd would accumulate a view onto itself, so a fresh
+    # buffer is used for that backward instead.
+    def _grad_arena(self, numel, device, params=()):
+        arena = self._arena
+        reusable = (arena is not None and arena.device == device and arena.numel() == numel + 4)
+        if reusable:
+            lo, hi = arena.data_ptr(), arena.data_ptr() + arena.numel() * 4
+            reusable = not any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in params)
+        if reusable:
+            arena.zero_()
+        else:
+            arena = torch.zeros(numel + 4, dtype=torch.float32, device=device)
+            self._arena = arena
+        self._arena_numel = numel
         return arena
 
     def forward(self, features, samples=1):
@@ -397,4 +414,10 @@ class GE2E_Loss(torch.nn.Module):
         if not torch.is_grad_enabled():
             return _GE2ELossFunction.apply(embeddings.detach(), self.weight.detach(), self.bias.detach(),
                                            int(pattern_per_speaker))
-        return _GE2ELossFunction.apply(embeddings, self.weight, self.bias, int(pattern_per_speaker))
+        loss = _GE2ELossFunction.apply(embeddings, self.weight, self.bias, int(pattern_per_speaker))
+        LAST_TRAINING_LOSS[loss.device] = loss.detach()      # picked up by distributed.allreduce_gradients
+        return loss
+
+
+# device -> the most recent training loss (a 0-dim tensor); see distributed.allreduce_gradients / reduce_tensor
+LAST_TRAINING_LOSS = {}

@@ -22,7 +22,8 @@ EXPORTS = (
     "spk_abi_version", "spk_last_error", "spk_encoder_workspace_bytes", "spk_encoder_forward",
     "spk_encoder_backward", "spk_ge2e_workspace_bytes", "spk_ge2e_loss", "spk_optim_step",
     "spk_gemm", "spk_split_pack", "spk_device_info", "spk_prof_enable", "spk_prof_report",
-    "spk_encoder_debug_layout", "spk_set_option", "spk_encoder_forward_view",
+    "spk_encoder_debug_layout", "spk_set_option", "spk_encoder_forward_view", "spk_plan_flags",
+    "spk_dropout_keep",
 )
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
@@ -139,6 +140,10 @@ def lib():
         L.spk_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.spk_set_option.restype = i32
         L.spk_set_option.argtypes = [ctypes.c_char_p, i32]
+        L.spk_dropout_keep.restype = i32
+        L.spk_dropout_keep.argtypes = [u64, f32, ctypes.c_uint32, u64, i64, vp, vp]
+        L.spk_plan_flags.restype = i32
+        L.spk_plan_flags.argtypes = []
         L.spk_prof_enable.restype = i32
         L.spk_prof_enable.argtypes = [i32]
         L.spk_prof_report.restype = i32
@@ -272,6 +277,22 @@ def prof_report():
         tag, cnt, ms, fl, by = line.split()
         out[tag] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by))
     return out
+
+
+def dropout_keep(seed, p, site, numel, device):
+    """Keep-scales (0 or 1/(1-p_q)) of elements [0, numel) of dropout site ``site`` (tests: masks fed to the oracle)."""
+    n8 = (numel + 7) // 8
+    out = torch.empty(n8 * 8, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(lib().spk_dropout_keep(ctypes.c_uint64(seed), float(p), int(site), ctypes.c_uint64(0), n8, ptr(out),
+                                     stream_ptr(device)), "spk_dropout_keep")
+    return out[:numel]
+
+
+def plan_flags():
+    """SPK_PLAN_* snapshot of the layout-shaping options, OR-ed into ``precision`` by the module layer so that a
+    backward call rebuilds exactly the plan of its forward call."""
+    return int(lib().spk_plan_flags())
 
 
 def set_option(name, value):

@@ -54,6 +54,10 @@ int spk_encoder_debug_layout(const spk_encoder_config* cfg, int batch, int frame
   return encoder_debug_layout(*cfg, batch, frames, samples, precision, keep_stash, buf, cap);
 }
 
+int spk_dropout_keep(uint64_t seed, float p, uint32_t site, uint64_t idx8_begin, int64_t n8, float* out, void* stream) {
+  return dropout_keep(seed, p, site, idx8_begin, n8, out, as_stream(stream));
+}
+
 size_t spk_ge2e_workspace_bytes(int speakers, int per_speaker) { return ge2e_workspace_bytes(speakers, per_speaker); }
 
 int spk_ge2e_loss(const float* emb, int speakers, int per_speaker, int dim, const float* weight, const float* bias,
@@ -101,10 +105,13 @@ int spk_set_option(const char* name, int value) {
   SPK_CHECK(name != nullptr, "spk_set_option: null name");
   if (strcmp(name, "prune_last_layer") == 0) { encoder_set_prune(value != 0); return 0; }
   if (strcmp(name, "fused_inference_attention") == 0) { encoder_set_fused_attn(value != 0); return 0; }
+  if (strcmp(name, "fused_training_attention") == 0) { encoder_set_fused_train_attn(value != 0); return 0; }
   if (strcmp(name, "gemm_cta_pairs") == 0) { gemm_set_cta_pairs(value != 0); return 0; }
   set_error("spk_set_option: unknown option '%s'", name);
   return SPK_EINVAL;
 }
+
+int spk_plan_flags(void) { return encoder_plan_flags(); }
 
 int spk_prof_enable(int on) { prof_set(on != 0); return 0; }
 int spk_prof_report(char* buf, size_t cap) { return prof_report(buf, cap); }

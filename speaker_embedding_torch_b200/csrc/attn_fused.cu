@@ -218,11 +218,11 @@ int attn_fused_fwd(const void* qkv, void* out, int64_t out_ld, int B, int H, int
   SPK_TRY(encode_map_4d(&a.q_map, base, dims, strides, 128));
   SPK_TRY(encode_map_4d(&a.k_map, base + 64 * H, dims, strides, a.Tk64));
   SPK_TRY(encode_map_4d(&a.v_map, base + 2 * 64 * H, dims, strides, a.Tk64));
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  SPK_TRY(once.run([]() -> int {
     SPK_CUDA(cudaFuncSetAttribute(attn_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-    configured = true;
-  }
+    return 0;
+  }));
   const int items = B * H * a.mtiles;
   const int grid = items < device_sm_count() ? items : device_sm_count();
   ProfScope prof("attn_fused_fwd", 4.0 * B * H * T * T * 64, 4.0 * B * T * 64 * H * 2.0, st);

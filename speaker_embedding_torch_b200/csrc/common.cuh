@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 
 namespace spk {
 
@@ -26,6 +27,24 @@ struct ProfScope {
   }
   ~ProfScope() {
     if (idx >= 0) prof_end(idx, st);
+  }
+};
+
+// One-time setup per (call site, device): cudaFuncSetAttribute / occupancy queries are per device, so a process that
+// touches a second GPU must repeat them there.  Thread-safe; the body's error code is returned and not latched.
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  template <class F>
+  int run(F fn) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return 0;
+    const int r = fn();
+    if (r == 0) done[dev] = true;
+    return r;
   }
 };
 

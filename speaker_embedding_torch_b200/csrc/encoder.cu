@@ -43,7 +43,7 @@ struct LastBufs {
 struct Plan {
   int B, T, S, P, Tp, H, D, F, C, L;
   int64_t Mt, BH;
-  bool keep, prune;
+  bool keep, prune, fused_infer, fused_train;
   LastBufs last;
   Split wpack;
   int64_t w_pre, w_in[SPK_MAX_LAYERS], w_out[SPK_MAX_LAYERS], w_l1[SPK_MAX_LAYERS], w_l2[SPK_MAX_LAYERS];
@@ -51,7 +51,7 @@ struct Plan {
   size_t pe_t;
   LayerBufs Lb[SPK_MAX_LAYERS];
   size_t hn, hst, emean, epre, de;
-  Split dh_a, dh_b, dz, dzd, df, datt, dqkv, ds;
+  Split dh_a, dh_b, dz, dzd, df, datt, dqkv, ds, dq0;
   size_t total;
 };
 
@@ -72,8 +72,20 @@ static bool g_prune_last = true;   // spk_set_option("prune_last_layer", 0/1)
 void encoder_set_prune(bool on) { g_prune_last = on; }
 static bool g_fused_attn = true;   // spk_set_option("fused_inference_attention", 0/1)
 void encoder_set_fused_attn(bool on) { g_fused_attn = on; }
+static bool g_fused_train_attn = true;   // spk_set_option("fused_training_attention", 0/1)
+void encoder_set_fused_train_attn(bool on) { g_fused_train_attn = on; }
 
-static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bool keep, Plan& pl) {
+// The options that shape the workspace layout travel with the call: `precision` carries them in its upper bits
+// (SPK_PLAN_*, include/spkemb.h) so that a backward pass always rebuilds the plan its forward pass used, whatever
+// spk_set_option did in between.  Without SPK_PLAN_EXPLICIT the process-wide options apply.
+int encoder_plan_flags() {
+  return SPK_PLAN_EXPLICIT | (g_prune_last ? SPK_PLAN_PRUNE : 0) | (g_fused_attn ? SPK_PLAN_FUSED_INFER_ATTN : 0) |
+         (g_fused_train_attn ? SPK_PLAN_FUSED_TRAIN_ATTN : 0);
+}
+
+static int make_plan(const spk_encoder_config& c, int B, int T, int S, int Pflags, bool keep, Plan& pl) {
+  const int P = Pflags & 0xFF;
+  const int opt = (Pflags & SPK_PLAN_EXPLICIT) ? Pflags : encoder_plan_flags();
   SPK_CHECK(c.mel_dim == 80 && c.emb == 256 && c.heads == 4 && c.ffn == 1024,
             "encoder: this build supports Mel_Dim 80, Embedding_Size 256, Head 4 (got %d/%d/%d/%d)", c.mel_dim, c.emb,
             c.heads, c.ffn);
@@ -87,7 +99,9 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
   pl.Mt = static_cast<int64_t>(B) * T;
   pl.BH = static_cast<int64_t>(B) * pl.H;
   pl.keep = keep;
-  pl.prune = g_prune_last;
+  pl.prune = (opt & SPK_PLAN_PRUNE) != 0;
+  pl.fused_infer = (opt & SPK_PLAN_FUSED_INFER_ATTN) != 0;
+  pl.fused_train = (opt & SPK_PLAN_FUSED_TRAIN_ATTN) != 0;
   const int64_t D = pl.D, F = pl.F, Mt = pl.Mt;
   size_t cur = 0;
   // packed weights
@@ -153,6 +167,9 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int P, bo
     pl.datt = take_split(cur, Mt * D, Pb);
     pl.dqkv = take_split(cur, Mt * 3 * D, Pb);
     pl.ds = take_split(cur, pl.BH * T * pl.Tp, Pb);
+    // compact [B, 256] gradient of the last layer's single query row (its own buffer: scr is BH*T*Tp elements per
+    // plane, smaller than B*256 for T < 8)
+    if (pl.prune) pl.dq0 = take_split(cur, static_cast<int64_t>(B) * D, Pb);
   }
   pl.total = cur + 1024;
   return 0;
@@ -402,6 +419,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
                     cudaStream_t st) {
   Plan pl;
   SPK_TRY(make_plan(cfg, B, T, S, P, keep != 0, pl));
+  P = pl.P;     // the upper bits carried the plan options
   if (ws_bytes < pl.total) { set_error("encoder: workspace too small (%zu < %zu)", ws_bytes, pl.total); return SPK_ENOMEM; }
   SPK_CHECK((reinterpret_cast<uintptr_t>(ws_v) & 255) == 0, "encoder: workspace must be 256-byte aligned");
   SPK_CHECK(!training || keep, "encoder: training forward needs keep_stash (dropout P buffers live in the stash)");
@@ -445,7 +463,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       SPK_TRY(gemm_run(g, st));
     }
     // inference (one plane, nothing kept for a backward pass): scores, softmax and PV in one tcgen05 kernel
-    const bool fused_attn = (P == 1) && !keep && !training && T <= 256 && g_fused_attn;
+    const bool fused_attn = (P == 1) && !keep && !training && T <= 256 && pl.fused_infer;
     if (fused_attn) {
       SPK_TRY(attn_fused_fwd(c.ptr(b.qkv), c.ptr(b.att), D, B, H, T, st));
     } else {
@@ -597,6 +615,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
                      size_t ws_bytes, cudaStream_t st) {
   Plan pl;
   SPK_TRY(make_plan(cfg, B, T, S, P_fwd, true, pl));
+  P_fwd = pl.P;
   if (ws_bytes < pl.total) { set_error("encoder: workspace too small (%zu < %zu)", ws_bytes, pl.total); return SPK_ENOMEM; }
   const int P = P_fwd < 2 ? P_fwd : 2;   // the stash may hold 3 planes; the backward pass reads / writes 2
   Ctx c{pl, reinterpret_cast<char*>(ws_v), st, P};
@@ -685,11 +704,11 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       c.out(g.epi, pl.datt, 0, D);
       SPK_TRY(gemm_run(g, st));
     }
-    // single-query attention backward: dq0 -> scr (compact), dK | dV -> dqkv viewed as [Mt, 512]
+    // single-query attention backward: dq0 (compact [B, 256]), dK | dV -> dqkv viewed as [Mt, 512]
     SPK_TRY(attn_row0_bwd(c.ptr(pl.datt), pl.datt.ps, P, c.ptr(lb.q0), lb.q0.ps, c.ptr(lb.kv), lb.kv.ps, P_fwd,
-                          c.f32(lb.p0), c.f32(lb.pd0), c.ptr(pl.scr), pl.scr.ps, c.ptr(pl.dqkv), pl.dqkv.ps,
+                          c.f32(lb.p0), c.f32(lb.pd0), c.ptr(pl.dq0), pl.dq0.ps, c.ptr(pl.dqkv), pl.dqkv.ps,
                           lg.in_proj_b, B, H, T, Tp, st));
-    SPK_TRY(small_wgrad(pl.scr, D, hin, D, (int64_t)T * D, lg.in_proj_w, "gemm.last.bwd.q_wgrad"));
+    SPK_TRY(small_wgrad(pl.dq0, D, hin, D, (int64_t)T * D, lg.in_proj_w, "gemm.last.bwd.q_wgrad"));
     {  // dW[K|V rows] = dKV^T hin
       GemmProblem g;
       g.tag = "gemm.last.bwd.kv_wgrad";
@@ -715,7 +734,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     {  // t = 0 rows additionally receive dq0 Wq and the residual path dZ1
       GemmProblem g;
       g.tag = "gemm.last.bwd.q_dgrad";
-      g.A = c.mat(pl.scr, 0, B, D, D);
+      g.A = c.mat(pl.dq0, 0, B, D, D);
       g.B = c.mat(pl.wpack, pl.w_in[l], D, D, D);
       g.b_mn = true;
       g.planes = P; g.M = B; g.N = (int)D; g.K = (int)D;

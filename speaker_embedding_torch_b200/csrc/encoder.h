@@ -15,4 +15,6 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
 int encoder_debug_layout(const spk_encoder_config& c, int B, int T, int S, int P, int keep, char* buf, size_t cap);
 void encoder_set_prune(bool on);
 void encoder_set_fused_attn(bool on);
+void encoder_set_fused_train_attn(bool on);
+int encoder_plan_flags();
 }  // namespace spk

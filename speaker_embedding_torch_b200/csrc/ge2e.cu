@@ -310,17 +310,22 @@ int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float*
   float* cinv = dchat + static_cast<size_t>(N) * GD;
   float* einv = cinv + N;
 
-  static int max_blocks = 0;
+  static int max_blocks_dev[64] = {};
+  static PerDeviceOnce once;
   const int smem = static_cast<int>(sizeof(Ge2eSmem));
-  if (max_blocks == 0) {
+  int dev = 0;
+  SPK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  SPK_TRY(once.run([&]() -> int {
     SPK_CUDA(cudaFuncSetAttribute(ge2e_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int per_sm = 0, dev = 0, sms = 0;
-    SPK_CUDA(cudaGetDevice(&dev));
+    int per_sm = 0, sms = 0;
     SPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     SPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ge2e_fused_kernel, 256, smem));
     SPK_CHECK(per_sm >= 1, "ge2e: kernel does not fit on an SM");
-    max_blocks = per_sm * sms;
-  }
+    max_blocks_dev[dev] = per_sm * sms;
+    return 0;
+  }));
+  const int max_blocks = max_blocks_dev[dev];
   const long long NM = 1LL * N * M;
   long long want = std::max<long long>((NM + TR - 1) / TR, N);
   const int grid = static_cast<int>(std::min<long long>(want, max_blocks));

@@ -884,13 +884,16 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] == 0) {      // benign race: every thread writes the same value
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n;
   }
-  return sms;
+  return sms[dev];
 }
 
 // 4-D map {cols, rows, nb0, nb1}; box = {64, box_rows, 1, 1}; bf16; 128-byte swizzle; OOB -> zeros.
@@ -970,13 +973,13 @@ static int configure_planes() {
   return 0;
 }
 static int configure_all() {
-  static bool done = false;
-  if (done) return 0;
-  SPK_TRY(configure_planes<1>());
-  SPK_TRY(configure_planes<2>());
-  SPK_TRY(configure_planes<3>());
-  done = true;
-  return 0;
+  static PerDeviceOnce once;
+  return once.run([]() -> int {
+    SPK_TRY(configure_planes<1>());
+    SPK_TRY(configure_planes<2>());
+    SPK_TRY(configure_planes<3>());
+    return 0;
+  });
 }
 
 template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
@@ -995,15 +998,15 @@ template <bool B_MN, int PLANES, int BLOCK_N>
 static int launch_pair(const GemmKernelArgs& args, int pairs, cudaStream_t stream) {
   using Cfg = PairCfg<PLANES, BLOCK_N>;
   auto kern = gemm_pair_kernel<B_MN, PLANES, BLOCK_N>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  SPK_TRY(once.run([&]() -> int {
     SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     cudaFuncAttributes fa;
     SPK_CUDA(cudaFuncGetAttributes(&fa, kern));
     SPK_CHECK(fa.numRegs == LAUNCH_REGS, "gemm pair kernel was built with %d registers/thread, expected %d", fa.numRegs,
               LAUNCH_REGS);
-    configured = true;
-  }
+    return 0;
+  }));
   kern<<<2 * pairs, 128 + 32 * NUM_EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(args);   // __cluster_dims__(2,1,1)
   SPK_CUDA(cudaGetLastError());
   return 0;

@@ -439,6 +439,28 @@ int softmax_bwd(const void* p, const void* dp, const float* dp_f32, int64_t ps, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Test aid: the keep-scale (0 or 1 / (1 - p_q)) every dropout site applies to elements [8 * idx8_begin, 8 * (idx8_begin
+// + n8)) of its index space -- the same pure function of (seed, site, index) the forward and backward kernels evaluate.
+__global__ void dropout_keep_kernel(DropCfg drop, uint32_t site, uint64_t idx8_begin, int64_t n8, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float k8[8];
+    dropout_scale8(drop.seed, site, idx8_begin + static_cast<uint64_t>(i), drop.thresh, drop.inv_keep, k8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[i * 8 + j] = k8[j];
+  }
+}
+int dropout_keep(uint64_t seed, float p, uint32_t site, uint64_t idx8_begin, int64_t n8, float* out, cudaStream_t st) {
+  SPK_CHECK(out != nullptr && n8 >= 0, "dropout_keep: bad argument");
+  if (n8 == 0) return 0;
+  const DropCfg drop = make_drop(seed, p, true);
+  SPK_CHECK(drop.thresh != 0, "dropout_keep: p must be > 0");
+  const int blocks = static_cast<int>(std::min<int64_t>((n8 + 255) / 256, 148 * 8));
+  dropout_keep_kernel<<<blocks, 256, 0, st>>>(drop, site, idx8_begin, n8, out);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // out[c] += sum_r x[r, c]   (bias gradients).  C % 8 == 0, C <= 1024.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ps, int planes,
                                                      float* __restrict__ out, int64_t rows, int C, int rows_per_block) {

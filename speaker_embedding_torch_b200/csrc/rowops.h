@@ -34,6 +34,7 @@ int softmax_fwd(const void* s, const float* s_f32, int64_t ps, int planes, void*
 int softmax_bwd(const void* p, const void* dp, const float* dp_f32, int64_t ps, int planes, void* ds, DropCfg drop,
                 uint32_t site, float scale, int64_t rows, int T, int Tp, cudaStream_t st);
 
+int dropout_keep(uint64_t seed, float p, uint32_t site, uint64_t idx8_begin, int64_t n8, float* out, cudaStream_t st);
 int colsum(const void* x, int64_t ps, int planes, float* out, int64_t rows, int C, cudaStream_t st);
 int pe_alpha_grad(const void* dh, int64_t ps, int planes, const float* pe_t, DropCfg drop, uint32_t site, float* dalpha,
                   int64_t rows, int T, cudaStream_t st);

@@ -21,8 +21,16 @@ import torch.distributed as dist
 from torch.autograd import Variable
 
 
+# data_ptr of the loss whose rank-mean already sits behind the gradients in the arena -> that arena element
+_PIGGYBACK = {}
+
+
 def reduce_tensor(tensor, num_gpus):
-    """Mean of ``tensor`` over ranks (logging only)."""
+    """Mean of ``tensor`` over ranks (logging only).  The training loss of the step whose gradients were just averaged
+    needs no collective of its own: its mean came back with the gradient arena."""
+    hit = _PIGGYBACK.pop(tensor.data_ptr(), None) if tensor.numel() == 1 else None
+    if hit is not None and hit.device == tensor.device:
+        return hit.clone().view_as(tensor)
     rt = tensor.clone()
     dist.all_reduce(rt, op=dist.ReduceOp.SUM)
     rt /= num_gpus
@@ -72,7 +80,16 @@ def allreduce_gradients(module):
     if arena is not None and arena.is_cuda == params[0].grad.is_cuda:
         lo, hi = arena.data_ptr(), arena.data_ptr() + arena.numel() * arena.element_size()
         if all(lo <= p.grad.data_ptr() < hi for p in params):
-            _average_inplace(arena, world)
+            from .Modules import LAST_TRAINING_LOSS
+            loss = LAST_TRAINING_LOSS.pop(arena.device, None)
+            numel = getattr(module, "_arena_numel", None)
+            _PIGGYBACK.clear()
+            if loss is not None and numel is not None and arena.numel() > numel:
+                arena[numel].copy_(loss.float())               # the step's loss rides behind the gradients
+                _average_inplace(arena, world)
+                _PIGGYBACK[loss.data_ptr()] = arena[numel]
+            else:
+                _average_inplace(arena, world)
             return 1
     # generic path (gradients produced by plain autograd, e.g. CPU tests): one flat bucket per dtype
     buckets = {}

@@ -137,3 +137,18 @@ def test_overlapped_slices_match_the_collater():
     import pytest
     with pytest.raises(RuntimeError):
         Overlapped_Slices(torch.zeros(2, 80, 32), 64, 32)
+
+
+def test_dropin_harness_is_what_the_reference_expects(tmp_path):
+    """tests/dropin_train_worker.py (the GPU drop-in test of the reference's unmodified Train.py) run against the
+    REFERENCE's own modules on CPU: the synthetic patterns, yaml and call sequence are valid reference usage."""
+    import subprocess
+    import sys
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "Train.py")):
+        pytest.skip("baseline/_ref is staged by __graft_entry__.build() where /root/reference exists")
+    env = dict(os.environ, SPK_DROPIN_REFERENCE_MODULES="1", CUDA_VISIBLE_DEVICES="")
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_train_worker.py"), ref, str(tmp_path)],
+                          capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert "DROPIN_TRAIN_OK" in proc.stdout

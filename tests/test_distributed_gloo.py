@@ -28,10 +28,11 @@ class _ArenaFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, w, b = ctx.saved_tensors
-        arena = torch.zeros(w.numel() + b.numel())
+        arena = torch.zeros(w.numel() + b.numel() + 4)        # + the spare slots behind the gradients (loss piggyback)
         ctx.module._arena = arena
+        ctx.module._arena_numel = w.numel() + b.numel()
         gw = arena[:w.numel()].view_as(w)
-        gb = arena[w.numel():].view_as(b)
+        gb = arena[w.numel():w.numel() + b.numel()].view_as(b)
         gw.copy_(x.sum(0).unsqueeze(1).expand_as(w) * g)
         gb.copy_(2 * b * x.mean() * g)
         return None, None, gw, gb
@@ -63,10 +64,20 @@ def _worker(rank, world, port, out):
     dist.all_gather(buf_all, toy.buf)
     assert all(torch.equal(w_all[0], t) for t in w_all) and all(torch.equal(buf_all[0], t) for t in buf_all)
 
-    # arena path
+    # arena path; the step's loss rides behind the gradients (what GE2E_Loss.forward registers)
+    from speaker_embedding_torch_b200 import distributed as D
+    from speaker_embedding_torch_b200.Modules import LAST_TRAINING_LOSS
     x = torch.randn(6, 4, generator=torch.Generator().manual_seed(7 + rank))
     loss = toy(x)
+    LAST_TRAINING_LOSS[loss.device] = loss.detach()
     loss.backward()
+    losses = [torch.zeros(()) for _ in range(world)]
+    dist.all_gather(losses, loss.detach())
+    assert loss.data_ptr() in D._PIGGYBACK
+    mean_loss = reduce_tensor(loss.data, world)                    # no collective: answered from the arena
+    torch.testing.assert_close(mean_loss, sum(losses) / world)
+    assert not D._PIGGYBACK
+    torch.testing.assert_close(reduce_tensor(loss.data, world), sum(losses) / world)     # second call: real collective
     assert toy.w.grad.data_ptr() == toy._arena.data_ptr()          # grads alias the arena
     local_gw = x.sum(0).unsqueeze(1).expand(4, 3)
     gw_all = [torch.zeros(4, 3) for _ in range(world)]

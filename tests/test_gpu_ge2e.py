@@ -56,6 +56,20 @@ def test_closed_form_sizes(n, m):
     assert abs(dw - dw_ref) <= 2e-4 * abs(dw_ref) + 1e-6
 
 
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_large_speaker_counts_match_the_closed_form(n):
+    """BASELINE config 5's upper end (the reference itself cannot hold N > ~512 in memory): fused kernel vs the fp64
+    closed form evaluated in row chunks."""
+    m = 15
+    E = synth.make_embeddings(1300 + n, n, m, unit_norm=True)
+    loss, dE, dw, db = _run(E, m)
+    l_ref, dE_ref, dw_ref, db_ref = O.ge2e_closed_form_chunked(E, m)
+    assert abs(loss - l_ref) <= 2e-5 * max(1.0, abs(l_ref)), (loss, l_ref)
+    assert np.linalg.norm(dE - dE_ref) / np.linalg.norm(dE_ref) <= 3e-4
+    assert abs(dw - dw_ref) <= 2e-4 * abs(dw_ref) + 1e-6
+    assert abs(db) <= 1e-5
+
+
 def test_grad_scaling_and_errors():
     from speaker_embedding_torch_b200 import GE2E_Loss
     E = synth.make_embeddings(3, 6, 4)

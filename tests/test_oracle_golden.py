@@ -53,6 +53,48 @@ def test_ge2e_loss_matches_reference(golden_dir):
         np.testing.assert_allclose(g["case%d_f32_loss" % i], g["case%d_f64_loss" % i], rtol=2e-5, atol=1e-6)
 
 
+def test_chunked_closed_form_equals_closed_form():
+    E = synth.make_embeddings(77, 37, 5, unit_norm=False)
+    a = O.ge2e_loss_and_grads_closed_form(E, 5, 7.0, -3.0)
+    b = O.ge2e_closed_form_chunked(E, 5, 7.0, -3.0, rows_per_chunk=16)
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-13)
+    np.testing.assert_allclose(a[1], b[1], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-11, atol=1e-16)
+    assert abs(b[3]) < 1e-12
+
+
+def test_explicit_dropout_scales_reach_every_site():
+    """The oracle's 13 dropout sites take explicit keep-scales (what the GPU mask test feeds it): all-ones scales
+    reproduce eval mode, and zeroing any single site changes the output."""
+    state = O.to_torch_state(synth.make_state(3), torch.float64)
+    mel = torch.as_tensor(synth.make_mel(5, 4, 12)).double()
+    B, T, D, F, H = 4, 12, 256, 1024, 4
+    shapes = {0: (B, T, D)}
+    for l in range(3):
+        shapes.update({1 + 4 * l: (B, H, T, T), 2 + 4 * l: (B, T, D), 3 + 4 * l: (B, T, F), 4 + 4 * l: (B, T, D)})
+    ones = {k: torch.ones(v, dtype=torch.float64) for k, v in shapes.items()}
+    base = O.encoder_forward(state, mel, 1)
+    np.testing.assert_allclose(O.encoder_forward(state, mel, 1, drop_scales=ones).numpy(), base.numpy(), atol=1e-14)
+    assert len(shapes) == 13
+    for site in shapes:
+        ds = dict(ones)
+        ds[site] = torch.zeros(shapes[site], dtype=torch.float64)
+        out = O.encoder_forward(state, mel, 1, drop_scales=ds)
+        assert (out - base).abs().max() > 1e-6, site
+
+
+def test_full_batch_golden_is_complete(golden_dir):
+    g = np.load(os.path.join(golden_dir, "train_full.npz"))
+    assert int(g["num_cases"]) == 3 and int(g["fp_k"]) == 4096
+    for i in range(3):
+        ss, ms, N, M, T = [int(v) for v in g["case%d_meta" % i]]
+        assert (N, M) == (64, 15) and T in (140, 160, 180)
+        assert g["case%d_dvec" % i].shape == (960, 256)
+        np.testing.assert_allclose(np.linalg.norm(g["case%d_dvec" % i].astype(np.float64), axis=1), 1.0, atol=1e-6)
+        names = [n for n, _ in synth.state_shapes() if not n.endswith(".pe")]
+        assert all("case%d_gsamp_%s" % (i, n) in g for n in names)
+
+
 def test_train_step_grads_match_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "train_grads.npz"))
     for i in range(int(g["num_cases"])):
