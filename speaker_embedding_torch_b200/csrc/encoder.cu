@@ -18,6 +18,12 @@ int attn_row0_bwd(const void* datt0, int64_t da_ps, int g_planes, const void* q0
                   int64_t kv_ps, int planes, const float* p0, const float* pd0, void* dq0, int64_t dq_ps, void* dkv,
                   int64_t dkv_ps, float* dbias, int B, int H, int T, int Tp, cudaStream_t st);
 int attn_fused_fwd(const void* qkv, void* out, int64_t out_ld, int B, int H, int T, cudaStream_t st);
+int attn_train_max_frames(int planes);
+int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64_t out_ps, int64_t out_ld, float* stats,
+                   uint32_t* mbits, DropCfg drop, uint32_t site, int B, int H, int T, int Tp, cudaStream_t st);
+int attn_train_bwd(const void* qkv, int64_t qkv_ps, const void* out, int64_t out_ps, const void* dout, int64_t dout_ps,
+                   const float* stats, const uint32_t* mbits, float* delta, void* dqkv, int64_t dqkv_ps, float* dbias,
+                   DropCfg drop, int B, int H, int T, int Tp, cudaStream_t st);
 int rows_add(void* dst, int64_t d_ps, int64_t dst_row_step, const void* src, int64_t s_ps, int planes, int rows,
              cudaStream_t st);
 
@@ -32,6 +38,8 @@ struct LayerBufs {
   Split qkv, p, pd, att, z1, h1, f, z2, hout;
   size_t st1 = 0, st2 = 0;
   size_t fbits = 0;   // ReLU mask of the FFN hidden activation, one bit per element ([F/32, Mt] words), for the backward
+  size_t astat = 0;   // fused training attention: (row max, row sum) per (slice, head, query)
+  size_t abits = 0;   // fused training attention: dropout keep bits [B*H][ceil(Tp/32)][T]
 };
 
 // Last layer, t = 0 rows only (see attn_row0.cu): compact [B, .] buffers + K|V for every frame.
@@ -44,6 +52,8 @@ struct Plan {
   int B, T, S, P, Tp, H, D, F, C, L;
   int64_t Mt, BH;
   bool keep, prune, fused_infer, fused_train;
+  bool attn_tr;       // the dense layers of this training plan use the fused attention kernels (attn_train.cu)
+  size_t adelta;      // fused training attention backward: delta = rowsum(dO * O), [B*H*T] fp32
   LastBufs last;
   Split wpack;
   int64_t w_pre, w_in[SPK_MAX_LAYERS], w_out[SPK_MAX_LAYERS], w_l1[SPK_MAX_LAYERS], w_l2[SPK_MAX_LAYERS];
@@ -117,15 +127,22 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int Pflag
   pl.x0 = take_split(cur, Mt * pl.C, P);
   pl.h0 = take_split(cur, Mt * D, P);
   pl.pe_t = take_f32(cur, static_cast<int64_t>(T) * D);
-  pl.scr = take_split(cur, pl.BH * T * pl.Tp, P < 2 ? 2 : P);   // also holds fp32 scores / dP (4 B per element)
+  // fused training attention (scores never leave the SM): multi-plane training plans up to 192 frames
+  pl.attn_tr = keep && pl.fused_train && P >= 2 && T <= 192 && T <= attn_train_max_frames(P) && pl.H == 4;
+  const int64_t score_elems = pl.attn_tr ? 128 : pl.BH * T * pl.Tp;     // the materialised path's score tensors
+  pl.scr = take_split(cur, score_elems, P < 2 ? 2 : P);   // also holds fp32 scores / dP (4 B per element)
   const bool drop = keep;   // P_drop is only distinct in training; allocate with the stash
   const int dense_layers = pl.prune ? pl.L - 1 : pl.L;
   for (int l = 0; l < dense_layers; ++l) {
     if (l > 0 && !keep) { pl.Lb[l] = pl.Lb[0]; continue; }
     LayerBufs& b = pl.Lb[l];
     b.qkv = take_split(cur, Mt * 3 * D, P);
-    b.p = take_split(cur, pl.BH * T * pl.Tp, P);
-    b.pd = drop ? take_split(cur, pl.BH * T * pl.Tp, P) : b.p;
+    b.p = take_split(cur, score_elems, P);
+    b.pd = drop ? take_split(cur, score_elems, P) : b.p;
+    if (pl.attn_tr) {
+      b.astat = take_f32(cur, pl.BH * T * 2);
+      b.abits = take_f32(cur, pl.BH * ((pl.Tp + 31) / 32) * T);
+    }
     b.att = take_split(cur, Mt * D, P);
     b.z1 = take_split(cur, Mt * D, P);
     b.st1 = take_f32(cur, Mt * 2);
@@ -166,7 +183,8 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int Pflag
     pl.df = take_split(cur, Mt * F, Pb);
     pl.datt = take_split(cur, Mt * D, Pb);
     pl.dqkv = take_split(cur, Mt * 3 * D, Pb);
-    pl.ds = take_split(cur, pl.BH * T * pl.Tp, Pb);
+    pl.ds = take_split(cur, score_elems, Pb);
+    pl.adelta = take_f32(cur, pl.BH * T);
     // compact [B, 256] gradient of the last layer's single query row (its own buffer: scr is BH*T*Tp elements per
     // plane, smaller than B*256 for T < 8)
     if (pl.prune) pl.dq0 = take_split(cur, static_cast<int64_t>(B) * D, Pb);
@@ -466,6 +484,9 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     const bool fused_attn = (P == 1) && !keep && !training && T <= 256 && pl.fused_infer;
     if (fused_attn) {
       SPK_TRY(attn_fused_fwd(c.ptr(b.qkv), c.ptr(b.att), D, B, H, T, st));
+    } else if (pl.attn_tr) {
+      SPK_TRY(attn_train_fwd(c.ptr(b.qkv), b.qkv.ps, P, c.ptr(b.att), b.att.ps, D, c.f32(b.astat),
+                             reinterpret_cast<uint32_t*>(c.f32(b.abits)), drop, 1 + 4 * l, B, H, T, Tp, st));
     } else {
     {  // S = Q K^T / sqrt(dh), per (slice, head)
       GemmProblem g;
@@ -799,6 +820,11 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       SPK_TRY(gemm_run(g, st));
     }
     // ---- attention backward, per (slice, head)
+    if (pl.attn_tr) {
+      SPK_TRY(attn_train_bwd(c.ptr(b.qkv), b.qkv.ps, c.ptr(b.att), b.att.ps, c.ptr(pl.datt), pl.datt.ps, c.f32(b.astat),
+                             reinterpret_cast<const uint32_t*>(c.f32(b.abits)), c.f32(pl.adelta), c.ptr(pl.dqkv),
+                             pl.dqkv.ps, lg.in_proj_b, drop, B, H, T, Tp, st));
+    } else {
     const Split& pdrop = drop.thresh ? b.pd : b.p;
     const int64_t sP0 = (int64_t)T * Tp, sP1 = (int64_t)H * T * Tp;
     const int64_t sQ0 = 64, sQ1 = (int64_t)T * 3 * D, sA1 = (int64_t)T * D;
@@ -847,6 +873,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.epi.flags = EPI_COLSUM; g.epi.colsum = lg.in_proj_b + D; g.epi.colsum_sb0 = 64;
       c.out(g.epi, pl.dqkv, D, 3 * D, sQ0, sQ1);
       SPK_TRY(gemm_run(g, st));
+    }
     }
     // ---- in-proj
     SPK_TRY(wgrad(c, pl.dqkv, 3 * D, hin, D, lg.in_proj_w, "gemm.bwd.qkv_wgrad"));

@@ -302,3 +302,50 @@ def test_fp16_patterns_are_upcast_in_the_prenet_load():
     # same inputs after the upcast; the split-K weight gradients use fp32 atomics, so not bit-for-bit
     rel = float((grads[0] - grads[1]).norm() / grads[1].norm())
     assert rel < 1e-5, rel
+
+
+@pytest.mark.parametrize("frames", [1, 7, 16, 40, 100, 128, 129, 144, 160, 177, 192])
+@pytest.mark.parametrize("train", [False, True])
+def test_fused_training_attention_matches_materialised_path(frames, train):
+    """The fused tcgen05 attention of the training path (forward: probabilities stay in TMEM; backward: recomputed
+    from the saved row statistics and the keep-bit mask) against the GEMM + softmax + GEMM composition it replaces:
+    same d-vectors and same gradients, in eval mode and -- same seed, hence same dropout masks -- in train mode."""
+    from speaker_embedding_torch_b200 import GE2E_Loss, _native
+    nspk, utt = 3, 2
+    mel = torch.as_tensor(synth.make_mel(400 + frames, nspk * utt, frames)).cuda()
+    res = {}
+    try:
+        for fused in (1, 0):
+            _native.set_option("fused_training_attention", fused)
+            m, _ = _model(45)
+            m.train(train)
+            crit = GE2E_Loss().cuda()
+            torch.manual_seed(77)
+            d = m(mel)
+            crit(d, utt).backward()
+            torch.cuda.synchronize()
+            res[fused] = (d.detach().clone(), torch.cat([p.grad.flatten() for p in m.parameters()]).clone())
+    finally:
+        _native.set_option("fused_training_attention", 1)
+    torch.testing.assert_close(res[1][0], res[0][0], atol=3e-6, rtol=0)
+    rel = float((res[1][1] - res[0][1]).double().norm() / res[0][1].double().norm())
+    assert rel <= 2e-4, rel
+
+
+def test_fused_training_attention_falls_back_beyond_its_frame_limit():
+    """T > 192 uses the materialised path (checked against the oracle in test_gpu_parity_full); the option is a no-op."""
+    from speaker_embedding_torch_b200 import GE2E_Loss, _native
+    mel = torch.as_tensor(synth.make_mel(499, 4, 200)).cuda()
+    out = {}
+    try:
+        for fused in (1, 0):
+            _native.set_option("fused_training_attention", fused)
+            m, _ = _model(46)
+            m.eval()
+            d = m(mel)
+            GE2E_Loss().cuda()(d, 2).backward()
+            out[fused] = torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
+    finally:
+        _native.set_option("fused_training_attention", 1)
+    # identical kernels either way; only the split-K weight gradients' fp32 atomics reorder
+    assert float((out[1] - out[0]).norm() / out[0].norm()) < 1e-5
