@@ -108,6 +108,25 @@ int spk_encoder_forward_view(const spk_encoder_config* cfg, const spk_encoder_pa
                              int batch, int frames, int samples, int precision, int training, uint64_t seed,
                              float* dvec, void* workspace, size_t workspace_bytes, int keep_stash, void* stream);
 
+/* The same forward fed by a RAGGED training batch, so that the training collater's work (Datasets.py:9-19 `Correction`,
+ * :72-86 `Collater`: one frame count T per batch, every utterance cropped at a random offset or reflect-padded to it)
+ * happens inside the prenet's input load:
+ *   data   [mel_dim, total_frames] in `dtype`: the utterances' patterns concatenated along time;
+ *   table  device int32 [batch][3] = (start column, length, crop offset) per utterance.  length > frames: frames
+ *          [offset, offset + frames) are used; otherwise the utterance is reflect-padded (numpy 'reflect') with
+ *          floor((frames - length) / 2) frames on the left, the rest on the right, exactly as np.pad does it.
+ * The random draws (T and the offsets) stay on the host, in the reference's order, so a seeded run collates the same
+ * batch as the reference's numpy collater.  samples is 1 for training batches but any divisor of batch is accepted. */
+typedef struct spk_mel_ragged {
+  const void* data;
+  int32_t dtype;             /* 0 = fp32, 1 = fp16 */
+  int64_t total_frames;      /* row stride of a mel channel */
+  const int32_t* table;      /* device pointer, [batch][3] */
+} spk_mel_ragged;
+int spk_encoder_forward_ragged(const spk_encoder_config* cfg, const spk_encoder_params* weights, const spk_mel_ragged* mel,
+                               int batch, int frames, int samples, int precision, int training, uint64_t seed,
+                               float* dvec, void* workspace, size_t workspace_bytes, int keep_stash, void* stream);
+
 /* Backward of the call above (same cfg/shape/precision/training/seed/workspace).  Accumulates
  * (+=) into `grads`, which the caller zero-initialises; replaces autograd through Modules.py:46-59. */
 int spk_encoder_backward(const spk_encoder_config* cfg, const spk_encoder_params* weights,
@@ -118,6 +137,16 @@ int spk_encoder_backward(const spk_encoder_config* cfg, const spk_encoder_params
 /* Test aid: text table "name byte_offset plane_stride" of the workspace buffers (returns bytes written). */
 int spk_encoder_debug_layout(const spk_encoder_config* cfg, int batch, int frames, int samples, int precision,
                              int keep_stash, char* buf, size_t cap);
+
+/* Mel front-end on the device (meldataset.py:73-96 `mel_spectrogram`, center = False; the step in front of the encoder
+ * in Inference.py:59-85): audio [batch, samples] fp32 in [-1, 1] -> log-mel [batch, n_mels, frames] (fp32, or fp16 --
+ * the format the reference stores its patterns in -- when out_fp16 != 0), frames = spk_mel_frames(samples, n_fft, hop).
+ * Reflect padding by (n_fft - hop) / 2, periodic Hann window of `win` samples centred in n_fft, magnitude
+ * sqrt(re^2 + im^2 + 1e-9), log(max(., 1e-5)).  basis: device fp32 [n_mels, n_fft / 2 + 1] (librosa.filters.mel);
+ * ranges: device int32 [n_mels][2] = [first, last + 1) non-zero bin of every filter.  n_fft in {512, 1024, 2048}. */
+int spk_mel_frames(int64_t samples, int n_fft, int hop);
+int spk_mel_spectrogram(const float* audio, int batch, int64_t samples, int n_fft, int hop, int win, const float* basis,
+                        const int32_t* ranges, int n_mels, void* out, int out_fp16, void* stream);
 
 /* Test aid: the dropout keep-scale (0 or 1 / (1 - p_q), p_q = round(p * 2^16) / 2^16) of elements
  * [8 * idx8_begin, 8 * (idx8_begin + n8)) of dropout site `site` under `seed` -- the pure function of

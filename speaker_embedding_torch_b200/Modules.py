@@ -120,14 +120,32 @@ def _run_forward(cfg, names, params, pe, features, samples, precision, training,
     reference stores its patterns as fp16, the upcast happens in the prenet load), or -- with
     ``slicing = (frame_length, hop, slices_per_window)`` -- un-sliced windows ``[Utterances, Mel_Dim, L]`` whose
     overlapping slices are cut by the same load."""
-    N.require_cuda(features, "features")
-    if features.dtype not in (torch.float32, torch.float16):
-        features = features.float()
-    features = features.contiguous()
-    if features.dim() != 3 or features.size(1) != cfg.mel_dim:
+    from .Datasets import RaggedMel
+    ragged = features if isinstance(features, RaggedMel) else None
+    if ragged is not None:            # training batch collated on the device (Datasets.Collater)
+        N.require_cuda(ragged.data, "features")
+        N.require_cuda(ragged.table, "features.table")
+        if ragged.data.dtype not in (torch.float32, torch.float16):
+            ragged = RaggedMel(ragged.data.float(), ragged.table, ragged.frames, _checked=True)
+        ragged = RaggedMel(ragged.data.contiguous(), ragged.table.to(torch.int32).contiguous(), ragged.frames,
+                           _checked=True)
+        features = ragged.data            # device / dtype bookkeeping below
+        if slicing is not None or ragged.data.dim() != 2 or ragged.data.size(0) != cfg.mel_dim:
+            raise RuntimeError("ragged features must be [Mel_Dim=%d, total_frames]" % cfg.mel_dim)
+        # (the table was validated on the host when the RaggedMel was built; no device -> host sync here)
+    else:
+        N.require_cuda(features, "features")
+        if features.dtype not in (torch.float32, torch.float16):
+            features = features.float()
+        features = features.contiguous()
+    if ragged is not None:
+        pass
+    elif features.dim() != 3 or features.size(1) != cfg.mel_dim:
         raise RuntimeError("features must be [Batch*Samples, Mel_Dim=%d, Time], got %s"
                            % (cfg.mel_dim, tuple(features.shape)))
-    if slicing is None:
+    if ragged is not None:
+        batch, frames = ragged.table.size(0), ragged.frames
+    elif slicing is None:
         batch, _, frames = features.shape
         window, hop, spw = frames, 0, 1
     else:
@@ -151,12 +169,21 @@ def _run_forward(cfg, names, params, pe, features, samples, precision, training,
         weights = _fill_params(N.EncoderParams(), tensors, pe, cfg.layers)
         ws, nbytes = _workspace(cfg, batch, frames, samples, precision, int(keep), features.device)
         dvec = torch.empty((batch // samples, cfg.emb), dtype=torch.float32, device=features.device)
-        view = N.MelView(features.data_ptr(), 1 if features.dtype == torch.float16 else 0, window, hop, spw)
-        N.check(N.lib().spk_encoder_forward_view(ctypes.byref(cfg), ctypes.byref(weights), ctypes.byref(view), batch,
-                                                 frames, samples, precision, int(training), ctypes.c_uint64(seed),
-                                                 N.ptr(dvec), _aligned_ptr(ws), nbytes, int(keep),
-                                                 N.stream_ptr(features.device)),
-                "spk_encoder_forward_view")
+        if ragged is not None:
+            view = N.MelRagged(ragged.data.data_ptr(), 1 if ragged.data.dtype == torch.float16 else 0,
+                               ragged.data.size(1), ragged.table.data_ptr())
+            N.check(N.lib().spk_encoder_forward_ragged(ctypes.byref(cfg), ctypes.byref(weights), ctypes.byref(view),
+                                                       batch, frames, samples, precision, int(training),
+                                                       ctypes.c_uint64(seed), N.ptr(dvec), _aligned_ptr(ws), nbytes,
+                                                       int(keep), N.stream_ptr(features.device)),
+                    "spk_encoder_forward_ragged")
+        else:
+            view = N.MelView(features.data_ptr(), 1 if features.dtype == torch.float16 else 0, window, hop, spw)
+            N.check(N.lib().spk_encoder_forward_view(ctypes.byref(cfg), ctypes.byref(weights), ctypes.byref(view),
+                                                     batch, frames, samples, precision, int(training),
+                                                     ctypes.c_uint64(seed), N.ptr(dvec), _aligned_ptr(ws), nbytes,
+                                                     int(keep), N.stream_ptr(features.device)),
+                    "spk_encoder_forward_view")
     return dvec, ws, nbytes, (batch, frames, precision)
 
 
@@ -277,6 +304,11 @@ class GE2E(torch.nn.Module):
                                           *params)
         if self.training:
             raise RuntimeError("GE2E.forward in train() mode without gradients is not supported; call eval()")
+        from .Datasets import RaggedMel
+        if isinstance(features, RaggedMel):       # evaluation batches of the device collater (Train.py:198-212)
+            return _run_forward(self._cfg, self._param_names, [p.detach() for p in params],
+                                self.positional_encoding.pe, features, samples, self.eval_precision, False, 0,
+                                keep=False)[0]
         return torch.ops.spkemb.encoder_infer(features, self.positional_encoding.pe, [p.detach() for p in params],
                                               samples, self.eval_precision, self.max_slices_per_call,
                                               self._cfg.mel_dim, self._cfg.emb, self._cfg.heads, self._cfg.layers,

@@ -23,7 +23,8 @@ EXPORTS = (
     "spk_encoder_backward", "spk_ge2e_workspace_bytes", "spk_ge2e_loss", "spk_optim_step",
     "spk_gemm", "spk_split_pack", "spk_device_info", "spk_prof_enable", "spk_prof_report",
     "spk_encoder_debug_layout", "spk_set_option", "spk_encoder_forward_view", "spk_plan_flags",
-    "spk_dropout_keep",
+    "spk_dropout_keep", "spk_encoder_forward_ragged",
+    "spk_mel_frames", "spk_mel_spectrogram",
 )
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
@@ -33,6 +34,12 @@ class MelView(ctypes.Structure):
     """spk_mel_view: strided / fp16 view of the mel input (overlapping inference slices cut inside the prenet load)."""
     _fields_ = [("data", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("window_frames", ctypes.c_int32),
                 ("hop", ctypes.c_int32), ("slices_per_window", ctypes.c_int32)]
+
+
+class MelRagged(ctypes.Structure):
+    """spk_mel_ragged: a training batch as one [Mel_Dim, total_frames] array + (start, length, offset) per utterance."""
+    _fields_ = [("data", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("total_frames", ctypes.c_int64),
+                ("table", ctypes.c_void_p)]
 
 
 class EncoderConfig(ctypes.Structure):
@@ -121,6 +128,10 @@ def lib():
         L.spk_encoder_forward_view.argtypes = [ctypes.POINTER(EncoderConfig), ctypes.POINTER(EncoderParams),
                                                ctypes.POINTER(MelView), i32, i32, i32, i32, i32, u64, vp, vp, sz,
                                                i32, vp]
+        L.spk_encoder_forward_ragged.restype = i32
+        L.spk_encoder_forward_ragged.argtypes = [ctypes.POINTER(EncoderConfig), ctypes.POINTER(EncoderParams),
+                                                 ctypes.POINTER(MelRagged), i32, i32, i32, i32, i32, u64, vp, vp, sz,
+                                                 i32, vp]
         L.spk_encoder_backward.restype = i32
         L.spk_encoder_backward.argtypes = [ctypes.POINTER(EncoderConfig), ctypes.POINTER(EncoderParams),
                                            ctypes.POINTER(EncoderParams), vp, i32, i32, i32, i32, i32, u64,
@@ -140,6 +151,10 @@ def lib():
         L.spk_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.spk_set_option.restype = i32
         L.spk_set_option.argtypes = [ctypes.c_char_p, i32]
+        L.spk_mel_frames.restype = i32
+        L.spk_mel_frames.argtypes = [i64, i32, i32]
+        L.spk_mel_spectrogram.restype = i32
+        L.spk_mel_spectrogram.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp, i32, vp, i32, vp]
         L.spk_dropout_keep.restype = i32
         L.spk_dropout_keep.argtypes = [u64, f32, ctypes.c_uint32, u64, i64, vp, vp]
         L.spk_plan_flags.restype = i32

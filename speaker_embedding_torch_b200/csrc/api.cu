@@ -3,6 +3,7 @@
 #include "encoder.h"
 #include "ge2e.h"
 #include "gemm.h"
+#include "melspec.h"
 #include "optim.h"
 #include "rowops.h"
 
@@ -27,16 +28,25 @@ int spk_encoder_forward(const spk_encoder_config* cfg, const spk_encoder_params*
   SPK_CHECK(cfg && weights && mel && dvec && workspace, "spk_encoder_forward: null argument");
   spk_mel_view view;
   view.data = mel; view.dtype = 0; view.window_frames = frames; view.hop = 0; view.slices_per_window = 1;
-  return encoder_forward(*cfg, *weights, view, batch, frames, samples, precision, training, seed, dvec, workspace,
-                         workspace_bytes, keep_stash, as_stream(stream));
+  return encoder_forward(*cfg, *weights, &view, nullptr, batch, frames, samples, precision, training, seed, dvec,
+                         workspace, workspace_bytes, keep_stash, as_stream(stream));
 }
 
 int spk_encoder_forward_view(const spk_encoder_config* cfg, const spk_encoder_params* weights, const spk_mel_view* mel,
                              int batch, int frames, int samples, int precision, int training, uint64_t seed,
                              float* dvec, void* workspace, size_t workspace_bytes, int keep_stash, void* stream) {
   SPK_CHECK(cfg && weights && mel && mel->data && dvec && workspace, "spk_encoder_forward_view: null argument");
-  return encoder_forward(*cfg, *weights, *mel, batch, frames, samples, precision, training, seed, dvec, workspace,
-                         workspace_bytes, keep_stash, as_stream(stream));
+  return encoder_forward(*cfg, *weights, mel, nullptr, batch, frames, samples, precision, training, seed, dvec,
+                         workspace, workspace_bytes, keep_stash, as_stream(stream));
+}
+
+int spk_encoder_forward_ragged(const spk_encoder_config* cfg, const spk_encoder_params* weights, const spk_mel_ragged* mel,
+                               int batch, int frames, int samples, int precision, int training, uint64_t seed,
+                               float* dvec, void* workspace, size_t workspace_bytes, int keep_stash, void* stream) {
+  SPK_CHECK(cfg && weights && mel && mel->data && mel->table && dvec && workspace,
+            "spk_encoder_forward_ragged: null argument");
+  return encoder_forward(*cfg, *weights, nullptr, mel, batch, frames, samples, precision, training, seed, dvec,
+                         workspace, workspace_bytes, keep_stash, as_stream(stream));
 }
 
 int spk_encoder_backward(const spk_encoder_config* cfg, const spk_encoder_params* weights,
@@ -52,6 +62,20 @@ int spk_encoder_debug_layout(const spk_encoder_config* cfg, int batch, int frame
                               int keep_stash, char* buf, size_t cap) {
   SPK_CHECK(cfg && buf, "spk_encoder_debug_layout: null argument");
   return encoder_debug_layout(*cfg, batch, frames, samples, precision, keep_stash, buf, cap);
+}
+
+int spk_mel_frames(int64_t samples, int n_fft, int hop) {
+  if (hop < 1 || n_fft < 1) return SPK_EINVAL;
+  const int64_t padded = samples + 2 * ((n_fft - hop) / 2);
+  if (padded < n_fft) return 0;
+  return static_cast<int>(1 + (padded - n_fft) / hop);
+}
+
+int spk_mel_spectrogram(const float* audio, int batch, int64_t samples, int n_fft, int hop, int win, const float* basis,
+                        const int32_t* ranges, int n_mels, void* out, int out_fp16, void* stream) {
+  const int r = mel_spectrogram(audio, batch, samples, n_fft, hop, win, basis, ranges, n_mels, out, out_fp16,
+                                as_stream(stream));
+  return r < 0 ? r : 0;
 }
 
 int spk_dropout_keep(uint64_t seed, float p, uint32_t site, uint64_t idx8_begin, int64_t n8, float* out, void* stream) {

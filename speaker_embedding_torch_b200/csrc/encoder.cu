@@ -432,9 +432,9 @@ static void fill_pack_table(const Plan& pl, const spk_encoder_params& w, PackTab
   tab.count = n;
 }
 
-int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, const spk_mel_view& mel, int B, int T, int S,
-                    int P, int training, uint64_t seed, float* dvec, void* ws_v, size_t ws_bytes, int keep,
-                    cudaStream_t st) {
+int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, const spk_mel_view* mel,
+                    const spk_mel_ragged* ragged, int B, int T, int S, int P, int training, uint64_t seed, float* dvec,
+                    void* ws_v, size_t ws_bytes, int keep, cudaStream_t st) {
   Plan pl;
   SPK_TRY(make_plan(cfg, B, T, S, P, keep != 0, pl));
   P = pl.P;     // the upper bits carried the plan options
@@ -450,7 +450,8 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
   PackTable tab;
   fill_pack_table(pl, w, tab);
   SPK_TRY(pack_weights(tab, c.ptr(pl.wpack), pl.wpack.ps, P, st));
-  SPK_TRY(mel_pack(mel, c.ptr(pl.x0), pl.x0.ps, P, B, pl.C, T, st));
+  if (ragged != nullptr) SPK_TRY(mel_pack_ragged(*ragged, c.ptr(pl.x0), pl.x0.ps, P, B, pl.C, T, st));
+  else SPK_TRY(mel_pack(*mel, c.ptr(pl.x0), pl.x0.ps, P, B, pl.C, T, st));
   SPK_TRY(pe_transpose(w.pe, c.f32(pl.pe_t), pl.D, cfg.max_pos, T, st));
 
   {  // prenet k=1 conv + ReLU + alpha * PE (+ dropout)        Modules.py:50-52,98-105

@@ -73,6 +73,67 @@ int mel_pack(const spk_mel_view& mel, void* out, int64_t plane_stride, int plane
   return 0;
 }
 
+// Training collation on the device (Datasets.py:9-19 `Correction`, :72-86 `Collater`): the batch arrives as ONE ragged
+// array [C, total_frames] (the utterances' patterns concatenated along time, fp16 as stored or fp32) plus a table
+// (start, length, offset) per utterance; every utterance is cut (length > T: frames [offset, offset + T)) or
+// reflect-padded (numpy 'reflect', floor / ceil of the missing frames left / right) to the batch's common T inside the
+// load that packs the token-major operand planes.  Host-side padded / cropped copies never exist.
+template <int C, typename TIn>
+__global__ void mel_pack_ragged_kernel(const TIn* __restrict__ mel, const int32_t* __restrict__ table, int64_t total,
+                                       __nv_bfloat16* __restrict__ out, int64_t plane_stride, int planes, int T) {
+  __shared__ float tile[C][33];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 32;
+  const int start = __ldg(table + 3 * b), len = __ldg(table + 3 * b + 1), off = __ldg(table + 3 * b + 2);
+  const int pad_left = len > T ? 0 : (T - len) / 2;
+  const int period = 2 * (len - 1);
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+    const int c = i >> 5, tl = i & 31, t = t0 + tl;
+    float v = 0.f;
+    if (t < T) {
+      int idx;
+      if (len > T) {
+        idx = off + t;
+      } else if (period == 0) {
+        idx = 0;
+      } else {
+        idx = (t - pad_left) % period;
+        if (idx < 0) idx += period;
+        if (idx >= len) idx = period - idx;
+      }
+      v = static_cast<float>(__ldg(mel + static_cast<int64_t>(c) * total + start + idx));
+    }
+    tile[c][tl] = v;
+  }
+  __syncthreads();
+  constexpr int G = C / 8;
+  for (int i = threadIdx.x; i < G * 32; i += blockDim.x) {
+    const int tl = i / G, g = i % G;
+    if (t0 + tl >= T) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = tile[g * 8 + j][tl];
+    store8_split(out, plane_stride, planes, (static_cast<int64_t>(b) * T + t0 + tl) * C + g * 8, v);
+  }
+}
+int mel_pack_ragged(const spk_mel_ragged& mel, void* out, int64_t plane_stride, int planes, int B, int C, int T,
+                    cudaStream_t st) {
+  ProfScope prof("mel_pack_ragged", 0, 1.0 * B * C * T * ((mel.dtype == 1 ? 2.0 : 4.0) + 2.0 * planes), st);
+  SPK_CHECK(C == 80, "mel_pack: Mel_Dim %d not supported by this build (80)", C);
+  SPK_CHECK(mel.data != nullptr && mel.table != nullptr && (mel.dtype == 0 || mel.dtype == 1) && mel.total_frames > 0,
+            "ragged mel: data / table missing or dtype not 0 (fp32) / 1 (fp16)");
+  dim3 grid((T + 31) / 32, B);
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (mel.dtype == 0)
+    mel_pack_ragged_kernel<80, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(mel.data), mel.table,
+                                                            mel.total_frames, o, plane_stride, planes, T);
+  else
+    mel_pack_ragged_kernel<80, __half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(mel.data), mel.table,
+                                                             mel.total_frames, o, plane_stride, planes, T);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // pe buffer [1, D, max_pos] -> pe_t [T, D]
 __global__ void pe_transpose_kernel(const float* __restrict__ pe, float* __restrict__ pe_t, int D, int max_pos, int T) {
   __shared__ float tile[32][33];

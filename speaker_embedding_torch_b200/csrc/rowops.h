@@ -19,6 +19,9 @@ struct PackTable {
 int pack_weights(const PackTable& tab, void* dst, int64_t plane_stride, int planes, cudaStream_t st);
 // mel view (include/spkemb.h spk_mel_view) -> token-major split tensor [B*T, C]
 int mel_pack(const spk_mel_view& mel, void* out, int64_t plane_stride, int planes, int B, int C, int T, cudaStream_t st);
+// ragged batch (include/spkemb.h spk_mel_ragged) -> token-major split tensor, crop / reflect-pad to T in the load
+int mel_pack_ragged(const spk_mel_ragged& mel, void* out, int64_t plane_stride, int planes, int B, int C, int T,
+                    cudaStream_t st);
 int pe_transpose(const float* pe, float* pe_t, int D, int max_pos, int T, cudaStream_t st);
 
 // y[r] = LN(z[r * z_row_step]) over 256 columns; stats[r] = (mean, rstd) (may be null)

@@ -78,6 +78,15 @@ def main():
         open(os.path.join(shims, "distributed.py"), "w").write(
             "from speaker_embedding_torch_b200.distributed import (      # noqa: F401\n"
             "    init_distributed, apply_gradient_allreduce, reduce_tensor)\n")
+    if os.environ.get("SPK_DROPIN_DEVICE_COLLATER") == "1" and not use_reference:
+        # third shim: the training collater of this package (crop / reflect-pad on the device), everything else of
+        # Datasets.py -- Dataset, Inference_Collater, Correction -- stays the reference's
+        open(os.path.join(shims, "Datasets.py"), "w").write(
+            "import importlib.util, os\n"
+            "_s = importlib.util.spec_from_file_location('reference_Datasets', os.path.join(%r, 'Datasets.py'))\n"
+            "_m = importlib.util.module_from_spec(_s); _s.loader.exec_module(_m)\n"
+            "Dataset, Inference_Collater, Correction = _m.Dataset, _m.Inference_Collater, _m.Correction\n"
+            "from speaker_embedding_torch_b200.Datasets import Collater      # noqa: F401\n" % ref)
     sys.path[:0] = [shims, ref, ROOT]
     stub_modules()
 

@@ -349,3 +349,33 @@ def test_fused_training_attention_falls_back_beyond_its_frame_limit():
         _native.set_option("fused_training_attention", 1)
     # identical kernels either way; only the split-K weight gradients' fp32 atomics reorder
     assert float((out[1] - out[0]).norm() / out[0].norm()) < 1e-5
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_device_collation_equals_the_host_collated_forward(golden_dir, case):
+    """Training collation inside the prenet load (spk_encoder_forward_ragged): crop / numpy-style reflect-pad / fp16
+    upcast of a ragged batch give exactly the d-vectors and gradients of the reference collater's dense tensor
+    (tests/golden/collate.npz holds the reference collater's output for the same seeds)."""
+    from oracle.make_golden_collate import make_batch
+    from speaker_embedding_torch_b200 import GE2E_Loss
+    from speaker_embedding_torch_b200.Datasets import Collater
+    g = np.load(os.path.join(golden_dir, "collate.npz"))
+    seed, spk, utt, tmin, tmax, lo, hi = [int(v) for v in g["case%d_meta" % case]]
+    np.random.seed(seed)
+    ragged = Collater(tmin, tmax)(make_batch(seed, spk, utt, lo, hi))
+    dense = torch.as_tensor(g["case%d_out" % case]).cuda()             # the reference collater's tensor
+    m, _ = _model(13)
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(ragged.to("cuda", non_blocking=True)), m(dense))
+    crit = GE2E_Loss().cuda()
+    grads = []
+    for x in (ragged.cuda(), dense):
+        m.zero_grad(set_to_none=True)
+        d = m(x)
+        crit(d, utt).backward()
+        grads.append((d.detach().clone(), torch.cat([p.grad.flatten() for p in m.parameters()]).clone()))
+    assert torch.equal(grads[0][0], grads[1][0])
+    assert float((grads[0][1] - grads[1][1]).norm() / grads[1][1].norm()) < 1e-5     # fp32 atomics reorder only
+    with pytest.raises(RuntimeError):
+        m(ragged)                                                        # host tensors: no CPU path

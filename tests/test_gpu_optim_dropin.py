@@ -126,3 +126,27 @@ def test_train_py_shaped_loop_reduces_loss():
         model(feats.cuda())
     h.remove()
     assert seen == [torch.Size([spk * utt, 256])]
+
+
+def test_arena_export_serves_the_same_dvectors_and_eer_harness_runs(tmp_path):
+    """N4: export -> model_from_arena on the device gives bit-identical d-vectors; the EER harness scores them."""
+    from speaker_embedding_torch_b200 import Export, GE2E
+    from speaker_embedding_torch_b200.Arg_Parser import default_hyper_parameters
+    from speaker_embedding_torch_b200.Verification import evaluate_eer
+    m = GE2E(default_hyper_parameters())
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in synth.make_state(23).items()}, strict=True)
+    m = m.cuda().eval()
+    path = str(tmp_path / "encoder.spkw")
+    Export.export_arena(m, path, steps=7)
+    served = Export.model_from_arena(path, device="cuda")
+    rng = np.random.default_rng(5)
+    spk, utt = 12, 6
+    centres = rng.standard_normal((spk, 1, 80, 1)) * 1.5
+    feats = torch.as_tensor((-5.0 + centres + 0.7 * rng.standard_normal((spk, utt, 80, 64))).reshape(spk * utt, 80, 64),
+                            dtype=torch.float32).cuda()
+    with torch.no_grad():
+        a, b = m(feats), served(feats)
+    assert torch.equal(a, b)
+    labels = np.repeat(np.arange(spk), utt)
+    eer = evaluate_eer(a, labels, num_trials=4000, seed=0)
+    assert 0.0 <= eer <= 0.5          # an untrained encoder still separates these synthetic speakers above chance
