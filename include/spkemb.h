@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPK_ABI_VERSION 1
+#define SPK_ABI_VERSION 2
 #define SPK_EINVAL (-22)
 #define SPK_ENOMEM (-12)
 #define SPK_EIO (-5)
@@ -167,7 +167,15 @@ int spk_ge2e_loss(const float* emb, int speakers, int per_speaker, int dim, cons
 
 /* Fused optimiser over a list of tensors (replaces Radam.py:25-90 / torch AdamW + the
  * clip_grad_norm_ site Train.py:154-159).  One launch computes the global grad norm, one applies
- * clip + update.  kind: 0 = RAdam (Radam.py), 1 = AdamW.  step is 1-based. */
+ * clip + update.  kind: 0 = RAdam (Radam.py), 1 = AdamW.  step is 1-based.
+ * The norm is reduced deterministically (per-block partials added in a fixed order), so data-parallel ranks that hold
+ * bit-identical gradients compute bit-identical clip coefficients and weights.
+ * More than 64 tensors, or parameter groups / step counts that need separate launches but ONE global norm
+ * (clip_grad_norm_ is global): call phase 1 for every chunk c of n (norm partials), then phase 2 for every chunk
+ * (update with the norm of all n chunks).  phase 0 = both for a single chunk (chunk 0 of 1).
+ * norm_scratch: device fp32 [SPK_OPTIM_SCRATCH_FLOATS(n)]; element 0 receives the squared global norm. */
+#define SPK_OPTIM_MAX_CHUNKS 16
+#define SPK_OPTIM_SCRATCH_FLOATS(nchunks) (1 + 296 * (nchunks))
 typedef struct spk_optim_tensors {
   int32_t count;
   float* param[64];
@@ -178,7 +186,7 @@ typedef struct spk_optim_tensors {
 } spk_optim_tensors;
 int spk_optim_step(const spk_optim_tensors* tensors, int kind, int64_t step, float lr, float beta1,
                    float beta2, float eps, float weight_decay, float max_grad_norm, float grad_scale,
-                   float* norm_scratch /* [2] fp32 */, void* stream);
+                   float* norm_scratch, int phase, int chunk, int nchunks, void* stream);
 
 /* Diagnostic / benchmark entry: one tensor-core GEMM on split-bf16 operands,
  * D[M,N] = A * B^T (+ bias, ReLU), used by the GEMM parity tests and the roofline bench. */

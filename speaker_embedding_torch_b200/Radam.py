@@ -25,49 +25,81 @@ class _FusedBase(Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):
+        """One fused step over ALL parameter groups.  The clip norm is global (every parameter of every group, as
+        ``clip_grad_norm_(model.parameters())`` at Train.py:154-159) and deterministic; tensors are launched in chunks
+        of 64 that share one (group, step count), so per-parameter step counts (a parameter whose gradient was None on
+        some steps) get their own bias correction, as in the reference's per-tensor loop (Radam.py:31-88)."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        chunks, dev = [], None
         for group in self.param_groups:
-            plist = [p for p in group["params"] if p.grad is not None]
-            if not plist:
-                continue
-            dev = plist[0].device
-            if self._scratch is None or self._scratch.device != dev:
-                self._scratch = torch.zeros(2, dtype=torch.float32, device=dev)
-            step = None
-            for start in range(0, len(plist), 64):
-                chunk = plist[start:start + 64]
-                if len(plist) > 64 and self.max_grad_norm > 0:
-                    raise RuntimeError("fused clip supports at most 64 tensors per group")
-                tab = N.OptimTensors()
-                tab.count = len(chunk)
-                for i, p in enumerate(chunk):
-                    N.require_cuda(p, "parameter")
-                    if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
-                        raise RuntimeError("fused optimiser needs contiguous fp32 parameters and gradients")
-                    st = self.state[p]
-                    if len(st) == 0:
-                        st["step"] = 0
-                        st["exp_avg"] = torch.zeros_like(p)
-                        st["exp_avg_sq"] = torch.zeros_like(p)
-                    st["step"] += 1
-                    step = st["step"]
-                    tab.param[i], tab.grad[i] = p.data_ptr(), p.grad.data_ptr()
-                    tab.exp_avg[i], tab.exp_avg_sq[i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-                    tab.numel[i] = p.numel()
-                b1, b2 = group["betas"]
-                with torch.cuda.device(dev):
-                    N.check(N.lib().spk_optim_step(ctypes.byref(tab), self.KIND, int(step), float(group["lr"]),
-                                                   float(b1), float(b2), float(group["eps"]),
-                                                   float(group["weight_decay"]), self.max_grad_norm,
-                                                   float(grad_scale), N.ptr(self._scratch), N.stream_ptr(dev)),
-                            "spk_optim_step")
+            buckets = {}
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                N.require_cuda(p, "parameter")
+                if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise RuntimeError("fused optimiser needs contiguous fp32 parameters and gradients")
+                dev = dev or p.device
+                if p.device != dev:
+                    raise RuntimeError("fused optimiser: all parameters must live on one device")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                buckets.setdefault(st["step"] + 1, []).append(p)
+            for step, plist in buckets.items():
+                for start in range(0, len(plist), 64):
+                    chunks.append((group, step, plist[start:start + 64]))
+        if not chunks:
+            return loss
+        if len(chunks) > N.OPTIM_MAX_CHUNKS:
+            raise RuntimeError("fused optimiser: %d launch chunks exceed the %d the norm scratch holds"
+                               % (len(chunks), N.OPTIM_MAX_CHUNKS))
+        need = 1 + 296 * N.OPTIM_MAX_CHUNKS
+        if self._scratch is None or self._scratch.device != dev or self._scratch.numel() < need:
+            self._scratch = torch.zeros(need, dtype=torch.float32, device=dev)
+        tables = []
+        for group, step, plist in chunks:
+            tab = N.OptimTensors()
+            tab.count = len(plist)
+            for i, p in enumerate(plist):
+                st = self.state[p]
+                tab.param[i], tab.grad[i] = p.data_ptr(), p.grad.data_ptr()
+                tab.exp_avg[i], tab.exp_avg_sq[i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                tab.numel[i] = p.numel()
+            tables.append(tab)
+
+        def launch(phase, c):
+            group, step, _ = chunks[c]
+            b1, b2 = group["betas"]
+            N.check(N.lib().spk_optim_step(ctypes.byref(tables[c]), self.KIND, int(step), float(group["lr"]),
+                                           float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                                           self.max_grad_norm, float(grad_scale), N.ptr(self._scratch), phase, c,
+                                           len(chunks), N.stream_ptr(dev)), "spk_optim_step")
+
+        with torch.cuda.device(dev):
+            if len(chunks) == 1:
+                launch(0, 0)
+            else:
+                if self.max_grad_norm > 0:
+                    for c in range(len(chunks)):
+                        launch(1, c)          # norm partials of every chunk first: the clip is global
+                for c in range(len(chunks)):
+                    launch(2, c)
+        for _, _, plist in chunks:            # only after every launch was accepted
+            for p in plist:
+                self.state[p]["step"] += 1
         return loss
 
     def grad_norm(self):
-        """Global gradient norm measured by the last fused step (device tensor; no sync)."""
+        """Global gradient norm measured by the last fused step (device tensor; no sync).  Only measured when
+        ``max_grad_norm > 0`` (the norm kernel is skipped otherwise)."""
+        if self.max_grad_norm <= 0 or self._scratch is None:
+            raise RuntimeError("grad_norm() is measured by the fused clip: construct the optimiser with max_grad_norm > 0")
         return self._scratch[0].sqrt()
 
 

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libspkemb.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 SPK_MAX_LAYERS = 8
-ABI_VERSION = 1
+OPTIM_MAX_CHUNKS = 16      # SPK_OPTIM_MAX_CHUNKS
+ABI_VERSION = 2
 
 EXPORTS = (
     "spk_abi_version", "spk_last_error", "spk_encoder_workspace_bytes", "spk_encoder_forward",
@@ -142,7 +143,7 @@ def lib():
         L.spk_ge2e_loss.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
         L.spk_optim_step.restype = i32
         L.spk_optim_step.argtypes = [ctypes.POINTER(OptimTensors), i32, i64, f32, f32, f32, f32, f32, f32, f32,
-                                     vp, vp]
+                                     vp, i32, i32, i32, vp]
         L.spk_gemm.restype = i32
         L.spk_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
         L.spk_split_pack.restype = i32

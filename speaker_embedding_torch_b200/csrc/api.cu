@@ -95,10 +95,10 @@ int spk_ge2e_loss(const float* emb, int speakers, int per_speaker, int dim, cons
 
 int spk_optim_step(const spk_optim_tensors* tensors, int kind, int64_t step, float lr, float beta1, float beta2,
                    float eps, float weight_decay, float max_grad_norm, float grad_scale, float* norm_scratch,
-                   void* stream) {
+                   int phase, int chunk, int nchunks, void* stream) {
   SPK_CHECK(tensors && norm_scratch, "spk_optim_step: null argument");
   return optim_step(*tensors, kind, step, lr, beta1, beta2, eps, weight_decay, max_grad_norm, grad_scale, norm_scratch,
-                    as_stream(stream));
+                    phase, chunk, nchunks, as_stream(stream));
 }
 
 int spk_gemm(const spk_gemm_desc* d, void* stream) {

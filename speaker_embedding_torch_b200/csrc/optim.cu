@@ -4,8 +4,13 @@
 
 namespace spk {
 
+// Squared gradient norm, DETERMINISTIC: block b writes its partial sum to partial[b] (fixed per-thread, shuffle and
+// shared-memory order); the update kernel adds the partials in a fixed order.  Bit-identical on every data-parallel
+// rank, so the clip coefficient -- and with it the weights -- cannot drift apart (an atomicAdd of the block sums made
+// the norm depend on the arrival order; tests/nccl_worker.py caught the ranks diverging in the last bit).
+constexpr int NORM_BLOCKS = 296;
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const __grid_constant__ spk_optim_tensors t, float gs,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ partial) {
   __shared__ float red[8];
   float acc = 0.f;
   for (int i = 0; i < t.count; ++i) {
@@ -22,7 +27,7 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const __grid_constant_
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += red[w];
-    atomicAdd(out, s);
+    partial[blockIdx.x] = s;
   }
 }
 
@@ -36,11 +41,23 @@ struct StepScalars {
 };
 
 __global__ void __launch_bounds__(256) optim_update_kernel(const __grid_constant__ spk_optim_tensors t,
-                                                           const StepScalars s, const float* __restrict__ sqnorm) {
+                                                           const StepScalars s, float* __restrict__ scratch,
+                                                           int npartial) {
   float coef = s.gs;
   if (s.max_norm > 0.f) {
-    const float total = sqrtf(*sqnorm);
-    coef *= fminf(1.f, s.max_norm / (total + 1e-6f));
+    // every block adds the same partials in the same order: warp 0, lane-strided, then the shuffle tree
+    __shared__ float total_s;
+    if (threadIdx.x < 32) {
+      float acc = 0.f;
+      for (int i = threadIdx.x; i < npartial; i += 32) acc += scratch[1 + i];
+      acc = warp_sum(acc);
+      if (threadIdx.x == 0) {
+        total_s = acc;
+        if (blockIdx.x == 0) scratch[0] = acc;      // squared global norm, for grad_norm()
+      }
+    }
+    __syncthreads();
+    coef *= fminf(1.f, s.max_norm / (sqrtf(total_s) + 1e-6f));
   }
   for (int i = 0; i < t.count; ++i) {
     float* p = t.param[i];
@@ -69,8 +86,19 @@ __global__ void __launch_bounds__(256) optim_update_kernel(const __grid_constant
 }
 
 int optim_step(const spk_optim_tensors& t, int kind, int64_t step, float lr, float beta1, float beta2, float eps,
-               float wd, float max_norm, float grad_scale, float* norm_scratch, cudaStream_t st) {
+               float wd, float max_norm, float grad_scale, float* norm_scratch, int phase, int chunk, int nchunks,
+               cudaStream_t st) {
   SPK_CHECK(t.count >= 1 && t.count <= 64, "optim: tensor count %d out of range", t.count);
+  SPK_CHECK(phase >= 0 && phase <= 2 && nchunks >= 1 && nchunks <= SPK_OPTIM_MAX_CHUNKS && chunk >= 0 && chunk < nchunks,
+            "optim: bad phase / chunk (%d, %d of %d)", phase, chunk, nchunks);
+  if (phase == 1) {      // norm partials of this chunk only
+    if (max_norm > 0.f) {
+      ProfScope prof("optim_norm", 0, 0, st);
+      grad_sqnorm_kernel<<<NORM_BLOCKS, 256, 0, st>>>(t, grad_scale, norm_scratch + 1 + chunk * NORM_BLOCKS);
+      SPK_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   SPK_CHECK(step >= 1, "optim: step is 1-based");
   SPK_CHECK(kind == 0 || kind == 1, "optim: kind must be 0 (RAdam) or 1 (AdamW)");
   StepScalars s;
@@ -95,12 +123,11 @@ int optim_step(const spk_optim_tensors& t, int kind, int64_t step, float lr, flo
   double numel = 0;
   for (int i = 0; i < t.count; ++i) numel += (double)t.numel[i];
   ProfScope prof("optim_step", 0, numel * 4.0 * (max_norm > 0.f ? 8 : 7), st);
-  if (max_norm > 0.f) {
-    SPK_CUDA(cudaMemsetAsync(norm_scratch, 0, sizeof(float), st));
-    grad_sqnorm_kernel<<<296, 256, 0, st>>>(t, grad_scale, norm_scratch);
+  if (max_norm > 0.f && phase == 0) {
+    grad_sqnorm_kernel<<<NORM_BLOCKS, 256, 0, st>>>(t, grad_scale, norm_scratch + 1 + chunk * NORM_BLOCKS);
     SPK_CUDA(cudaGetLastError());
   }
-  optim_update_kernel<<<296, 256, 0, st>>>(t, s, norm_scratch);
+  optim_update_kernel<<<296, 256, 0, st>>>(t, s, norm_scratch, nchunks * NORM_BLOCKS);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -5,5 +5,6 @@
 #include "common.cuh"
 namespace spk {
 int optim_step(const spk_optim_tensors& t, int kind, int64_t step, float lr, float beta1, float beta2, float eps,
-               float wd, float max_norm, float grad_scale, float* norm_scratch, cudaStream_t st);
+               float wd, float max_norm, float grad_scale, float* norm_scratch, int phase, int chunk, int nchunks,
+               cudaStream_t st);
 }

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(native):
     L = native.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.spk_abi_version() == 1
+    assert L.spk_abi_version() == native.ABI_VERSION == 2
 
 
 def test_workspace_query_is_host_only(native):

@@ -51,6 +51,44 @@ def test_fused_adamw_and_clip_match_torch():
             torch.testing.assert_close(p, q, rtol=2e-5, atol=2e-7)
 
 
+def test_fused_step_many_tensors_groups_and_uneven_step_counts():
+    """More than 64 tensors, two parameter groups with different learning rates, one tensor whose gradient is None
+    on the first step (its step count lags): the clip norm is GLOBAL over everything that has a gradient, like
+    clip_grad_norm_(all parameters), and every tensor gets the bias correction of its own step count; the norm is
+    bit-reproducible (deterministic reduction)."""
+    from speaker_embedding_torch_b200.Radam import FusedAdamW
+    torch.manual_seed(1)
+    shapes = [(37, 5)] * 40 + [(129,)] * 30 + [(256, 64)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    split = 35
+    o1 = FusedAdamW([{"params": ours[:split], "lr": 1e-3}, {"params": ours[split:], "lr": 3e-3}], betas=(0.9, 0.999),
+                    eps=1e-6, weight_decay=0.01, max_grad_norm=0.5)
+    o2 = torch.optim.AdamW([{"params": ref[:split], "lr": 1e-3}, {"params": ref[split:], "lr": 3e-3}],
+                           betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01)
+    norms = []
+    for step in range(4):
+        for i, (p, q) in enumerate(zip(ours, ref)):
+            if step == 0 and i == 3:
+                p.grad = q.grad = None
+                continue
+            gr = torch.randn(p.shape, device="cuda") * 0.3
+            p.grad, q.grad = gr.clone(), gr.clone()
+        total = torch.nn.utils.clip_grad_norm_([q for q in ref if q.grad is not None], max_norm=0.5)
+        o2.step()
+        o1.step()
+        torch.testing.assert_close(o1.grad_norm(), total, rtol=1e-5, atol=1e-7)
+        norms.append(o1.grad_norm().clone())
+        for p, q in zip(ours, ref):
+            torch.testing.assert_close(p, q, rtol=3e-5, atol=3e-7)
+    assert o1.state[ours[3]]["step"] == 3 and o1.state[ours[0]]["step"] == 4
+    # same gradients again -> bit-identical norm (no atomics in the reduction)
+    o1.step()
+    n1 = o1.grad_norm().clone()
+    o1.step()
+    assert torch.equal(n1, o1.grad_norm())
+
+
 def _hp_file(tmp_path):
     hp = {"Sound": {"Mel_Dim": 80},
           "GE2E": {"Embedding_Size": 256, "Positional_Encoding": {"Max_Position": 1024, "Dropout_Rate": 0.1},
