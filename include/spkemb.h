@@ -216,6 +216,11 @@ int spk_set_option(const char* name, int value);
 /* Snapshot of the options above as SPK_PLAN_* bits (SPK_PLAN_EXPLICIT set), to be OR-ed into `precision`. */
 int spk_plan_flags(void);
 
+/* Diagnostics: while a device buffer is registered, CTA 0 of the fused attention backward kernel records the SM clock
+ * at the phase boundaries of its first units into it (8 uint64 slots per (key tile, query tile) unit; see
+ * csrc/attn_train.cu).  NULL unregisters.  The caller owns the buffer and keeps it alive while registered. */
+int spk_set_debug_buffer(void* device_buffer, size_t bytes);
+
 /* Launch profiler (used by bench.py for the per-kernel roofline): when enabled every launcher brackets
  * its kernel with CUDA events on the launching stream.  spk_prof_report synchronises those events,
  * writes one text line per kernel tag -- "tag launches total_ms algorithmic_flops algorithmic_bytes" --

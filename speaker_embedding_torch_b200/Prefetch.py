@@ -28,8 +28,11 @@ class Device_Prefetcher:
         self._free_evt = [None] * (self.depth + 1)                # consumer finished reading slot k
         self.reserve_bytes = int(reserve_bytes)
         if self.reserve_bytes > 0:
-            for slot in self._slots:
-                slot[1] = torch.empty(self.reserve_bytes, dtype=torch.uint8, device=self.device)
+            # allocated under the copy stream, like the buffers grown in _leaf: the caching allocator only guarantees
+            # stream-ordered reuse on the allocating stream, and the first writer of these buffers is the side stream
+            with torch.cuda.stream(self.stream):
+                for slot in self._slots:
+                    slot[1] = torch.empty(self.reserve_bytes, dtype=torch.uint8, device=self.device)
 
     def _leaf(self, slot, index, src):
         nbytes = src.numel() * src.element_size()

@@ -25,7 +25,7 @@ EXPORTS = (
     "spk_gemm", "spk_split_pack", "spk_device_info", "spk_prof_enable", "spk_prof_report",
     "spk_encoder_debug_layout", "spk_set_option", "spk_encoder_forward_view", "spk_plan_flags",
     "spk_dropout_keep", "spk_encoder_forward_ragged",
-    "spk_mel_frames", "spk_mel_spectrogram",
+    "spk_mel_frames", "spk_mel_spectrogram", "spk_set_debug_buffer",
 )
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
@@ -152,6 +152,8 @@ def lib():
         L.spk_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.spk_set_option.restype = i32
         L.spk_set_option.argtypes = [ctypes.c_char_p, i32]
+        L.spk_set_debug_buffer.restype = i32
+        L.spk_set_debug_buffer.argtypes = [vp, sz]
         L.spk_mel_frames.restype = i32
         L.spk_mel_frames.argtypes = [i64, i32, i32]
         L.spk_mel_spectrogram.restype = i32

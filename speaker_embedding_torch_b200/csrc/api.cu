@@ -9,6 +9,10 @@
 
 using namespace spk;
 
+namespace spk {
+void attn_train_set_timeline(void* buf, size_t bytes);   // attn_train.cu
+}
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 extern "C" {
@@ -136,6 +140,11 @@ int spk_set_option(const char* name, int value) {
 }
 
 int spk_plan_flags(void) { return encoder_plan_flags(); }
+
+int spk_set_debug_buffer(void* device_buffer, size_t bytes) {
+  attn_train_set_timeline(device_buffer, device_buffer ? bytes : 0);
+  return 0;
+}
 
 int spk_prof_enable(int on) { prof_set(on != 0); return 0; }
 int spk_prof_report(char* buf, size_t cap) { return prof_report(buf, cap); }

@@ -5,6 +5,11 @@
 // SM.  Reference: torch scaled_dot_product_attention inside nn.TransformerEncoderLayer (Modules.py:25-36,53), scale
 // 1/sqrt(64), dropout on the probabilities.
 //
+// Warp roles (640 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 idle, 4..19 = sixteen compute
+// warps: warp 4 + 4p + w owns TMEM lane quarter w (tcgen05.ld/st restrict a warp to lanes 32 (warp % 4) ..) and
+// takes every fourth 16-column chunk (p = 0..3).  The per-element work (exp2, Philox, plane splits) is what these
+// kernels are bound by, so it is spread over as many warps as the register file allows.
+//
 // Forward, per (slice, head) and 128-query tile:
 //   TMA       Q tile, K, V (PL planes each) out of the packed qkv buffer [B*T, 768]
 //   tcgen05   S = Q K^T into TMEM (6 plane products for PL = 3, 3 for PL = 2), fp32
@@ -47,6 +52,11 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]: A is [128 lanes x K] packed bf16 pairs in tensor memory (K-major by construction)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -59,8 +69,18 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void pair_sync(int quarter) {   // the two warps that share a TMEM lane quarter
-  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+// One lane of a CONVERGED warp (the MMA warp runs its loops with all 32 lanes and elects the issuer here: tcgen05.mma
+// takes its operands from uniform registers, and issued from divergent `if (lane == 0)` code every MMA costs an
+// election loop and register moves -- ~60 cycles each, more than a 128 x 64 x 16 MMA takes to execute).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor of the same tile `bytes` further on (the start-address field holds address >> 4 in its low 14 bits)
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (bytes >> 4); }
+__device__ __forceinline__ void quarter_sync(int quarter) {   // the four warps that share a TMEM lane quarter
+  asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory");
 }
 // keep bits (bit i <-> element idx8 * 8 + i) of one Philox call; same function of (seed, site, element) as dropout_scale8
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t site, uint64_t idx8, uint32_t thresh) {
@@ -76,7 +96,9 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t site, 
   return bits;
 }
 
-constexpr int ATF_THREADS = 384;
+
+constexpr int ATF_THREADS = 640;
+constexpr int ATF_CW = 16;                                 // compute warps
 constexpr int ATF_TMEM_PLO = 256, ATF_TMEM_O = 384;
 constexpr float ATF_SC = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
 
@@ -85,8 +107,9 @@ struct AtfCfg {
   static constexpr int KV_ROWS = PL == 3 ? 192 : 256;            // max frames of the fused path
   static constexpr int Q_BYTES = 128 * 128, KV_BYTES = KV_ROWS * 128;
   static constexpr int OFF_K = PL * Q_BYTES, OFF_V = OFF_K + PL * KV_BYTES;
-  static constexpr int OFF_X = OFF_V + PL * KV_BYTES;            // float xmax[2][128], xsum[2][128]
-  static constexpr int OFF_BAR = OFF_X + 2048;
+  static constexpr int OFF_X = OFF_V + PL * KV_BYTES;            // float xmax[4][128], xsum[4][128]
+  static constexpr int OFF_STG = OFF_X + 4096;                   // output staging: one plane, 128 rows x 128 B
+  static constexpr int OFF_BAR = OFF_STG + 16384;
   static constexpr int SMEM = OFF_BAR + 128;
 };
 
@@ -96,7 +119,7 @@ struct AttnTrainFwdArgs {
   __nv_bfloat16* out;      // [PL][B*T, out_ld], head h at column h*64
   int64_t out_ps, out_ld;
   float2* stats;           // [B*H*T] (row max * ATF_SC, row sum of exp2), may be null
-  uint32_t* mbits;         // [B*H][nC][T] keep bits of 32-key chunk c of query q, null without dropout
+  uint16_t* mbits;         // [B*H][nC][T] keep bits of 16-key chunk c of query q, null without dropout
   DropCfg drop;
   uint32_t site;
 };
@@ -107,7 +130,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sQ = sbase, sK = sbase + Cfg::OFF_K, sV = sbase + Cfg::OFF_V;
-  float* xch = reinterpret_cast<float*>(smem_raw + Cfg::OFF_X);   // [0..255] max halves, [256..511] sum halves
+  float* xch = reinterpret_cast<float*>(smem_raw + Cfg::OFF_X);   // [0..511] max parts, [512..1023] sum parts
   const uint32_t bar_kv = sbase + Cfg::OFF_BAR, bar_q = bar_kv + 8, bar_s = bar_kv + 16, bar_p = bar_kv + 24,
                  bar_o = bar_kv + 32, bar_oe = bar_kv + 40, bar_kvfree = bar_kv + 48, tmem_slot = bar_kv + 56;
   // Every waiter of an mbarrier observes EVERY phase of it, in order (a parity wait that skips a phase passes
@@ -120,8 +143,8 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
     for (int p = 0; p < PL; ++p) { tma_prefetch_desc(&a.q_map[p]); tma_prefetch_desc(&a.k_map[p]); tma_prefetch_desc(&a.v_map[p]); }
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1);
-    mbar_init(bar_oe, 256); mbar_init(bar_kvfree, 1);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 32 * ATF_CW); mbar_init(bar_o, 1);
+    mbar_init(bar_oe, 32 * ATF_CW); mbar_init(bar_kvfree, 1);
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -155,56 +178,60 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, a.Tk16, false, false);
-      const uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-      constexpr int NCOMBO = PL == 3 ? 6 : 3;
-      // plane products, smallest terms first (plane 0 = hi)
-      constexpr int PA3[6] = {1, 0, 2, 0, 1, 0}, PB3[6] = {1, 2, 0, 1, 0, 0};
-      constexpr int PA2[3] = {1, 0, 0}, PB2[3] = {0, 1, 0};
-      uint32_t u = 0, it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        for (int mt = 0; mt < a.mtiles; ++mt, ++u) {
-          mbar_wait(bar_q, u & 1u, 0x610u);
-          if (mt == 0) mbar_wait(bar_kv, it & 1u, 0x611u);
-          tc_fence_after();
-          uint32_t acc = 0;
+    // whole warp, converged; one elected lane issues
+    const uint32_t idesc_s = umma_idesc_bf16(128, a.Tk16, false, false);
+    const uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+    constexpr int NCOMBO = PL == 3 ? 6 : 3;
+    // plane products, smallest terms first (plane 0 = hi)
+    constexpr int PA3[6] = {1, 0, 2, 0, 1, 0}, PB3[6] = {1, 2, 0, 1, 0, 0};
+    constexpr int PA2[3] = {1, 0, 0}, PB2[3] = {0, 1, 0};
+    const uint64_t dQ0 = umma_smem_desc(sQ, 16, 1024), dK0 = umma_smem_desc(sK, 16, 1024);
+    const uint64_t dV0 = umma_smem_desc(sV, 8192, 1024);
+    const int ksteps = a.Tk16 / 16;
+    uint32_t u = 0, it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      for (int mt = 0; mt < a.mtiles; ++mt, ++u) {
+        mbar_wait(bar_q, u & 1u, 0x610u);
+        if (mt == 0) mbar_wait(bar_kv, it & 1u, 0x611u);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int cb = 0; cb < NCOMBO; ++cb) {
             const int pa = PL == 3 ? PA3[cb] : PA2[cb], pb = PL == 3 ? PB3[cb] : PB2[cb];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(tS, umma_smem_desc(sQ + pa * Cfg::Q_BYTES + k * 32, 16, 1024),
-                        umma_smem_desc(sK + pb * Cfg::KV_BYTES + k * 32, 16, 1024), idesc_s, acc);
-              acc = 1;
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tS, desc_add(dQ0, pa * Cfg::Q_BYTES + k * 32), desc_add(dK0, pb * Cfg::KV_BYTES + k * 32), idesc_s,
+                        (cb | k) ? 1u : 0u);
           }
           umma_commit(bar_s);
-          mbar_wait(bar_p, u & 1u, 0x612u);                       // probabilities are in TMEM
-          if (u > 0) mbar_wait(bar_oe, (u - 1) & 1u, 0x613u);     // previous output tile drained
-          tc_fence_after();
-          acc = 0;
-          for (int t = 0; t < a.Tk16 / 16; ++t) {
+        }
+        __syncwarp();
+        mbar_wait(bar_p, u & 1u, 0x612u);                       // probabilities are in TMEM
+        if (u > 0) mbar_wait(bar_oe, (u - 1) & 1u, 0x613u);     // previous output tile drained
+        tc_fence_after();
+        if (elect_one()) {
+          for (int t = 0; t < ksteps; ++t) {
+            const uint32_t voff = (t >> 2) * 8192 + (t & 3) * 2048;
 #pragma unroll
             for (int cb = 0; cb < NCOMBO; ++cb) {
               const int pa = PL == 3 ? PA3[cb] : PA2[cb], pb = PL == 3 ? PB3[cb] : PB2[cb];
               const uint32_t ta = pa == 0 ? tS + 16 * t : (pa == 1 ? tS + 16 * t + 8 : tPlo + 8 * t);
-              umma_bf16_ts(tO, ta, umma_smem_desc(sV + pb * Cfg::KV_BYTES + (t >> 2) * 8192 + (t & 3) * 2048, 8192, 1024),
-                           idesc_o, acc);
-              acc = 1;
+              umma_bf16_ts(tO, ta, desc_add(dV0, pb * Cfg::KV_BYTES + voff), idesc_o, (t | cb) ? 1u : 0u);
             }
           }
           umma_commit(bar_o);
           if (mt == a.mtiles - 1) umma_commit(bar_kvfree);
         }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
-    const int w = (warp - 4) & 3, half = (warp - 4) >> 2;
+    const int w = (warp - 4) & 3, part = (warp - 4) >> 2;          // lane quarter, column part (0..3)
     const int r = w * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(w * 32) << 16;
     const bool use_drop = a.drop.thresh != 0;
     const float inv_keep = use_drop ? a.drop.inv_keep : 1.f;
+    const int nchunks = a.Tk16 / 16;                               // 16-key chunks == MMA key steps
     uint32_t u = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int h = item % a.H, b = item / a.H;
@@ -214,101 +241,115 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
         const bool active = mt * 128 + w * 32 < a.T;              // warp-uniform
         mbar_wait(bar_s, ph, 0x620u);
         tc_fence_after();
-        uint32_t sreg[32];
+        uint32_t sreg[16];
         float mx = -INFINITY;
         if (active) {
-          for (int c = half; c * 32 < a.T; c += 2) {
-            tmem_ld_32x32(tS + t_lane + c * 32, sreg);
+          for (int c = part; c * 16 < a.T; c += 4) {
+            tmem_ld_32x16(tS + t_lane + c * 16, sreg);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < a.T) mx = fmaxf(mx, __uint_as_float(sreg[i]));
+            for (int i = 0; i < 16; ++i)
+              if (c * 16 + i < a.T) mx = fmaxf(mx, __uint_as_float(sreg[i]));
           }
         }
-        xch[half * 128 + r] = mx;
-        pair_sync(w);
-        mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);
+        xch[part * 128 + r] = mx;
+        quarter_sync(w);
+        mx = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
         const float mxs = mx * ATF_SC;
         float sum = 0.f;
         if (active) {
           const uint64_t row_idx8 = ((static_cast<uint64_t>(item) * a.T + q) * a.Tp) >> 3;   // Tp % 8 == 0
-          for (int c = half; c * 32 < a.Tk16; c += 2) {
-            tmem_ld_32x32(tS + t_lane + c * 32, sreg);
-            uint32_t keep = 0xFFFFFFFFu;
-            if (use_drop) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                keep = (g == 0 ? 0u : keep) | (dropout_keep8(a.drop.seed, a.site, row_idx8 + c * 4 + g, a.drop.thresh) << (8 * g));
-            }
+          for (int c = part; c < nchunks; c += 4) {
+            tmem_ld_32x16(tS + t_lane + c * 16, sreg);
+            uint32_t keep = 0xFFFFu;
+            if (use_drop)
+              keep = dropout_keep8(a.drop.seed, a.site, row_idx8 + 2 * c, a.drop.thresh) |
+                     (dropout_keep8(a.drop.seed, a.site, row_idx8 + 2 * c + 1, a.drop.thresh) << 8);
             tmem_ld_wait();
-            uint32_t o01[32];
-            uint32_t o2[16];
+            uint32_t o01[16];
+            uint32_t o2[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int key = c * 32 + 2 * j;
+            for (int j = 0; j < 8; ++j) {
+              const int key = c * 16 + 2 * j;
               float e0 = key < a.T ? at_exp2(__uint_as_float(sreg[2 * j]) * ATF_SC - mxs) : 0.f;
               float e1 = key + 1 < a.T ? at_exp2(__uint_as_float(sreg[2 * j + 1]) * ATF_SC - mxs) : 0.f;
               sum += e0 + e1;
               e0 = ((keep >> (2 * j)) & 1u) ? e0 : 0.f;
               e1 = ((keep >> (2 * j + 1)) & 1u) ? e1 : 0.f;
-              // key step t = 2c + (j >> 3): planes 0 / 1 at 16t + (j & 7) and 16t + 8 + (j & 7)
-              const int slot = (j >> 3) * 16 + (j & 7);
               const __nv_bfloat162 hi = __floats2bfloat162_rn(e0, e1);
-              o01[slot] = *reinterpret_cast<const uint32_t*>(&hi);
+              o01[j] = *reinterpret_cast<const uint32_t*>(&hi);           // plane 0 at columns 16c + j
               e0 -= __bfloat162float(hi.x);
               e1 -= __bfloat162float(hi.y);
               const __nv_bfloat162 mid = __floats2bfloat162_rn(e0, e1);
-              o01[slot + 8] = *reinterpret_cast<const uint32_t*>(&mid);
+              o01[8 + j] = *reinterpret_cast<const uint32_t*>(&mid);      // plane 1 at columns 16c + 8 + j
               if (PL == 3) {
                 e0 -= __bfloat162float(mid.x);
                 e1 -= __bfloat162float(mid.y);
                 o2[j] = pack_bf16x2(e0, e1);
               }
             }
-            tmem_st_32x32(tS + t_lane + c * 32, o01);
-            if (PL == 3) tmem_st_32x16(tPlo + t_lane + c * 16, o2);
+            tmem_st_32x16(tS + t_lane + c * 16, o01);
+            if (PL == 3) tmem_st_32x8(tPlo + t_lane + c * 8, o2);
             if (a.mbits != nullptr && q < a.T)
-              a.mbits[(static_cast<int64_t>(item) * a.nC + c) * a.T + q] = keep;
+              a.mbits[(static_cast<int64_t>(item) * a.nC + c) * a.T + q] = static_cast<uint16_t>(keep);
           }
           tmem_st_wait();
         }
-        xch[256 + half * 128 + r] = sum;
+        xch[512 + part * 128 + r] = sum;
         tc_fence_before();
         mbar_arrive(bar_p);
-        pair_sync(w);
-        sum += xch[256 + (half ^ 1) * 128 + r];
-        // ---- epilogue: O * inv_keep / sum -> PL planes
+        quarter_sync(w);
+        sum = (xch[512 + r] + xch[640 + r]) + (xch[768 + r] + xch[896 + r]);
+        // ---- epilogue: O * inv_keep / sum -> PL planes.  This warp takes 16 of the head's 64 columns out of TMEM; the
+        //      planes go through a shared-memory tile so that global memory sees full 128-byte rows (8 lanes x 16 B)
         mbar_wait(bar_o, ph, 0x621u);
         tc_fence_after();
+        float v[16];
         if (active) {
-          tmem_ld_32x32(tO + t_lane + half * 32, sreg);
+          tmem_ld_32x16(tO + t_lane + part * 16, sreg);
           tmem_ld_wait();
-          if (q < a.T) {
-            const float sc = inv_keep / sum;
-            float v[32];
+          const float sc = inv_keep / sum;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(sreg[i]) * sc;
-            __nv_bfloat16* dst = a.out + (static_cast<int64_t>(b) * a.T + q) * a.out_ld + h * 64 + half * 32;
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(sreg[i]) * sc;
+          if (part == 0 && q < a.T && a.stats != nullptr) a.stats[static_cast<int64_t>(item) * a.T + q] = make_float2(mxs, sum);
+        }
+        tc_fence_before();
+        mbar_arrive(bar_oe);                                      // the accumulator is free for the next tile's PV
+        if (active) {                                             // uniform over the quarter's four warps
+          const uint32_t stg = sbase + Cfg::OFF_STG;
+          const uint32_t my0 = stg + r * 128 + (((2 * part) ^ (r & 7)) << 4), my1 = stg + r * 128 + (((2 * part + 1) ^ (r & 7)) << 4);
 #pragma unroll
-            for (int p = 0; p < PL; ++p) {
+          for (int p = 0; p < PL; ++p) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint32_t wv[4];
+            for (int g = 0; g < 2; ++g) {
+              uint32_t wv[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const __nv_bfloat162 qv = __floats2bfloat162_rn(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
-                  wv[i] = *reinterpret_cast<const uint32_t*>(&qv);
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 qv = __floats2bfloat162_rn(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
+                wv[i] = *reinterpret_cast<const uint32_t*>(&qv);
+                if (p + 1 < PL) {
                   v[g * 8 + 2 * i] -= __bfloat162float(qv.x);
                   v[g * 8 + 2 * i + 1] -= __bfloat162float(qv.y);
                 }
-                *reinterpret_cast<uint4*>(dst + p * a.out_ps + g * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
               }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g ? my1 : my0), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]),
+                           "r"(wv[3]) : "memory");
             }
-            if (half == 0 && a.stats != nullptr) a.stats[static_cast<int64_t>(item) * a.T + q] = make_float2(mxs, sum);
+            quarter_sync(w);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {                      // 8 of the quarter's 32 rows per warp, 4 rows per instruction
+              const int row = w * 32 + part * 8 + it * 4 + (lane >> 3);
+              uint4 val;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                           : "r"(stg + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) : "memory");
+              const int qq = mt * 128 + row;
+              if (qq < a.T)
+                *reinterpret_cast<uint4*>(a.out + p * a.out_ps + (static_cast<int64_t>(b) * a.T + qq) * a.out_ld + h * 64 +
+                                          (lane & 7) * 8) = val;
+            }
+            quarter_sync(w);
           }
         }
-        tc_fence_before();
-        mbar_arrive(bar_oe);
       }
     }
   }
@@ -347,7 +388,7 @@ static int attn_train_fwd_launch(AttnTrainFwdArgs& a, const __nv_bfloat16* qkv, 
   return 0;
 }
 
-// qkv: [planes][B*T, 768] split tensor; out: [planes][B*T, 256]; stats [B*H*T] float2; mbits [B*H][ceil(Tp/32)][T]
+// qkv: [planes][B*T, 768] split tensor; out: [planes][B*T, 256]; stats [B*H*T] float2; mbits [B*H][ceil(Tp/16)][T] u16
 int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64_t out_ps, int64_t out_ld, float* stats,
                    uint32_t* mbits, DropCfg drop, uint32_t site, int B, int H, int T, int Tp, cudaStream_t st) {
   SPK_CHECK(planes == 2 || planes == 3, "attn_train_fwd: planes must be 2 or 3");
@@ -360,11 +401,11 @@ int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64
   a.Tk16 = (T + 15) / 16 * 16;
   a.Tk64 = (T + 63) / 64 * 64;
   a.mtiles = (T + 127) / 128;
-  a.nC = (Tp + 31) / 32;
+  a.nC = (Tp + 15) / 16;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.out_ps = out_ps; a.out_ld = out_ld;
   a.stats = reinterpret_cast<float2*>(stats);
-  a.mbits = drop.thresh != 0 ? mbits : nullptr;
+  a.mbits = drop.thresh != 0 ? reinterpret_cast<uint16_t*>(mbits) : nullptr;
   a.drop = drop; a.site = site;
   // algorithmic work: QK^T and PV (bf16 dense count); bytes: Q, K, V in, O out
   ProfScope prof("attn_train_fwd", 4.0 * B * H * T * T * 64, 4.0 * B * T * 64 * H * 2.0 * planes, st);
@@ -372,46 +413,66 @@ int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64
   return attn_train_fwd_launch<2>(a, reinterpret_cast<const __nv_bfloat16*>(qkv), qkv_ps, st);
 }
 
-
 // =====================================================================================================================
 // Backward.  Two bf16 planes everywhere (gradients are smooth in their inputs, DESIGN.md "precision").  Per (slice,
-// head) the keys are walked in 128-row tiles i, the queries in 128-row tiles j; everything is computed TRANSPOSED (keys
-// on the TMEM lanes) so that the two products contracted over queries take their A operand straight from tensor memory:
+// head) the keys are walked in tiles i, the queries in tiles j of `rpt` rows each (rpt = the frames split evenly over
+// ceil(T / 128) tiles, rounded up to 16: 160 frames -> 2 x 80, so that every (i, j) unit is the same size and keeps
+// three of the four lane quarters busy); everything is computed TRANSPOSED (keys on the TMEM lanes) so that the two
+// products contracted over queries take their A operand straight from tensor memory:
 //
 //   tcgen05   S^T  = K_i Q_j^T ,  dP^T = V_i dO_j^T                    -> TMEM (fp32)
-//   8 warps   thread <-> key row: P^T = exp2(S^T * c - m_q) / l_q (row statistics saved by the forward), keep bit from
+//   16 warps  thread <-> key row: P^T = exp2(S^T * c - m_q) / l_q (row statistics saved by the forward), keep bit from
 //             the forward's bit mask (32 x 32 bit transpose by warp shuffles), dS^T = P^T (keep dP^T/(1-p) - delta_q) / 8;
 //             P_drop^T and dS^T go back into TMEM over S^T / dP^T as bf16 planes; dS^T also into shared memory in the
 //             MN-major operand layout (probe: tools/probe/ts_probe.cu)
 //   tcgen05   dV_i += P_drop^T dO_j  and  dK_i += dS^T Q_j   (A from TMEM, B MN-major from shared memory)
 //             dQ_j += dS K_i                                  (A = dS from shared memory, MN-major)
-//   8 warps   drain dV_i, dK_i after the last j, dQ_j after the last i -> dqkv planes; their column sums (the in-proj
+//   16 warps  drain dV_i, dK_i after the last j, dQ_j after the last i -> dqkv planes; their column sums (the in-proj
 //             bias gradient) stay in registers for the whole kernel (a CTA only ever sees one head) and are added to
 //             global memory once per warp at the end.
 // delta_q = sum_d dO_qd O_qd comes from attn_delta_kernel.  T <= 192: Q and dO of the whole slice stay resident.
-constexpr int ATB_THREADS = 384;
+// Optional phase timeline of CTA 0 (diagnostics: spk_set_debug_buffer): slot [unit * 8 + event] = clock64 at
+//   0 operands of the unit are in shared memory   1 S^T / dP^T MMAs issued   2 P^T / dS^T written (bar_p seen by the MMA thread)
+//   3 accumulating MMAs issued                     4 scores visible to a compute warp   5 that warp finished its chunks
+static unsigned long long* g_attn_timeline = nullptr;
+static size_t g_attn_timeline_slots = 0;
+void attn_train_set_timeline(void* buf, size_t bytes) {
+  g_attn_timeline = reinterpret_cast<unsigned long long*>(buf);
+  g_attn_timeline_slots = bytes / 8;
+}
+#define ATB_STAMP(unit, ev)                                                                   \
+  do {                                                                                        \
+    if (a.timeline != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 &&                \
+        static_cast<size_t>((unit) * 8 + (ev)) < a.timeline_slots)                            \
+      a.timeline[(unit) * 8 + (ev)] = clock64();                                              \
+  } while (0)
+
+constexpr int ATB_THREADS = 640;
+constexpr int ATB_CW = 16;
 constexpr int ATB_MAXT = 192;
 constexpr int ATB_QROWS = ATB_MAXT * 128;                 // bytes per plane of Q / dO
 constexpr int ATB_OFF_DO = 2 * ATB_QROWS;                 // 49152
 constexpr int ATB_OFF_K = 4 * ATB_QROWS;                  // 98304
 constexpr int ATB_OFF_V = ATB_OFF_K + 32768;              // 131072
 constexpr int ATB_OFF_DS = ATB_OFF_V + 32768;             // 163840
-constexpr int ATB_OFF_STAT = ATB_OFF_DS + 65536;          // 229376: float2 (m, 1/l) [192]
-constexpr int ATB_OFF_DELTA = ATB_OFF_STAT + ATB_MAXT * 8;   // float [192]
-constexpr int ATB_OFF_BAR = ATB_OFF_DELTA + ATB_MAXT * 4;    // 231680
-constexpr int ATB_SMEM = ATB_OFF_BAR + 128;               // 231808 <= 232448
+constexpr int ATB_STATS = 224;                            // >= rpt + 128 (the last query tile's 16-query chunks may run past T)
+constexpr int ATB_OFF_STAT = ATB_OFF_DS + 65536;          // 229376: float2 (m + log2 l, delta) [224]
+constexpr int ATB_OFF_BAR = ATB_OFF_STAT + ATB_STATS * 8; // 231168
+constexpr int ATB_SMEM = ATB_OFF_BAR + 128;               // 231296 <= 232448
 constexpr int ATB_T_ST = 0, ATB_T_DP = 128, ATB_T_DV = 256, ATB_T_DK = 320, ATB_T_DQ = 384;
 
 struct AttnTrainBwdArgs {
   CUtensorMap q_map[2], k_map[2], v_map[2], do_map[2];
-  int B, H, T, Tk16, Tk64, tiles, nC;
+  int B, H, T, Tk64, tiles, rpt, nC;
   const float2* stats;      // [B*H*T] from the forward
   const float* delta;       // [B*H*T]
-  const uint32_t* mbits;    // [B*H][nC][T] or null (no dropout)
+  const uint16_t* mbits;    // [B*H][nC][T] or null (no dropout)
   __nv_bfloat16* dqkv;      // [2][B*T, 768]
   int64_t dqkv_ps;
   float* dbias;             // [768] += column sums of dQ | dK | dV
   float inv_keep;
+  unsigned long long* timeline;
+  size_t timeline_slots;
 };
 
 // lane r holds row r of a 32 x 32 bit matrix (bit c = column c); afterwards lane c holds column c (bit r = row r)
@@ -424,10 +485,10 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
   }
   return x;
 }
-// v[x] of lane r = element (r, x); returns for lane c the sum over r of element (r, c)
-__device__ __forceinline__ float column_sums32(float (&v)[32], int lane) {
+// v[x] of lane r = element (r, x), 16 columns; returns (in every lane c and c + 16) the sum over all 32 lanes of column c & 15
+__device__ __forceinline__ float column_sums16(float (&v)[16], int lane) {
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
+  for (int s = 8; s >= 1; s >>= 1) {
 #pragma unroll
     for (int k = 0; k < s; ++k) {
       const float send = (lane & s) ? v[k] : v[k + s];
@@ -435,7 +496,45 @@ __device__ __forceinline__ float column_sums32(float (&v)[32], int lane) {
       v[k] = ((lane & s) ? v[k + s] : v[k]) + recv;
     }
   }
-  return v[0];
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+// 16 fp32 values -> two bf16 planes at dst / dst + ps (16-byte stores)
+__device__ __forceinline__ void store16_two_planes(__nv_bfloat16* dst, int64_t ps, const float (&v)[16]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = v[g * 8 + 2 * e], x1 = v[g * 8 + 2 * e + 1];
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[e] = pack_bf16x2(x0 - __bfloat162float(hh.x), x1 - __bfloat162float(hh.y));
+    }
+    *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + ps + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// 16 fp32 values -> two bf16 planes, 2 x 16 bytes each, into shared-memory staging chunks
+__device__ __forceinline__ void stage16_two_planes(uint32_t hi0, uint32_t hi1, uint32_t lo0, uint32_t lo1, const float (&v)[16]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = v[g * 8 + 2 * e], x1 = v[g * 8 + 2 * e + 1];
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[e] = pack_bf16x2(x0 - __bfloat162float(hh.x), x1 - __bfloat162float(hh.y));
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g ? hi1 : hi0), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g ? lo1 : lo0), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+  }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 w;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(addr) : "memory");
+  return w;
 }
 
 __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __grid_constant__ AttnTrainBwdArgs a) {
@@ -443,7 +542,6 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sQ = sbase, sdO = sbase + ATB_OFF_DO, sK = sbase + ATB_OFF_K, sV = sbase + ATB_OFF_V, sdS = sbase + ATB_OFF_DS;
   float2* sStat = reinterpret_cast<float2*>(smem_raw + ATB_OFF_STAT);
-  float* sDelta = reinterpret_cast<float*>(smem_raw + ATB_OFF_DELTA);
   const uint32_t bar_qdo = sbase + ATB_OFF_BAR, bar_kv = bar_qdo + 8, bar_m1 = bar_qdo + 16, bar_p = bar_qdo + 24,
                  bar_tile = bar_qdo + 32, bar_kvd = bar_qdo + 40, bar_dqd = bar_qdo + 48, tmem_slot = bar_qdo + 56;
   // Every waiter of an mbarrier observes EVERY phase of it, in order: bar_m1 / bar_p advance once per (i, j) unit,
@@ -458,8 +556,8 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
     }
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_qdo, 1); mbar_init(bar_kv, 1); mbar_init(bar_m1, 1); mbar_init(bar_p, 256); mbar_init(bar_tile, 1);
-    mbar_init(bar_kvd, 256); mbar_init(bar_dqd, 256);
+    mbar_init(bar_qdo, 1); mbar_init(bar_kv, 1); mbar_init(bar_m1, 1); mbar_init(bar_p, 32 * ATB_CW); mbar_init(bar_tile, 1);
+    mbar_init(bar_kvd, 32 * ATB_CW); mbar_init(bar_dqd, 32 * ATB_CW);
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -469,8 +567,10 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const int items = a.B * a.H;
-  const int tiles = a.tiles;                              // key tiles == query tiles == ceil(T / 128)
-  auto nq_of = [&](int j) { const int n = a.Tk16 - 128 * j; return n < 128 ? n : 128; };   // multiple of 16
+  const int tiles = a.tiles, rpt = a.rpt;                 // key tiles == query tiles, rpt rows each (rpt % 16 == 0)
+  // rows of tile t that hold frames, and the same rounded up to the MMA's 16-row steps
+  auto rows_of = [&](int t) { const int n = a.T - rpt * t; return n < rpt ? n : rpt; };
+  auto rows16_of = [&](int t) { return (rows_of(t) + 15) & ~15; };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -490,251 +590,277 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
           mbar_arrive_expect_tx(bar_kv, 4u * 16384);
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
-            tma_load_4d(sK + p * 16384, &a.k_map[p], bar_kv, 0, i * 128, h, b);
-            tma_load_4d(sV + p * 16384, &a.v_map[p], bar_kv, 0, i * 128, h, b);
+            tma_load_4d(sK + p * 16384, &a.k_map[p], bar_kv, 0, i * rpt, h, b);
+            tma_load_4d(sV + p * 16384, &a.v_map[p], bar_kv, 0, i * rpt, h, b);
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr int PA[3] = {1, 0, 0}, PB[3] = {0, 1, 0};          // lo*hi, hi*lo, hi*hi
-      const uint32_t tST = tmem_base + ATB_T_ST, tDP = tmem_base + ATB_T_DP, tdV = tmem_base + ATB_T_DV,
-                     tdK = tmem_base + ATB_T_DK;
-      const uint32_t idesc_acc = umma_idesc_bf16(128, 64, false, true);      // A from TMEM, B MN-major
-      const uint32_t idesc_dq = umma_idesc_bf16(128, 64, true, true);        // A and B MN-major from shared memory
-      uint32_t u = 0, kt = 0, it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        mbar_wait(bar_qdo, it & 1u, 0x710u);
-        for (int i = 0; i < tiles; ++i, ++kt) {
-          mbar_wait(bar_kv, kt & 1u, 0x711u);
-          const int nk = (nq_of(i)) / 16;                          // key steps of this tile that hold frames
-          for (int j = 0; j < tiles; ++j, ++u) {
-            const int nq = nq_of(j);
-            const uint32_t idesc_s = umma_idesc_bf16(128, nq, false, false);
-            tc_fence_after();
-            // ---- S^T = K_i Q_j^T, dP^T = V_i dO_j^T
+    // whole warp, converged; one elected lane issues (see elect_one)
+    constexpr int PA[3] = {1, 0, 0}, PB[3] = {0, 1, 0};          // lo*hi, hi*lo, hi*hi
+    const uint32_t tST = tmem_base + ATB_T_ST, tDP = tmem_base + ATB_T_DP, tdV = tmem_base + ATB_T_DV,
+                   tdK = tmem_base + ATB_T_DK;
+    const uint32_t idesc_acc = umma_idesc_bf16(128, 64, false, true);      // A from TMEM, B MN-major
+    const uint32_t idesc_dq = umma_idesc_bf16(128, 64, true, true);        // A and B MN-major from shared memory
+    const uint64_t dKk = umma_smem_desc(sK, 16, 1024), dVk = umma_smem_desc(sV, 16, 1024);          // K-major A
+    const uint64_t dQk = umma_smem_desc(sQ, 16, 1024), dOk = umma_smem_desc(sdO, 16, 1024);         // K-major B
+    const uint64_t dQm = umma_smem_desc(sQ, 8192, 1024), dOm = umma_smem_desc(sdO, 8192, 1024);     // MN-major B
+    const uint64_t dKm = umma_smem_desc(sK, 8192, 1024), dSm = umma_smem_desc(sdS, 8192, 1024);     // MN-major B / A
+    uint32_t u = 0, kt = 0, it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      mbar_wait(bar_qdo, it & 1u, 0x710u);
+      for (int i = 0; i < tiles; ++i, ++kt) {
+        mbar_wait(bar_kv, kt & 1u, 0x711u);
+        const int nk = rows16_of(i) / 16;                        // key steps of this tile that hold frames
+        for (int j = 0; j < tiles; ++j, ++u) {
+          const int nq = rows16_of(j);
+          const uint32_t qoff = static_cast<uint32_t>(j * rpt) * 128u;      // byte offset of query tile j (1024-aligned)
+          const uint32_t idesc_s = umma_idesc_bf16(128, nq, false, false);
+          tc_fence_after();
+          ATB_STAMP(u, 0);
+          // ---- S^T = K_i Q_j^T, dP^T = V_i dO_j^T
+          if (elect_one()) {
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
-              const uint32_t sa = which ? sV : sK, sb = (which ? sdO : sQ) + j * 16384, td = which ? tDP : tST;
-              uint32_t acc = 0;
+              const uint64_t da = which ? dVk : dKk, db = desc_add(which ? dOk : dQk, qoff);
+              const uint32_t td = which ? tDP : tST;
 #pragma unroll
               for (int cb = 0; cb < 3; ++cb) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_bf16(td, umma_smem_desc(sa + PA[cb] * 16384 + k * 32, 16, 1024),
-                            umma_smem_desc(sb + PB[cb] * ATB_QROWS + k * 32, 16, 1024), idesc_s, acc);
-                  acc = 1;
-                }
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(td, desc_add(da, PA[cb] * 16384 + k * 32), desc_add(db, PB[cb] * ATB_QROWS + k * 32), idesc_s,
+                            (cb | k) ? 1u : 0u);
               }
             }
             umma_commit(bar_m1);
-            mbar_wait(bar_p, u & 1u, 0x712u);
-            if (j == 0 && kt > 0) mbar_wait(bar_kvd, (kt - 1) & 1u, 0x713u);            // dV / dK of the previous key tile drained
-            if (i == 0 && j == 0 && it > 0) mbar_wait(bar_dqd, (it - 1) & 1u, 0x714u);  // dQ of the previous item drained
-            tc_fence_after();
+          }
+          __syncwarp();
+          ATB_STAMP(u, 1);
+          mbar_wait(bar_p, u & 1u, 0x712u);
+          ATB_STAMP(u, 2);
+          if (j == 0 && kt > 0) mbar_wait(bar_kvd, (kt - 1) & 1u, 0x713u);            // dV / dK of the previous key tile drained
+          if (i == 0 && j == 0 && it > 0) mbar_wait(bar_dqd, (it - 1) & 1u, 0x714u);  // dQ of the previous item drained
+          tc_fence_after();
+          if (elect_one()) {
             // ---- dV_i += P_drop^T dO_j ; dK_i += dS^T Q_j     (contraction over the nq queries of tile j)
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
-              const uint32_t ta = which ? tDP : tST, sb = (which ? sQ : sdO) + j * 16384, td = which ? tdK : tdV;
+              const uint32_t ta = which ? tDP : tST, td = which ? tdK : tdV;
+              const uint64_t db = desc_add(which ? dQm : dOm, qoff);
               for (int t = 0; t < nq / 16; ++t) {
 #pragma unroll
-                for (int cb = 0; cb < 3; ++cb) {
-                  umma_bf16_ts(td, ta + 16 * t + 8 * PA[cb], umma_smem_desc(sb + PB[cb] * ATB_QROWS + t * 2048, 8192, 1024),
-                               idesc_acc, (j > 0 || t > 0 || cb > 0) ? 1u : 0u);
-                }
+                for (int cb = 0; cb < 3; ++cb)
+                  umma_bf16_ts(td, ta + 16 * t + 8 * PA[cb], desc_add(db, PB[cb] * ATB_QROWS + t * 2048), idesc_acc,
+                               (j > 0 || t > 0 || cb > 0) ? 1u : 0u);
               }
             }
             // ---- dQ_j += dS_ij K_i     (contraction over the keys of tile i)
             const uint32_t tdQ = tmem_base + ATB_T_DQ + 64 * j;
             for (int t = 0; t < nk; ++t) {
 #pragma unroll
-              for (int cb = 0; cb < 3; ++cb) {
-                umma_bf16(tdQ, umma_smem_desc(sdS + PA[cb] * 32768 + (t >> 2) * 16384 + (t & 3) * 2048, 8192, 1024),
-                          umma_smem_desc(sK + PB[cb] * 16384 + t * 2048, 8192, 1024), idesc_dq,
-                          (i > 0 || t > 0 || cb > 0) ? 1u : 0u);
-              }
+              for (int cb = 0; cb < 3; ++cb)
+                umma_bf16(tdQ, desc_add(dSm, PA[cb] * 32768 + (t >> 2) * 16384 + (t & 3) * 2048),
+                          desc_add(dKm, PB[cb] * 16384 + t * 2048), idesc_dq, (i > 0 || t > 0 || cb > 0) ? 1u : 0u);
             }
             if (j == tiles - 1) umma_commit(bar_tile);       // dV_i / dK_i (and, after the last tile, dQ) are complete
           }
+          __syncwarp();
+          ATB_STAMP(u, 3);
         }
       }
     }
   } else if (warp >= 4) {
-    const int w = (warp - 4) & 3, half = (warp - 4) >> 2;
+    const int w = (warp - 4) & 3, part = (warp - 4) >> 2;          // lane quarter, column part (0..3)
     const int rr = w * 32 + lane;
-    const int cw = threadIdx.x - 128;                              // 0..255 among the compute threads
+    const int cw = threadIdx.x - 128;                              // 0..511 among the compute threads
     const uint32_t t_lane = static_cast<uint32_t>(w * 32) << 16;
     const uint32_t tST = tmem_base + ATB_T_ST + t_lane, tDP = tmem_base + ATB_T_DP + t_lane;
     const int h = static_cast<int>(blockIdx.x) % a.H;              // gridDim.x % H == 0: one head per CTA
-    float acc_dq = 0.f, acc_dk = 0.f, acc_dv = 0.f;                // bias-gradient column (half * 32 + lane) of this head
-    uint32_t u = 0, kt = 0, it = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    float acc_dq = 0.f, acc_dk = 0.f, acc_dv = 0.f;                // bias-gradient column (part * 16 + (lane & 15)) of this head
+    // this thread's row in the dS^T operand tile (row = key): plane 0 at +0, plane 1 at +32768, query chunk c64 at + c64 * 8192
+    const uint32_t ds_row = sdS + (rr >> 6) * 16384 + (rr & 63) * 128;
+    const uint32_t ds_swz = static_cast<uint32_t>(rr & 7);
+    // The same addresses double as the staging tiles of the coalesced drains (tile t = tensor * 2 + plane at
+    // (t >> 1) * 32768 + (t & 1) * 8192): a lane quarter only ever touches its own rows of that region, so its four warps
+    // synchronise among themselves (quarter_sync) and never with the other quarters.
+    auto stage_addr = [&](int t, int row, int ch) {
+      return sdS + (t >> 1) * 32768 + (t & 1) * 8192 + (row >> 6) * 16384 + (row & 63) * 128 + ((ch ^ (row & 7)) << 4);
+    };
+    uint32_t u = 0, kt = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int b = item / a.H;
-      // ---- per-query statistics of this slice and head
-      asm volatile("bar.sync 5, 256;" ::: "memory");               // everybody is done with the previous item's statistics
-      if (cw < ATB_MAXT) {
-        float2 st = make_float2(0.f, 0.f);
-        float dl = 0.f;
+      // ---- per-query statistics of this slice and head: (m + log2 l, delta); queries past T get m = +inf -> P = 0
+      asm volatile("bar.sync 5, 512;" ::: "memory");               // everybody is done with the previous item's statistics
+      if (cw < ATB_STATS) {
+        float2 st = make_float2(INFINITY, 0.f);
         if (cw < a.T) {
-          st = a.stats[static_cast<int64_t>(item) * a.T + cw];
-          st.y = 1.f / st.y;
-          dl = a.delta[static_cast<int64_t>(item) * a.T + cw];
+          const float2 ml = a.stats[static_cast<int64_t>(item) * a.T + cw];
+          st.x = ml.x + __log2f(ml.y);
+          st.y = a.delta[static_cast<int64_t>(item) * a.T + cw];
         }
         sStat[cw] = st;
-        sDelta[cw] = dl;
       }
-      asm volatile("bar.sync 5, 256;" ::: "memory");
+      asm volatile("bar.sync 5, 512;" ::: "memory");
       for (int i = 0; i < tiles; ++i, ++kt) {
-        const int key = 128 * i + rr;
-        const bool kvalid = key < a.T;
-        const bool warp_keys = 128 * i + w * 32 < a.Tk16;          // warp-uniform: some key step of this warp is contracted
+        const int krows = rows_of(i);
+        const bool kvalid = rr < krows;                            // rows >= krows belong to the next tile or lie past T
+        const bool warp_keys = w * 32 < rows16_of(i);              // warp-uniform: some key step of this warp is contracted
         for (int j = 0; j < tiles; ++j, ++u) {
-          const int nq = nq_of(j);
+          const int nq = rows16_of(j);
+          // keep bits of this warp's 32 keys for the queries it will visit: issued before the scores are waited for
+          uint32_t mword[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+          if (a.mbits != nullptr && warp_keys) {
+            const int kc = (rpt * i + w * 32) >> 4;                // first of the two 16-key chunks of this warp's keys
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+              const int c = part + 4 * n;
+              uint32_t mine = 0;
+              const int q = rpt * j + 16 * c + lane;               // lanes 0..15 fetch one query each
+              if (lane < 16 && 16 * c < nq && q < a.T) {
+                const uint16_t* mb = a.mbits + (static_cast<int64_t>(item) * a.nC + kc) * a.T + q;
+                mine = __ldg(mb);
+                if (kc + 1 < a.nC) mine |= static_cast<uint32_t>(__ldg(mb + a.T)) << 16;
+              }
+              mword[n] = mine;
+            }
+          }
           mbar_wait(bar_m1, u & 1u, 0x720u);
           tc_fence_after();
+          if (warp == 4 && lane == 0) ATB_STAMP(u, 4);
           if (warp_keys) {
-            for (int c = half; c * 32 < nq; c += 2) {
-              const int q0 = 128 * j + 32 * c;
-              uint32_t s_[32], d_[32];
-              tmem_ld_32x32(tST + c * 32, s_);
-              tmem_ld_32x32(tDP + c * 32, d_);
-              uint32_t word = 0xFFFFFFFFu;
-              if (a.mbits != nullptr) {
-                const int kc = (128 * i + w * 32) >> 5;
-                uint32_t mine = 0;
-                if (q0 + lane < a.T && kc < a.nC) mine = __ldg(a.mbits + (static_cast<int64_t>(item) * a.nC + kc) * a.T + q0 + lane);
-                word = transpose32(mine, lane);                    // bit x = keep(query q0 + x, this key)
-              }
-              tmem_ld_wait();
-              uint32_t op[32], ods[32];
 #pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
+            for (int n = 0; n < 2; ++n) {                          // nq <= 128: at most 8 chunks of 16, two per warp
+              const int c = part + 4 * n;
+              if (16 * c >= nq) break;
+              const int qt = 16 * c;                               // query inside the tile
+              uint32_t s_[16], d_[16];
+              tmem_ld_32x16(tST + qt, s_);
+              tmem_ld_32x16(tDP + qt, d_);
+              // this key's keep bits over the chunk's 16 queries (bit x = query qt + x)
+              uint32_t word = 0xFFFFFFFFu;
+              if (a.mbits != nullptr) word = transpose32(mword[n], lane);
+              const float2* strow = sStat + rpt * j + qt;          // < ATB_STATS entries are initialised for every index used
+              tmem_ld_wait();
+              uint32_t op[16], ods[16];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
                 float pd[2], ds[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   const int x = 2 * jj + e;
-                  const int qi = q0 + x >= ATB_MAXT ? 0 : q0 + x;       // past the slice: value unused (ok == false)
-                  const float2 st = sStat[qi];
-                  const float dl = sDelta[qi];
-                  const bool ok = kvalid && (q0 + x < a.T);
-                  const bool kp = (word >> x) & 1u;
-                  const float p = at_exp2(__uint_as_float(s_[x]) * ATF_SC - st.x) * st.y;
-                  const float dpm = kp ? __uint_as_float(d_[x]) * a.inv_keep : 0.f;
-                  pd[e] = (ok && kp) ? p * a.inv_keep : 0.f;
-                  ds[e] = ok ? p * (dpm - dl) * 0.125f : 0.f;
+                  const float2 st = strow[x];                      // (m + log2 l, delta); +inf past the slice -> p = 0
+                  const float kf = (word & (1u << x)) ? a.inv_keep : 0.f;
+                  const float p = at_exp2(fmaf(__uint_as_float(s_[x]), ATF_SC, -st.x));
+                  pd[e] = p * kf;
+                  ds[e] = (p * 0.125f) * fmaf(__uint_as_float(d_[x]), kf, -st.y);
                 }
-                const int slot = (jj >> 3) * 16 + (jj & 7);
                 const __nv_bfloat162 ph = __floats2bfloat162_rn(pd[0], pd[1]);
-                op[slot] = *reinterpret_cast<const uint32_t*>(&ph);
-                op[slot + 8] = pack_bf16x2(pd[0] - __bfloat162float(ph.x), pd[1] - __bfloat162float(ph.y));
+                op[jj] = *reinterpret_cast<const uint32_t*>(&ph);
+                op[jj + 8] = pack_bf16x2(pd[0] - __bfloat162float(ph.x), pd[1] - __bfloat162float(ph.y));
                 const __nv_bfloat162 dh = __floats2bfloat162_rn(ds[0], ds[1]);
-                ods[slot] = *reinterpret_cast<const uint32_t*>(&dh);
-                ods[slot + 8] = pack_bf16x2(ds[0] - __bfloat162float(dh.x), ds[1] - __bfloat162float(dh.y));
+                ods[jj] = *reinterpret_cast<const uint32_t*>(&dh);
+                ods[jj + 8] = pack_bf16x2(ds[0] - __bfloat162float(dh.x), ds[1] - __bfloat162float(dh.y));
               }
-              tmem_st_32x32(tST + c * 32, op);
-              tmem_st_32x32(tDP + c * 32, ods);
+              // rows of keys that do not belong to this tile produce rows of dV / dK nobody reads, but their dS is
+              // CONTRACTED by dQ = dS K: zero it there (the shared-memory copy), leave the TMEM copy alone
+              tmem_st_32x16(tST + qt, op);
+              tmem_st_32x16(tDP + qt, ods);
+              if (!kvalid) {
+#pragma unroll
+                for (int x = 0; x < 16; ++x) ods[x] = 0u;
+              }
               // dS^T -> shared memory, MN-major operand layout: row = key, 64 queries per 128-byte row
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int qq = 32 * c + 8 * g;                     // query inside the tile
-                const uint32_t dst = sdS + (rr >> 6) * 16384 + (qq >> 6) * 8192 + (rr & 63) * 128 +
-                                     ((((qq & 63) >> 3) ^ (rr & 7)) << 4);
-                // slots of queries 8g .. 8g+7: key step (g >> 1), pairs (g & 1) * 4 .. +3
-                const int s0 = (g >> 1) * 16 + (g & 1) * 4;
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ods[s0]), "r"(ods[s0 + 1]),
-                             "r"(ods[s0 + 2]), "r"(ods[s0 + 3]) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 32768), "r"(ods[s0 + 8]), "r"(ods[s0 + 9]),
-                             "r"(ods[s0 + 10]), "r"(ods[s0 + 11]) : "memory");
+              for (int g = 0; g < 2; ++g) {
+                const int qq = qt + 8 * g;
+                const uint32_t dst = ds_row + (qq >> 6) * 8192 + ((((qq & 63) >> 3) ^ ds_swz) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ods[4 * g]), "r"(ods[4 * g + 1]),
+                             "r"(ods[4 * g + 2]), "r"(ods[4 * g + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 32768), "r"(ods[8 + 4 * g]),
+                             "r"(ods[9 + 4 * g]), "r"(ods[10 + 4 * g]), "r"(ods[11 + 4 * g]) : "memory");
               }
             }
             tmem_st_wait();
           }
+          if (warp == 4 && lane == 0) ATB_STAMP(u, 5);
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(bar_p);
         }
-        // ---- dV_i, dK_i complete (last query tile's MMAs retired)
+        // ---- dV_i, dK_i complete (last query tile's MMAs retired; the dS tile in shared memory is free): every warp
+        //      takes 16 of the 64 columns of each out of TMEM, stages them as bf16 planes, then the quarter's four warps
+        //      write one (tensor, plane) each with full 128-byte rows
         mbar_wait(bar_tile, kt & 1u, 0x721u);
         tc_fence_after();
+        if (warp == 4 && lane == 0) ATB_STAMP(u - 1, 6);
         if (warp_keys) {
 #pragma unroll
           for (int which = 0; which < 2; ++which) {                // 0: dV, 1: dK
-            uint32_t acc[32];
-            tmem_ld_32x32(tmem_base + t_lane + (which ? ATB_T_DK : ATB_T_DV) + half * 32, acc);
+            uint32_t acc[16];
+            tmem_ld_32x16(tmem_base + t_lane + (which ? ATB_T_DK : ATB_T_DV) + part * 16, acc);
             tmem_ld_wait();
-            float v[32];
+            float v[16];
 #pragma unroll
-            for (int x = 0; x < 32; ++x) v[x] = kvalid ? __uint_as_float(acc[x]) : 0.f;
-            if (kvalid) {
-              __nv_bfloat16* dst = a.dqkv + (static_cast<int64_t>(b) * a.T + key) * (3 * 64 * a.H) + (which ? 1 : 2) * 64 * a.H +
-                                   h * 64 + half * 32;
-#pragma unroll
-              for (int p = 0; p < 2; ++p) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  uint32_t wv[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float x0 = v[g * 8 + 2 * e], x1 = v[g * 8 + 2 * e + 1];
-                    if (p == 0) {
-                      wv[e] = pack_bf16x2(x0, x1);
-                    } else {
-                      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-                      wv[e] = pack_bf16x2(x0 - __bfloat162float(hh.x), x1 - __bfloat162float(hh.y));
-                    }
-                  }
-                  *reinterpret_cast<uint4*>(dst + p * a.dqkv_ps + g * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-                }
-              }
-            }
-            const float cs = column_sums32(v, lane);
+            for (int x = 0; x < 16; ++x) v[x] = kvalid ? __uint_as_float(acc[x]) : 0.f;
+            stage16_two_planes(stage_addr(2 * which, rr, 2 * part), stage_addr(2 * which, rr, 2 * part + 1),
+                               stage_addr(2 * which + 1, rr, 2 * part), stage_addr(2 * which + 1, rr, 2 * part + 1), v);
+            const float cs = column_sums16(v, lane);
             if (which) acc_dk += cs; else acc_dv += cs;
           }
         }
         tc_fence_before();
-        mbar_arrive(bar_kvd);
-      }
-      // ---- dQ of the whole slice (thread <-> query row)
-      for (int j = 0; j < tiles; ++j) {
-        const int q = 128 * j + rr;
-        if (128 * j + w * 32 < a.Tk16) {                           // warp-uniform
-          uint32_t acc[32];
-          tmem_ld_32x32(tmem_base + t_lane + ATB_T_DQ + 64 * j + half * 32, acc);
-          tmem_ld_wait();
-          float v[32];
+        mbar_arrive(bar_kvd);                                     // TMEM accumulators are drained
+        if (warp_keys) {
+          quarter_sync(w);
+          {   // tile `part`: tensor part >> 1 (0 dV, 1 dK), plane part & 1
+            __nv_bfloat16* gbase = a.dqkv + (part & 1) * a.dqkv_ps + ((part >> 1) ? 1 : 2) * 64 * a.H + h * 64 + (lane & 7) * 8;
 #pragma unroll
-          for (int x = 0; x < 32; ++x) v[x] = q < a.T ? __uint_as_float(acc[x]) : 0.f;
-          if (q < a.T) {
-            __nv_bfloat16* dst = a.dqkv + (static_cast<int64_t>(b) * a.T + q) * (3 * 64 * a.H) + h * 64 + half * 32;
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint32_t wv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float x0 = v[g * 8 + 2 * e], x1 = v[g * 8 + 2 * e + 1];
-                  if (p == 0) {
-                    wv[e] = pack_bf16x2(x0, x1);
-                  } else {
-                    const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-                    wv[e] = pack_bf16x2(x0 - __bfloat162float(hh.x), x1 - __bfloat162float(hh.y));
-                  }
-                }
-                *reinterpret_cast<uint4*>(dst + p * a.dqkv_ps + g * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-              }
+            for (int it = 0; it < 8; ++it) {
+              const int row = w * 32 + it * 4 + (lane >> 3);
+              const uint4 val = lds128(stage_addr(part, row, lane & 7));
+              if (row < krows)
+                *reinterpret_cast<uint4*>(gbase + (static_cast<int64_t>(b) * a.T + rpt * i + row) * (3 * 64 * a.H)) = val;
             }
           }
-          acc_dq += column_sums32(v, lane);
+          quarter_sync(w);                                         // staging rows are free before the quarter writes dS again
+        }
+        if (warp == 4 && lane == 0) ATB_STAMP(u - 1, 7);
+      }
+      // ---- dQ of the whole slice (thread <-> query row), staged the same way (two planes: parts 0 and 1 write)
+      for (int j = 0; j < tiles; ++j) {
+        const int qrows = rows_of(j);
+        const bool qvalid = rr < qrows;
+        if (w * 32 < rows16_of(j)) {                               // warp-uniform (and uniform over the quarter)
+          uint32_t acc[16];
+          tmem_ld_32x16(tmem_base + t_lane + ATB_T_DQ + 64 * j + part * 16, acc);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int x = 0; x < 16; ++x) v[x] = qvalid ? __uint_as_float(acc[x]) : 0.f;
+          stage16_two_planes(stage_addr(0, rr, 2 * part), stage_addr(0, rr, 2 * part + 1), stage_addr(1, rr, 2 * part),
+                             stage_addr(1, rr, 2 * part + 1), v);
+          acc_dq += column_sums16(v, lane);
+          quarter_sync(w);
+          if (part < 2) {
+            __nv_bfloat16* gbase = a.dqkv + part * a.dqkv_ps + h * 64 + (lane & 7) * 8;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = w * 32 + it * 4 + (lane >> 3);
+              const uint4 val = lds128(stage_addr(part, row, lane & 7));
+              if (row < qrows)
+                *reinterpret_cast<uint4*>(gbase + (static_cast<int64_t>(b) * a.T + rpt * j + row) * (3 * 64 * a.H)) = val;
+            }
+          }
+          quarter_sync(w);
         }
       }
       tc_fence_before();
       mbar_arrive(bar_dqd);
     }
-    // ---- in-proj bias gradient: one atomic per warp and tensor for the whole kernel
-    if (blockIdx.x < items) {
-      const int col = h * 64 + half * 32 + lane;
+    // ---- in-proj bias gradient: one atomic per warp, tensor and column for the whole kernel
+    if (blockIdx.x < items && lane < 16) {
+      const int col = h * 64 + part * 16 + lane;
       atomicAdd(a.dbias + col, acc_dq);
       atomicAdd(a.dbias + 64 * a.H + col, acc_dk);
       atomicAdd(a.dbias + 2 * 64 * a.H + col, acc_dv);
@@ -792,17 +918,19 @@ int attn_train_bwd(const void* qkv, int64_t qkv_ps, const void* out, int64_t out
   AttnTrainBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.H = H; a.T = T;
-  a.Tk16 = (T + 15) / 16 * 16;
   a.Tk64 = (T + 63) / 64 * 64;
   a.tiles = (T + 127) / 128;
-  a.nC = (Tp + 31) / 32;
+  a.rpt = ((T + a.tiles - 1) / a.tiles + 15) / 16 * 16;      // frames split evenly over the tiles, in 16-row steps
+  a.nC = (Tp + 15) / 16;
   a.stats = reinterpret_cast<const float2*>(stats);
   a.delta = delta;
-  a.mbits = drop.thresh != 0 ? mbits : nullptr;
+  a.mbits = drop.thresh != 0 ? reinterpret_cast<const uint16_t*>(mbits) : nullptr;
   a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   a.dqkv_ps = dqkv_ps;
   a.dbias = dbias;
   a.inv_keep = drop.thresh != 0 ? drop.inv_keep : 1.f;
+  a.timeline = g_attn_timeline;
+  a.timeline_slots = g_attn_timeline_slots;
   const int64_t ld = 3 * 64 * H;
   const int64_t dims[4] = {64, T, H, B};
   const int64_t strides[3] = {ld, 64, static_cast<int64_t>(T) * ld};

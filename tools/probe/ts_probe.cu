@@ -7,6 +7,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../speaker_embedding_torch_b200/csrc ts_probe.cu -o ts_probe
 #include <cstdio>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 
 using namespace spk;
@@ -40,7 +41,12 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-// mode 0: TS, even K element in the low half; mode 1: TS, even K element in the high half; mode 2: SS with MN-major A
+__device__ __forceinline__ uint32_t pack2h(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// mode 0: TS, even K element in the low half; mode 1: TS, even K element in the high half; mode 2: SS with MN-major A;
+// mode 3: SS, A bf16 (K-major) x B fp16 (mixed operand formats in one kind::f16 MMA); mode 4: TS, A fp16 in TMEM x B bf16
 __global__ void __launch_bounds__(128, 1) probe_kernel(int mode, int* mism, float* sample) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -49,6 +55,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(int mode, int* mism, floa
   const uint32_t bar = sbase + 16384 + 32768, tmem_slot = bar + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = threadIdx.x;
   const int K = (mode == 2) ? 128 : 64;
+  const float want_scale = mode == 3 ? 0.5f : (mode == 4 ? 0.25f : 1.f);
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (warp == 0) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
   tc_fence_before();
@@ -63,17 +70,28 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(int mode, int* mism, floa
     for (int kb = 0; kb < K / 64; ++kb)
       for (int c = 0; c < 8; ++c) {
         uint32_t w[4];
-        for (int j = 0; j < 4; ++j) w[j] = pack2(bv(r, kb * 64 + c * 8 + 2 * j), bv(r, kb * 64 + c * 8 + 2 * j + 1));
+        for (int j = 0; j < 4; ++j)
+          w[j] = (mode == 3) ? pack2h(0.5f * bv(r, kb * 64 + c * 8 + 2 * j), 0.5f * bv(r, kb * 64 + c * 8 + 2 * j + 1))
+                             : pack2(bv(r, kb * 64 + c * 8 + 2 * j), bv(r, kb * 64 + c * 8 + 2 * j + 1));
         const uint32_t dst = sB + kb * 8192 + r * 128 + ((c ^ (r & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
       }
   }
-  if (mode < 2) {
+  if (mode < 2 || mode == 4) {
     uint32_t regs[32];
     for (int c = 0; c < 32; ++c)
-      regs[c] = (mode == 0) ? pack2(av(r, 2 * c), av(r, 2 * c + 1)) : pack2(av(r, 2 * c + 1), av(r, 2 * c));
+      regs[c] = (mode == 4) ? pack2h(0.25f * av(r, 2 * c), 0.25f * av(r, 2 * c + 1))
+                            : ((mode == 0) ? pack2(av(r, 2 * c), av(r, 2 * c + 1)) : pack2(av(r, 2 * c + 1), av(r, 2 * c)));
     tmem_st_32x32(tmem_base + t_lane + 64, regs);
     tmem_st_wait();
+  } else if (mode == 3) {
+    // A[r][k] bf16, K-major swizzled, one 64-wide k block: thread r writes its row
+    for (int c = 0; c < 8; ++c) {
+      uint32_t w[4];
+      for (int j = 0; j < 4; ++j) w[j] = pack2(av(r, c * 8 + 2 * j), av(r, c * 8 + 2 * j + 1));
+      const uint32_t dst = sA + r * 128 + ((c ^ (r & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    }
   } else {
     // A^T: thread kk (= k index, 128 of them) writes the 128 M values of its k row
     const int kk = r;
@@ -90,10 +108,15 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(int mode, int* mism, floa
   __syncthreads();
   tc_fence_after();
   if (threadIdx.x == 0) {
-    if (mode < 2) {
-      const uint32_t idesc = umma_idesc_bf16(128, 64, false, false);
+    if (mode < 2 || mode == 4) {
+      // mode 4: A format field [7,10) = 0 (F16), B stays BF16
+      const uint32_t idesc = umma_idesc_bf16(128, 64, false, false) & ~(mode == 4 ? (7u << 7) : 0u);
       for (int k = 0; k < 4; ++k)
         umma_bf16_ts(tmem_base, tmem_base + 64 + k * 8, umma_smem_desc(sB + k * 32, 16, 1024), idesc, k > 0);
+    } else if (mode == 3) {
+      const uint32_t idesc = umma_idesc_bf16(128, 64, false, false) & ~(7u << 10);   // B format = F16
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_base, umma_smem_desc(sA + k * 32, 16, 1024), umma_smem_desc(sB + k * 32, 16, 1024), idesc, k > 0);
     } else {
       const uint32_t idesc = umma_idesc_bf16(128, 64, true, false);
       for (int kb = 0; kb < 2; ++kb)
@@ -114,6 +137,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(int mode, int* mism, floa
       const int n = c * 32 + i;
       float want = 0.f;
       for (int k = 0; k < K; ++k) want += av(r, k) * bv(n, k);
+      want *= want_scale;
       if (__uint_as_float(d[i]) != want) ++bad;
       if (r == 5 && n == 9) { sample[0] = __uint_as_float(d[i]); sample[1] = want; }
     }
@@ -129,8 +153,9 @@ int main() {
   cudaMalloc(&mism, 4); cudaMalloc(&sample, 8);
   const int smem = 16384 + 32768 + 64 + 1024;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const char* names[3] = {"TS  A-in-TMEM, even k in LOW  half", "TS  A-in-TMEM, even k in HIGH half", "SS  MN-major A written by threads  "};
-  for (int mode = 0; mode < 3; ++mode) {
+  const char* names[5] = {"TS  A-in-TMEM, even k in LOW  half", "TS  A-in-TMEM, even k in HIGH half", "SS  MN-major A written by threads  ",
+                          "SS  A bf16 x B fp16 (mixed formats)  ", "TS  A fp16 in TMEM x B bf16        "};
+  for (int mode = 0; mode < 5; ++mode) {
     cudaMemset(mism, 0, 4);
     probe_kernel<<<1, 128, smem>>>(mode, mism, sample);
     cudaError_t e = cudaDeviceSynchronize();
