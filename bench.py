@@ -662,6 +662,51 @@ def run_infer(args):
         dist.destroy_process_group()
 
 
+def run_ge2e(args):
+    """BASELINE config 5: fused GE2E loss forward + backward, N = 64 .. 4096 speakers x 15 utterances x 256-d.
+    One JSON line: per N the device time of the library's launches (CUDA events around every kernel), the algorithmic
+    bytes (2 N M D 4: read E, write dE) and FLOPs (6 N M N D), the binding roofline side and the fraction reached."""
+    from speaker_embedding_torch_b200 import GE2E_Loss, _native
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    pk = peaks()
+    crit = GE2E_Loss().cuda()
+    M, D = 15, 256
+    rows = []
+    for N in (64, 128, 256, 512, 1024, 2048, 4096):
+        torch.manual_seed(N)
+        e = torch.nn.functional.normalize(torch.randn(N * M, D, device="cuda"), dim=1).requires_grad_(True)
+        for _ in range(max(3, args.warmup)):
+            e.grad = None
+            crit(e, M).backward()
+        torch.cuda.synchronize()
+        iters = max(5, args.steps) if N <= 1024 else 5
+        _native.prof_enable(True)
+        for _ in range(iters):
+            e.grad = None
+            loss = crit(e, M)
+            loss.backward()
+        torch.cuda.synchronize()
+        rep = _native.prof_report()
+        _native.prof_enable(False)
+        us = sum(v["ms"] for k, v in rep.items() if k.startswith("ge2e")) / iters * 1e3
+        launches = sum(v["launches"] for k, v in rep.items() if k.startswith("ge2e")) // iters
+        nbytes, flops = 2.0 * N * M * D * 4, 6.0 * N * M * N * D
+        t_hbm, t_tc = nbytes / (pk["hbm"] * 1e9), flops / (pk["tf_burst"] * 1e12)
+        bound = "hbm" if t_hbm > t_tc else "tensor"
+        achieved = nbytes / us / 1e3 if bound == "hbm" else flops / us / 1e6
+        peak = pk["hbm"] if bound == "hbm" else pk["tf_burst"]
+        rows.append({"N": N, "M": M, "us": round(us, 1), "launches": launches, "loss": round(loss.item(), 5),
+                     "alg_GBps": round(nbytes / us / 1e3, 1), "alg_TFLOPs": round(flops / us / 1e6, 2),
+                     "roofline_us": round(max(t_hbm, t_tc) * 1e6, 2), "bound": bound,
+                     "frac": round(achieved / peak, 4),
+                     "path": "fused SIMT kernel (3 stream-ordered stages)" if N < 256 else "tcgen05 GEMM composition"})
+    print(json.dumps({"metric": "fused GE2E loss fwd+bwd, microseconds per call (device time)", "unit": "us",
+                      "higher_is_better": False, "n_gpus": 1, "data": "synthetic", "dtype": "f32 (N < 256) / split-bf16 tensor core",
+                      "config": {"workload": "ge2e_sweep_N64-4096_M15_D256"}, "peaks": pk, "sweep": rows}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -669,13 +714,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="train", choices=["train", "infer"],
-                    help="train: GE2E training step (headline, BASELINE config 2/4); infer: multi-slice extraction (config 3)")
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "ge2e"],
+                    help="train: GE2E training step (headline, BASELINE config 2/4, the line also carries config 3); "
+                         "infer: multi-slice extraction alone (config 3); ge2e: fused-loss sweep (config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "infer":
         run_infer(args)
+    elif args.workload == "ge2e":
+        run_ge2e(args)
     else:
         run_native(args)
 

@@ -1,4 +1,4 @@
-// Fused GE2E loss: ONE cooperative kernel computes centroids, row/centroid normalisation, the
+// Fused GE2E loss: one kernel, three stream-ordered launches (stages), computes centroids, row/centroid normalisation, the
 // N*M x N cosine-similarity matrix, w*S - b, log-softmax cross-entropy, and its gradient
 // (dE, dw, db) without ever materialising the [N*M, N] logits or the reference's two
 // [N*M, N, D] expanded operands (/root/reference/Modules.py:121-156; math: SURVEY.md App. B).
@@ -13,11 +13,8 @@
 //
 // fp32 SIMT math throughout (bit-for-bit deterministic except the fp32 atomics of dchat/loss).
 // D is fixed at 256 (= Embedding_Size of the reference hyper-parameters): thread <-> column.
-#include <cooperative_groups.h>
 #include "common.cuh"
 #include "ge2e.h"
-
-namespace cg = cooperative_groups;
 
 namespace spk {
 
@@ -51,16 +48,18 @@ ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __rest
                   const float* __restrict__ b_ptr, float* __restrict__ loss, float* __restrict__ dE,
                   float* __restrict__ dw, float* __restrict__ db, float* __restrict__ chat,
                   float* __restrict__ cinv, float* __restrict__ einv, float* __restrict__ dchat, int need_grad,
-                  float eps) {
+                  float eps, int phase) {
+  // `phase` selects one of the three stages; the launcher enqueues them back to back on one stream (stream order is the
+  // grid-wide barrier: a cooperative launch with two grid.sync() cost 32 us at the training size, mostly in the syncs)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Ge2eSmem& sm = *reinterpret_cast<Ge2eSmem*>(smem_raw);
-  cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t NM = static_cast<int64_t>(N) * M;
   const float w = __ldg(w_ptr), b = __ldg(b_ptr);
   float* red8 = &sm.red[0][0];
 
   // ------------------------------------------------------------------ phase 1
+  if (phase == 1) {
   if (blockIdx.x == 0 && tid == 0) {
     loss[0] = 0.f;
     if (need_grad) { dw[0] = 0.f; db[0] = 0.f; }
@@ -93,9 +92,11 @@ ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __rest
     if (tid == 0) cinv[k] = 1.f / nrm;
     __syncthreads();
   }
-  grid.sync();
+  return;
+  }
 
   // ------------------------------------------------------------------ phase 2
+  if (phase == 2) {
   const int r_loc = tid >> 4;      // 0..15 : row within tile (S-tile compute mapping)
   const int cgp = tid & 15;        // columns cgp, cgp+16, cgp+32, cgp+48 of the centroid tile
   const int64_t row_tiles = (NM + TR - 1) / TR;
@@ -272,8 +273,8 @@ ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __rest
       }
     }
   }
-  if (!need_grad) return;
-  grid.sync();
+  return;
+  }
 
   // ------------------------------------------------------------------ phase 3
   for (int k = blockIdx.x; k < N; k += gridDim.x) {
@@ -310,32 +311,26 @@ int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float*
   float* cinv = dchat + static_cast<size_t>(N) * GD;
   float* einv = cinv + N;
 
-  static int max_blocks_dev[64] = {};
   static PerDeviceOnce once;
   const int smem = static_cast<int>(sizeof(Ge2eSmem));
-  int dev = 0;
-  SPK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) dev = 0;
   SPK_TRY(once.run([&]() -> int {
     SPK_CUDA(cudaFuncSetAttribute(ge2e_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int per_sm = 0, sms = 0;
-    SPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ge2e_fused_kernel, 256, smem));
-    SPK_CHECK(per_sm >= 1, "ge2e: kernel does not fit on an SM");
-    max_blocks_dev[dev] = per_sm * sms;
     return 0;
   }));
-  const int max_blocks = max_blocks_dev[dev];
   const long long NM = 1LL * N * M;
-  long long want = std::max<long long>((NM + TR - 1) / TR, N);
-  const int grid = static_cast<int>(std::min<long long>(want, max_blocks));
-  float eps = 1e-8f;
-  int ng = need_grad;
-  void* args[] = {(void*)&E, (void*)&N, (void*)&M, (void*)&w, (void*)&b, (void*)&loss, (void*)&dE, (void*)&dw,
-                  (void*)&db, (void*)&chat, (void*)&cinv, (void*)&einv, (void*)&dchat, (void*)&ng, (void*)&eps};
+  const int row_tiles = static_cast<int>((NM + TR - 1) / TR);
+  const float eps = 1e-8f;
   ProfScope prof(need_grad ? "ge2e_fused_fwd_bwd" : "ge2e_fused_fwd", (need_grad ? 6.0 : 2.0) * NM * N * GD,
                  (need_grad ? 2.0 : 1.0) * NM * GD * 4.0, st);
-  SPK_CUDA(cudaLaunchCooperativeKernel((void*)ge2e_fused_kernel, dim3(grid), dim3(256), args, smem, st));
+  // three launches in stream order: centroids | row tiles (loss, dE row part, dC) | centroid part of dE
+  ge2e_fused_kernel<<<N, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 1);
+  SPK_CUDA(cudaGetLastError());
+  ge2e_fused_kernel<<<row_tiles, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 2);
+  SPK_CUDA(cudaGetLastError());
+  if (need_grad) {
+    ge2e_fused_kernel<<<N, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 3);
+    SPK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
