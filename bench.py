@@ -473,7 +473,7 @@ def run_native(args):
                                              "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else 0.0,
                                              "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)}
                                          for k, v in sorted(irep.items(), key=lambda kv: -kv[1]["ms"])}
-        line_extra["extra"] = {"flop_accounting": "F_min (last layer pruned to the t=0 query), bf16 dense count, extra split-plane MMAs not credited",
+        line_extra["extra"] = {"flop_accounting": "F_min (last layer pruned to the t=0 query), 16-bit dense count, extra split-plane MMAs not credited",
                                "infer_tensor_frac_of_sustained": batch * min_flops_fwd(160) / (dv_ms * 1e-3) / 1e12 / pk["tf_sus"],
                                "train_precision": int(model.train_precision), "last_loss": last_loss}
 
@@ -491,7 +491,7 @@ def run_native(args):
             "metric": "GE2E train steps/sec (64 spk x 15 utt, fwd+bwd+clip+RAdam/Noam)",
             "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 (split into %d planes per operand forward / 2 backward, fp32 accumulate)" % int(model.train_precision),
+            "dtype": "f16 (operands split into %d fp16 planes forward / 2 backward = fp32-class mantissa, fp32 accumulate)" % int(model.train_precision),
             "data": "synthetic",
             "config": {"workload": "ge2e_train_step_64x15_T140-180", "speakers_per_gpu": SPEAKERS,
                        "utterances_per_speaker": UTTS, "frames": "one T~U[140,180] per step", "mel": MEL,
@@ -649,7 +649,7 @@ def run_infer(args):
             "metric": "utterances/sec, multi-slice d-vector extraction (5 x 64 frames, 32 overlap)",
             "value": world * K * utt / (ms * 1e-3), "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 operands, fp32 accumulate", "data": "synthetic",
+            "dtype": "f16 operands, fp32 accumulate", "data": "synthetic",
             "config": {"workload": "multislice_inference_5x64_o32", "utterances_per_step_per_gpu": utt,
                        "parallelism": "dp%d (utterance shards, no collective)" % world},
             "clocks": clk.summary(),
@@ -703,7 +703,7 @@ def run_ge2e(args):
                      "frac": round(achieved / peak, 4),
                      "path": "fused SIMT kernel (3 stream-ordered stages)" if N < 256 else "tcgen05 GEMM composition"})
     print(json.dumps({"metric": "fused GE2E loss fwd+bwd, microseconds per call (device time)", "unit": "us",
-                      "higher_is_better": False, "n_gpus": 1, "data": "synthetic", "dtype": "f32 (N < 256) / split-bf16 tensor core",
+                      "higher_is_better": False, "n_gpus": 1, "data": "synthetic", "dtype": "f32 (N < 256) / split-fp16 tensor core",
                       "config": {"workload": "ge2e_sweep_N64-4096_M15_D256"}, "peaks": pk, "sweep": rows}))
 
 

@@ -12,12 +12,12 @@ The modules only OWN parameters; the arithmetic runs in libspkemb.so (hand-writt
 kernels behind the C ABI of include/spkemb.h).  There is no CPU or eager-PyTorch fallback:
 CPU inputs raise ``RuntimeError``.
 
-Precision: inference (no grad) uses bf16 tensor-core operands (``eval_precision = 1``); when
-gradients are required the forward runs on three bf16 planes (hi + mid + lo, 6 MMAs per product,
-fp32-equivalent, ``train_precision = 3``) and the backward on two (3 MMAs).  The fp32-accurate
-forward is what keeps gradients within 1e-3 of the fp32 reference: a forward error delta flips
-~delta of the ReLU gates and each flip is an O(1) gradient error ("Precision").
-``train_precision = 2`` trades that for speed (gradient error ~ sqrt(2 * 3e-6) ~ 2.5e-3).
+Precision: every tensor that feeds the tensor cores is stored as fp16 "planes" (csrc/common.cuh).  Inference uses
+one plane (``eval_precision = 1``: fp16 operands, fp32 accumulate); when gradients are required forward and backward
+run on two planes (``train_precision = 2``: hi + lo = an fp32-class 22-bit mantissa, three MMAs per product).  Two
+planes matter for the GRADIENTS: a forward error delta flips ~delta of the ReLU gates and each flip is an O(1)
+gradient error ("Precision"); two bf16 planes (16 bits) were not enough, two fp16 planes are.
+``train_precision = 3`` (a third plane, six MMAs) is kept as a cross-check.
 """
 import ctypes
 import math
@@ -262,8 +262,8 @@ class GE2E(torch.nn.Module):
         self.projection = Conv1d(in_channels=emb, out_channels=emb, kernel_size=1, bias=True,
                                  w_init_gain="linear")
 
-        self.train_precision = 3      # hi+mid+lo forward / hi+lo backward when gradients are needed
-        self.eval_precision = 1       # plain bf16 operands for inference
+        self.train_precision = 2      # two fp16 planes (hi + lo ~ fp32 mantissa), forward and backward
+        self.eval_precision = 1       # one fp16 plane for inference
         self.max_slices_per_call = 8192   # inference batches are processed in chunks of this many slices
         self._cfg = N.EncoderConfig(hp.Sound.Mel_Dim, emb, hp.GE2E.Transformer.Head, emb * 4,
                                     hp.GE2E.Transformer.Num_Layers, hp.GE2E.Positional_Encoding.Max_Position,

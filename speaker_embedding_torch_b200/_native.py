@@ -202,17 +202,17 @@ def ptr(t):
 # helpers shared by tests and bench: split-bf16 planes <-> fp32
 
 def split_pack(x, planes):
-    """fp32 CUDA tensor -> bf16 tensor [planes, *x.shape] (hi, lo) via the library's kernel."""
+    """fp32 CUDA tensor -> fp16 tensor [planes, *x.shape] (hi, lo) via the library's kernel."""
     require_cuda(x, "x")
     x = x.contiguous().float()
-    out = torch.empty((planes,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((planes,) + tuple(x.shape), dtype=torch.float16, device=x.device)
     check(lib().spk_split_pack(ptr(x), ptr(out), x.numel(), planes, x.numel(), stream_ptr(x.device)),
           "spk_split_pack")
     return out
 
 
 def split_unpack(s):
-    """bf16 [planes, ...] -> fp32 (hi + lo)."""
+    """fp16 [planes, ...] -> fp32 (hi + lo)."""
     return s.float().sum(dim=0)
 
 
@@ -220,8 +220,8 @@ def gemm(a, b, planes, m, n, k, a_mn=False, b_mn=False, bias=None, relu=False, o
          atomic_out=None, ksplit=1, block_n=0, alpha=1.0):
     """D[M,N] = alpha * A B^T on split operands (test / roofline entry, 2-D unbatched).
 
-    a: bf16 [planes, M, K] (K-major) or [planes, K, M] (a_mn); b likewise with N.
-    Returns bf16 [planes, M, N], or fp32 [M, N] when out_f32 / atomic_out.
+    a: fp16 [planes, M, K] (K-major) or [planes, K, M] (a_mn); b likewise with N.
+    Returns fp16 [planes, M, N], or fp32 [M, N] when out_f32 / atomic_out.
     """
     require_cuda(a, "a")
     require_cuda(b, "b")
@@ -250,7 +250,7 @@ def gemm(a, b, planes, m, n, k, a_mn=False, b_mn=False, bias=None, relu=False, o
         flags |= 1 << 8
         d.out_planes = 1
     else:
-        out = torch.empty((planes, m, n), dtype=torch.bfloat16, device=a.device)
+        out = torch.empty((planes, m, n), dtype=torch.float16, device=a.device)
         d.out_plane_stride = out.stride(0)
         d.out_planes = planes
     d.flags = flags
@@ -277,7 +277,7 @@ def read_split(ws, layout, name, rows, cols, planes):
     out = None
     for p in range(planes):
         start = base + p * ps * 2
-        t = ws[start:start + rows * cols * 2].view(torch.bfloat16).view(rows, cols).float()
+        t = ws[start:start + rows * cols * 2].view(torch.float16).view(rows, cols).float()
         out = t if out is None else out + t
     return out
 

@@ -36,7 +36,7 @@ constexpr int AF_SMEM = AF_BAR + 128 + 1024;      // + alignment slack (230 528 
 struct AttnFusedArgs {
   CUtensorMap q_map, k_map, v_map;
   int B, H, T, Tk16, Tk64, mtiles;
-  __nv_bfloat16* out;      // [B*T, out_ld] plane 0, head h at column h*64
+  elem_t* out;      // [B*T, out_ld] plane 0, head h at column h*64
   int64_t out_ld;
 };
 
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, a.Tk16, false, false);
-      const uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+      const uint32_t idesc_s = umma_idesc_f16(128, a.Tk16, false, false);
+      const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);
       auto issue_s = [&](int it) {
         const int s = it & 1;
         const uint32_t sQ = sbase + s * AF_STAGE, sK = sQ + AF_SK;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_S, umma_smem_desc(sQ + k * 32, 16, 1024), umma_smem_desc(sK + k * 32, 16, 1024), idesc_s,
+          umma_f16(tmem_S, umma_smem_desc(sQ + k * 32, 16, 1024), umma_smem_desc(sK + k * 32, 16, 1024), idesc_s,
                     k > 0 ? 1u : 0u);
         umma_commit(bar_s);
       };
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
         for (int kb = 0; kb < a.Tk64 / 64; ++kb) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_bf16(tmem_O, umma_smem_desc(sP + kb * 16384 + k * 32, 16, 1024),
+            umma_f16(tmem_O, umma_smem_desc(sP + kb * 16384 + k * 32, 16, 1024),
                       umma_smem_desc(sV + kb * 8192 + k * 2048, 8192, 1024), idesc_o, acc);
             acc = 1;
           }
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
             const float e0 = key < a.T ? fast_exp2(__uint_as_float(sreg[g * 8 + 2 * j]) * sc - mxs) : 0.f;
             const float e1 = key + 1 < a.T ? fast_exp2(__uint_as_float(sreg[g * 8 + 2 * j + 1]) * sc - mxs) : 0.f;
             sum += e0 + e1;
-            pk[j] = pack_bf16x2(e0, e1);
+            pk[j] = pack2(e0, e1);
           }
           const int chunk = (c & 1) * 4 + g;                      // 16-byte chunk inside the 128-byte row of k-block kb
           const uint32_t dst = sP + kb * 16384 + r * 128 + ((chunk ^ (r & 7)) << 4);
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
       tc_fence_after();
       const float inv = 1.f / sum;
       const int q = mt * 128 + r;
-      __nv_bfloat16* dst = a.out + (static_cast<int64_t>(b) * a.T + q) * a.out_ld + h * 64;
+      elem_t* dst = a.out + (static_cast<int64_t>(b) * a.T + q) * a.out_ld + h * 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         tmem_ld_32x32(tmem_O + t_lane + c * 32, sreg);
@@ -181,10 +181,10 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(sreg[g * 8 + 0]) * inv, __uint_as_float(sreg[g * 8 + 1]) * inv);
-            v.y = pack_bf16x2(__uint_as_float(sreg[g * 8 + 2]) * inv, __uint_as_float(sreg[g * 8 + 3]) * inv);
-            v.z = pack_bf16x2(__uint_as_float(sreg[g * 8 + 4]) * inv, __uint_as_float(sreg[g * 8 + 5]) * inv);
-            v.w = pack_bf16x2(__uint_as_float(sreg[g * 8 + 6]) * inv, __uint_as_float(sreg[g * 8 + 7]) * inv);
+            v.x = pack2(__uint_as_float(sreg[g * 8 + 0]) * inv, __uint_as_float(sreg[g * 8 + 1]) * inv);
+            v.y = pack2(__uint_as_float(sreg[g * 8 + 2]) * inv, __uint_as_float(sreg[g * 8 + 3]) * inv);
+            v.z = pack2(__uint_as_float(sreg[g * 8 + 4]) * inv, __uint_as_float(sreg[g * 8 + 5]) * inv);
+            v.w = pack2(__uint_as_float(sreg[g * 8 + 6]) * inv, __uint_as_float(sreg[g * 8 + 7]) * inv);
             *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = v;
           }
         }
@@ -209,9 +209,9 @@ int attn_fused_fwd(const void* qkv, void* out, int64_t out_ld, int B, int H, int
   a.Tk16 = (T + 15) / 16 * 16;
   a.Tk64 = (T + 63) / 64 * 64;
   a.mtiles = (T + 127) / 128;
-  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.out = reinterpret_cast<elem_t*>(out);
   a.out_ld = out_ld;
-  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  const elem_t* base = reinterpret_cast<const elem_t*>(qkv);
   const int64_t ld = 3 * 64 * H;           // qkv row stride
   const int64_t dims[4] = {64, T, H, B};
   const int64_t strides[3] = {ld, 64, static_cast<int64_t>(T) * ld};

@@ -15,21 +15,21 @@ namespace spk {
 
 constexpr int R0_WARPS = 4;   // warps per block == heads of one slice
 
-__device__ __forceinline__ float2 load2_split(const __nv_bfloat16* base, int64_t ps, int planes, int64_t off) {
+__device__ __forceinline__ float2 load2_split(const elem_t* base, int64_t ps, int planes, int64_t off) {
   float2 r = make_float2(0.f, 0.f);
   for (int p = 0; p < planes; ++p) {
     const uint32_t w = *reinterpret_cast<const uint32_t*>(base + p * ps + off);
-    r.x += bf16lo_to_f(w);
-    r.y += bf16hi_to_f(w);
+    r.x += lo_to_f(w);
+    r.y += hi_to_f(w);
   }
   return r;
 }
-__device__ __forceinline__ void store2_split(__nv_bfloat16* base, int64_t ps, int planes, int64_t off, float a, float b) {
+__device__ __forceinline__ void store2_split(elem_t* base, int64_t ps, int planes, int64_t off, float a, float b) {
   for (int p = 0; p < planes; ++p) {
-    __nv_bfloat162 q = __floats2bfloat162_rn(a, b);
-    *reinterpret_cast<__nv_bfloat162*>(base + p * ps + off) = q;
-    a -= __bfloat162float(q.x);
-    b -= __bfloat162float(q.y);
+    const uint32_t q = pack2(a, b);
+    *reinterpret_cast<uint32_t*>(base + p * ps + off) = q;
+    a -= lo_to_f(q);
+    b -= hi_to_f(q);
   }
 }
 __device__ __forceinline__ float keep_of(const DropCfg& d, uint32_t site, uint64_t idx) {
@@ -42,7 +42,7 @@ __device__ __forceinline__ float keep_of(const DropCfg& d, uint32_t site, uint64
 // One warp per (slice b, head h).  Lane (g = lane >> 3, d8 = lane & 7): key group g handles keys t = 4 i + g,
 // d8 selects 8 consecutive head dims (one 16-byte load per plane), so a warp instruction moves 4 keys x 128 B
 // and the per-key reduction is 3 shuffles inside an 8-lane group.
-__device__ __forceinline__ void load8f(const __nv_bfloat16* base, int64_t ps, int planes, int64_t off, float (&v)[8]) {
+__device__ __forceinline__ void load8f(const elem_t* base, int64_t ps, int planes, int64_t off, float (&v)[8]) {
   load8_split(base, ps, planes, off, v);
 }
 __device__ __forceinline__ float group8_sum(float v) {
@@ -53,8 +53,8 @@ __device__ __forceinline__ float group8_sum(float v) {
 }
 
 __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
-    const __nv_bfloat16* __restrict__ q0, int64_t q_ps, const __nv_bfloat16* __restrict__ kv, int64_t kv_ps, int planes,
-    __nv_bfloat16* __restrict__ att0, int64_t a_ps, float* __restrict__ p0, float* __restrict__ pd0, DropCfg drop,
+    const elem_t* __restrict__ q0, int64_t q_ps, const elem_t* __restrict__ kv, int64_t kv_ps, int planes,
+    elem_t* __restrict__ att0, int64_t a_ps, float* __restrict__ p0, float* __restrict__ pd0, DropCfg drop,
     uint32_t site, int B, int H, int T, int Tp) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,8 +129,8 @@ int attn_row0_fwd(const void* q0, int64_t q_ps, const void* kv, int64_t kv_ps, i
   ProfScope prof("attn_row0_fwd", 4.0 * B * H * T * 64, 2.0 * B * T * 512 * planes, st);
   const int blocks = (B * H + R0_WARPS - 1) / R0_WARPS;
   attn_row0_fwd_kernel<<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(q0), q_ps, reinterpret_cast<const __nv_bfloat16*>(kv), kv_ps, planes,
-      reinterpret_cast<__nv_bfloat16*>(att0), a_ps, p0, pd0, drop, site, B, H, T, Tp);
+      reinterpret_cast<const elem_t*>(q0), q_ps, reinterpret_cast<const elem_t*>(kv), kv_ps, planes,
+      reinterpret_cast<elem_t*>(att0), a_ps, p0, pd0, drop, site, B, H, T, Tp);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -138,10 +138,11 @@ int attn_row0_fwd(const void* q0, int64_t q_ps, const void* kv, int64_t kv_ps, i
 // Backward: given d(att0), produces dq0 [B,256], dense dK | dV rows [B*T, 512] and the three in-proj bias
 // gradient slices.  p*dp' = pd*dp (pd = p*keep), so the saved p / pd pair is all the dropout state needed.
 __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
-    const __nv_bfloat16* __restrict__ datt0, int64_t da_ps, int g_planes, const __nv_bfloat16* __restrict__ q0,
-    int64_t q_ps, const __nv_bfloat16* __restrict__ kv, int64_t kv_ps, int planes, const float* __restrict__ p0,
-    const float* __restrict__ pd0, __nv_bfloat16* __restrict__ dq0, int64_t dq_ps, __nv_bfloat16* __restrict__ dkv,
-    int64_t dkv_ps, float* __restrict__ dbias /* [768] q | k | v */, int B, int H, int T, int Tp) {
+    const elem_t* __restrict__ datt0, int64_t da_ps, int g_planes, const elem_t* __restrict__ q0,
+    int64_t q_ps, const elem_t* __restrict__ kv, int64_t kv_ps, int planes, const float* __restrict__ p0,
+    const float* __restrict__ pd0, elem_t* __restrict__ dq0, int64_t dq_ps, elem_t* __restrict__ dkv,
+    int64_t dkv_ps, float* __restrict__ dbias /* [768] q | k | v */, const float* __restrict__ gscale, int B, int H,
+    int T, int Tp) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t bh = static_cast<int64_t>(blockIdx.x) * R0_WARPS + warp;
@@ -213,32 +214,33 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
   }
   if (g == 0) {
     store8_split(dq0, dq_ps, g_planes, static_cast<int64_t>(b) * 256 + col, dq);
+    const float inv_s = gscale != nullptr ? __ldg(gscale + 1) : 1.f;     // gradients arrive scaled by gscale[0]
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(dbias + col + i, dq[i]);
-      atomicAdd(dbias + 256 + col + i, ds_sum * q[i]);
-      atomicAdd(dbias + 512 + col + i, pd_sum * dout[i]);
+      atomicAdd(dbias + col + i, dq[i] * inv_s);
+      atomicAdd(dbias + 256 + col + i, ds_sum * q[i] * inv_s);
+      atomicAdd(dbias + 512 + col + i, pd_sum * dout[i] * inv_s);
     }
   }
 }
 
 int attn_row0_bwd(const void* datt0, int64_t da_ps, int g_planes, const void* q0, int64_t q_ps, const void* kv,
                   int64_t kv_ps, int planes, const float* p0, const float* pd0, void* dq0, int64_t dq_ps, void* dkv,
-                  int64_t dkv_ps, float* dbias, int B, int H, int T, int Tp, cudaStream_t st) {
+                  int64_t dkv_ps, float* dbias, const float* gscale, int B, int H, int T, int Tp, cudaStream_t st) {
   SPK_CHECK(H == R0_WARPS, "attn_row0: %d heads unsupported", H);
   ProfScope prof("attn_row0_bwd", 8.0 * B * H * T * 64, 2.0 * B * T * 512 * (planes + g_planes), st);
   const int blocks = (B * H + R0_WARPS - 1) / R0_WARPS;
   attn_row0_bwd_kernel<<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(datt0), da_ps, g_planes, reinterpret_cast<const __nv_bfloat16*>(q0), q_ps,
-      reinterpret_cast<const __nv_bfloat16*>(kv), kv_ps, planes, p0, pd0, reinterpret_cast<__nv_bfloat16*>(dq0), dq_ps,
-      reinterpret_cast<__nv_bfloat16*>(dkv), dkv_ps, dbias, B, H, T, Tp);
+      reinterpret_cast<const elem_t*>(datt0), da_ps, g_planes, reinterpret_cast<const elem_t*>(q0), q_ps,
+      reinterpret_cast<const elem_t*>(kv), kv_ps, planes, p0, pd0, reinterpret_cast<elem_t*>(dq0), dq_ps,
+      reinterpret_cast<elem_t*>(dkv), dkv_ps, dbias, gscale, B, H, T, Tp);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
 
 // dst[b * dst_row_step, :] += src[b, :]   (256 columns; scatters the t = 0 rows back into a token-major tensor)
-__global__ void __launch_bounds__(256) rows_add_kernel(__nv_bfloat16* __restrict__ dst, int64_t d_ps, int64_t dst_row_step,
-                                                       const __nv_bfloat16* __restrict__ src, int64_t s_ps, int planes,
+__global__ void __launch_bounds__(256) rows_add_kernel(elem_t* __restrict__ dst, int64_t d_ps, int64_t dst_row_step,
+                                                       const elem_t* __restrict__ src, int64_t s_ps, int planes,
                                                        int rows) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -253,8 +255,8 @@ __global__ void __launch_bounds__(256) rows_add_kernel(__nv_bfloat16* __restrict
 int rows_add(void* dst, int64_t d_ps, int64_t dst_row_step, const void* src, int64_t s_ps, int planes, int rows,
              cudaStream_t st) {
   ProfScope prof("rows_add", 0, 3.0 * rows * 512 * planes, st);
-  rows_add_kernel<<<(rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(dst), d_ps, dst_row_step,
-                                                  reinterpret_cast<const __nv_bfloat16*>(src), s_ps, planes, rows);
+  rows_add_kernel<<<(rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<elem_t*>(dst), d_ps, dst_row_step,
+                                                  reinterpret_cast<const elem_t*>(src), s_ps, planes, rows);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }

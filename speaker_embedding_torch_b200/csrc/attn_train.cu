@@ -59,7 +59,7 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]: A is [128 lanes x K] packed bf16 pairs in tensor memory (K-major by construction)
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -116,7 +116,7 @@ struct AtfCfg {
 struct AttnTrainFwdArgs {
   CUtensorMap q_map[3], k_map[3], v_map[3];
   int B, H, T, Tp, Tk16, Tk64, mtiles, nC;
-  __nv_bfloat16* out;      // [PL][B*T, out_ld], head h at column h*64
+  elem_t* out;      // [PL][B*T, out_ld], head h at column h*64
   int64_t out_ps, out_ld;
   float2* stats;           // [B*H*T] (row max * ATF_SC, row sum of exp2), may be null
   uint16_t* mbits;         // [B*H][nC][T] keep bits of 16-key chunk c of query q, null without dropout
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
     }
   } else if (warp == 1) {
     // whole warp, converged; one elected lane issues
-    const uint32_t idesc_s = umma_idesc_bf16(128, a.Tk16, false, false);
-    const uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+    const uint32_t idesc_s = umma_idesc_f16(128, a.Tk16, false, false);
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);
     constexpr int NCOMBO = PL == 3 ? 6 : 3;
     // plane products, smallest terms first (plane 0 = hi)
     constexpr int PA3[6] = {1, 0, 2, 0, 1, 0}, PB3[6] = {1, 2, 0, 1, 0, 0};
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
             const int pa = PL == 3 ? PA3[cb] : PA2[cb], pb = PL == 3 ? PB3[cb] : PB2[cb];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tS, desc_add(dQ0, pa * Cfg::Q_BYTES + k * 32), desc_add(dK0, pb * Cfg::KV_BYTES + k * 32), idesc_s,
+              umma_f16(tS, desc_add(dQ0, pa * Cfg::Q_BYTES + k * 32), desc_add(dK0, pb * Cfg::KV_BYTES + k * 32), idesc_s,
                         (cb | k) ? 1u : 0u);
           }
           umma_commit(bar_s);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
             for (int cb = 0; cb < NCOMBO; ++cb) {
               const int pa = PL == 3 ? PA3[cb] : PA2[cb], pb = PL == 3 ? PB3[cb] : PB2[cb];
               const uint32_t ta = pa == 0 ? tS + 16 * t : (pa == 1 ? tS + 16 * t + 8 : tPlo + 8 * t);
-              umma_bf16_ts(tO, ta, desc_add(dV0, pb * Cfg::KV_BYTES + voff), idesc_o, (t | cb) ? 1u : 0u);
+              umma_f16_ts(tO, ta, desc_add(dV0, pb * Cfg::KV_BYTES + voff), idesc_o, (t | cb) ? 1u : 0u);
             }
           }
           umma_commit(bar_o);
@@ -276,16 +276,16 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
               sum += e0 + e1;
               e0 = ((keep >> (2 * j)) & 1u) ? e0 : 0.f;
               e1 = ((keep >> (2 * j + 1)) & 1u) ? e1 : 0.f;
-              const __nv_bfloat162 hi = __floats2bfloat162_rn(e0, e1);
-              o01[j] = *reinterpret_cast<const uint32_t*>(&hi);           // plane 0 at columns 16c + j
-              e0 -= __bfloat162float(hi.x);
-              e1 -= __bfloat162float(hi.y);
-              const __nv_bfloat162 mid = __floats2bfloat162_rn(e0, e1);
-              o01[8 + j] = *reinterpret_cast<const uint32_t*>(&mid);      // plane 1 at columns 16c + 8 + j
+              const uint32_t hi = pack2(e0, e1);
+              o01[j] = hi;                                                // plane 0 at columns 16c + j
+              e0 -= lo_to_f(hi);
+              e1 -= hi_to_f(hi);
+              const uint32_t mid = pack2(e0, e1);
+              o01[8 + j] = mid;                                           // plane 1 at columns 16c + 8 + j
               if (PL == 3) {
-                e0 -= __bfloat162float(mid.x);
-                e1 -= __bfloat162float(mid.y);
-                o2[j] = pack_bf16x2(e0, e1);
+                e0 -= lo_to_f(mid);
+                e1 -= hi_to_f(mid);
+                o2[j] = pack2(e0, e1);
               }
             }
             tmem_st_32x16(tS + t_lane + c * 16, o01);
@@ -325,11 +325,10 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
               uint32_t wv[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 qv = __floats2bfloat162_rn(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
-                wv[i] = *reinterpret_cast<const uint32_t*>(&qv);
+                wv[i] = pack2(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
                 if (p + 1 < PL) {
-                  v[g * 8 + 2 * i] -= __bfloat162float(qv.x);
-                  v[g * 8 + 2 * i + 1] -= __bfloat162float(qv.y);
+                  v[g * 8 + 2 * i] -= lo_to_f(wv[i]);
+                  v[g * 8 + 2 * i + 1] -= hi_to_f(wv[i]);
                 }
               }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g ? my1 : my0), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]),
@@ -365,13 +364,13 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
 int attn_train_max_frames(int planes) { return planes == 3 ? AtfCfg<3>::KV_ROWS : AtfCfg<2>::KV_ROWS; }
 
 template <int PL>
-static int attn_train_fwd_launch(AttnTrainFwdArgs& a, const __nv_bfloat16* qkv, int64_t qkv_ps, cudaStream_t st) {
+static int attn_train_fwd_launch(AttnTrainFwdArgs& a, const elem_t* qkv, int64_t qkv_ps, cudaStream_t st) {
   using Cfg = AtfCfg<PL>;
   const int64_t ld = 3 * 64 * a.H;
   const int64_t dims[4] = {64, a.T, a.H, a.B};
   const int64_t strides[3] = {ld, 64, static_cast<int64_t>(a.T) * ld};
   for (int p = 0; p < PL; ++p) {
-    const __nv_bfloat16* base = qkv + p * qkv_ps;
+    const elem_t* base = qkv + p * qkv_ps;
     SPK_TRY(encode_map_4d(&a.q_map[p], base, dims, strides, 128));
     SPK_TRY(encode_map_4d(&a.k_map[p], base + 64 * a.H, dims, strides, a.Tk64));
     SPK_TRY(encode_map_4d(&a.v_map[p], base + 2 * 64 * a.H, dims, strides, a.Tk64));
@@ -402,15 +401,15 @@ int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64
   a.Tk64 = (T + 63) / 64 * 64;
   a.mtiles = (T + 127) / 128;
   a.nC = (Tp + 15) / 16;
-  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.out = reinterpret_cast<elem_t*>(out);
   a.out_ps = out_ps; a.out_ld = out_ld;
   a.stats = reinterpret_cast<float2*>(stats);
   a.mbits = drop.thresh != 0 ? reinterpret_cast<uint16_t*>(mbits) : nullptr;
   a.drop = drop; a.site = site;
   // algorithmic work: QK^T and PV (bf16 dense count); bytes: Q, K, V in, O out
   ProfScope prof("attn_train_fwd", 4.0 * B * H * T * T * 64, 4.0 * B * T * 64 * H * 2.0 * planes, st);
-  if (planes == 3) return attn_train_fwd_launch<3>(a, reinterpret_cast<const __nv_bfloat16*>(qkv), qkv_ps, st);
-  return attn_train_fwd_launch<2>(a, reinterpret_cast<const __nv_bfloat16*>(qkv), qkv_ps, st);
+  if (planes == 3) return attn_train_fwd_launch<3>(a, reinterpret_cast<const elem_t*>(qkv), qkv_ps, st);
+  return attn_train_fwd_launch<2>(a, reinterpret_cast<const elem_t*>(qkv), qkv_ps, st);
 }
 
 // =====================================================================================================================
@@ -467,9 +466,10 @@ struct AttnTrainBwdArgs {
   const float2* stats;      // [B*H*T] from the forward
   const float* delta;       // [B*H*T]
   const uint16_t* mbits;    // [B*H][nC][T] or null (no dropout)
-  __nv_bfloat16* dqkv;      // [2][B*T, 768]
+  elem_t* dqkv;      // [2][B*T, 768]
   int64_t dqkv_ps;
-  float* dbias;             // [768] += column sums of dQ | dK | dV
+  float* dbias;             // [768] += column sums of dQ | dK | dV, times *(gscale + 1)
+  const float* gscale;      // device (S, 1 / S): the gradients arrive scaled by S (may be null)
   float inv_keep;
   unsigned long long* timeline;
   size_t timeline_slots;
@@ -499,16 +499,15 @@ __device__ __forceinline__ float column_sums16(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 // 16 fp32 values -> two bf16 planes at dst / dst + ps (16-byte stores)
-__device__ __forceinline__ void store16_two_planes(__nv_bfloat16* dst, int64_t ps, const float (&v)[16]) {
+__device__ __forceinline__ void store16_two_planes(elem_t* dst, int64_t ps, const float (&v)[16]) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float x0 = v[g * 8 + 2 * e], x1 = v[g * 8 + 2 * e + 1];
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      lo[e] = pack_bf16x2(x0 - __bfloat162float(hh.x), x1 - __bfloat162float(hh.y));
+      hi[e] = pack2(x0, x1);
+      lo[e] = pack2(x0 - lo_to_f(hi[e]), x1 - hi_to_f(hi[e]));
     }
     *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(dst + ps + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -523,9 +522,8 @@ __device__ __forceinline__ void stage16_two_planes(uint32_t hi0, uint32_t hi1, u
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float x0 = v[g * 8 + 2 * e], x1 = v[g * 8 + 2 * e + 1];
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      lo[e] = pack_bf16x2(x0 - __bfloat162float(hh.x), x1 - __bfloat162float(hh.y));
+      hi[e] = pack2(x0, x1);
+      lo[e] = pack2(x0 - lo_to_f(hi[e]), x1 - hi_to_f(hi[e]));
     }
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g ? hi1 : hi0), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g ? lo1 : lo0), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
@@ -601,8 +599,8 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
     constexpr int PA[3] = {1, 0, 0}, PB[3] = {0, 1, 0};          // lo*hi, hi*lo, hi*hi
     const uint32_t tST = tmem_base + ATB_T_ST, tDP = tmem_base + ATB_T_DP, tdV = tmem_base + ATB_T_DV,
                    tdK = tmem_base + ATB_T_DK;
-    const uint32_t idesc_acc = umma_idesc_bf16(128, 64, false, true);      // A from TMEM, B MN-major
-    const uint32_t idesc_dq = umma_idesc_bf16(128, 64, true, true);        // A and B MN-major from shared memory
+    const uint32_t idesc_acc = umma_idesc_f16(128, 64, false, true);      // A from TMEM, B MN-major
+    const uint32_t idesc_dq = umma_idesc_f16(128, 64, true, true);        // A and B MN-major from shared memory
     const uint64_t dKk = umma_smem_desc(sK, 16, 1024), dVk = umma_smem_desc(sV, 16, 1024);          // K-major A
     const uint64_t dQk = umma_smem_desc(sQ, 16, 1024), dOk = umma_smem_desc(sdO, 16, 1024);         // K-major B
     const uint64_t dQm = umma_smem_desc(sQ, 8192, 1024), dOm = umma_smem_desc(sdO, 8192, 1024);     // MN-major B
@@ -616,7 +614,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
         for (int j = 0; j < tiles; ++j, ++u) {
           const int nq = rows16_of(j);
           const uint32_t qoff = static_cast<uint32_t>(j * rpt) * 128u;      // byte offset of query tile j (1024-aligned)
-          const uint32_t idesc_s = umma_idesc_bf16(128, nq, false, false);
+          const uint32_t idesc_s = umma_idesc_f16(128, nq, false, false);
           tc_fence_after();
           ATB_STAMP(u, 0);
           // ---- S^T = K_i Q_j^T, dP^T = V_i dO_j^T
@@ -629,7 +627,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
               for (int cb = 0; cb < 3; ++cb) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(td, desc_add(da, PA[cb] * 16384 + k * 32), desc_add(db, PB[cb] * ATB_QROWS + k * 32), idesc_s,
+                  umma_f16(td, desc_add(da, PA[cb] * 16384 + k * 32), desc_add(db, PB[cb] * ATB_QROWS + k * 32), idesc_s,
                             (cb | k) ? 1u : 0u);
               }
             }
@@ -651,7 +649,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
               for (int t = 0; t < nq / 16; ++t) {
 #pragma unroll
                 for (int cb = 0; cb < 3; ++cb)
-                  umma_bf16_ts(td, ta + 16 * t + 8 * PA[cb], desc_add(db, PB[cb] * ATB_QROWS + t * 2048), idesc_acc,
+                  umma_f16_ts(td, ta + 16 * t + 8 * PA[cb], desc_add(db, PB[cb] * ATB_QROWS + t * 2048), idesc_acc,
                                (j > 0 || t > 0 || cb > 0) ? 1u : 0u);
               }
             }
@@ -660,7 +658,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
             for (int t = 0; t < nk; ++t) {
 #pragma unroll
               for (int cb = 0; cb < 3; ++cb)
-                umma_bf16(tdQ, desc_add(dSm, PA[cb] * 32768 + (t >> 2) * 16384 + (t & 3) * 2048),
+                umma_f16(tdQ, desc_add(dSm, PA[cb] * 32768 + (t >> 2) * 16384 + (t & 3) * 2048),
                           desc_add(dKm, PB[cb] * 16384 + t * 2048), idesc_dq, (i > 0 || t > 0 || cb > 0) ? 1u : 0u);
             }
             if (j == tiles - 1) umma_commit(bar_tile);       // dV_i / dK_i (and, after the last tile, dQ) are complete
@@ -755,12 +753,10 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
                   pd[e] = p * kf;
                   ds[e] = (p * 0.125f) * fmaf(__uint_as_float(d_[x]), kf, -st.y);
                 }
-                const __nv_bfloat162 ph = __floats2bfloat162_rn(pd[0], pd[1]);
-                op[jj] = *reinterpret_cast<const uint32_t*>(&ph);
-                op[jj + 8] = pack_bf16x2(pd[0] - __bfloat162float(ph.x), pd[1] - __bfloat162float(ph.y));
-                const __nv_bfloat162 dh = __floats2bfloat162_rn(ds[0], ds[1]);
-                ods[jj] = *reinterpret_cast<const uint32_t*>(&dh);
-                ods[jj + 8] = pack_bf16x2(ds[0] - __bfloat162float(dh.x), ds[1] - __bfloat162float(dh.y));
+                op[jj] = pack2(pd[0], pd[1]);
+                op[jj + 8] = pack2(pd[0] - lo_to_f(op[jj]), pd[1] - hi_to_f(op[jj]));
+                ods[jj] = pack2(ds[0], ds[1]);
+                ods[jj + 8] = pack2(ds[0] - lo_to_f(ods[jj]), ds[1] - hi_to_f(ods[jj]));
               }
               // rows of keys that do not belong to this tile produce rows of dV / dK nobody reads, but their dS is
               // CONTRACTED by dQ = dS K: zero it there (the shared-memory copy), leave the TMEM copy alone
@@ -814,7 +810,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
         if (warp_keys) {
           quarter_sync(w);
           {   // tile `part`: tensor part >> 1 (0 dV, 1 dK), plane part & 1
-            __nv_bfloat16* gbase = a.dqkv + (part & 1) * a.dqkv_ps + ((part >> 1) ? 1 : 2) * 64 * a.H + h * 64 + (lane & 7) * 8;
+            elem_t* gbase = a.dqkv + (part & 1) * a.dqkv_ps + ((part >> 1) ? 1 : 2) * 64 * a.H + h * 64 + (lane & 7) * 8;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = w * 32 + it * 4 + (lane >> 3);
@@ -843,7 +839,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
           acc_dq += column_sums16(v, lane);
           quarter_sync(w);
           if (part < 2) {
-            __nv_bfloat16* gbase = a.dqkv + part * a.dqkv_ps + h * 64 + (lane & 7) * 8;
+            elem_t* gbase = a.dqkv + part * a.dqkv_ps + h * 64 + (lane & 7) * 8;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = w * 32 + it * 4 + (lane >> 3);
@@ -861,9 +857,10 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
     // ---- in-proj bias gradient: one atomic per warp, tensor and column for the whole kernel
     if (blockIdx.x < items && lane < 16) {
       const int col = h * 64 + part * 16 + lane;
-      atomicAdd(a.dbias + col, acc_dq);
-      atomicAdd(a.dbias + 64 * a.H + col, acc_dk);
-      atomicAdd(a.dbias + 2 * 64 * a.H + col, acc_dv);
+      const float inv_s = a.gscale != nullptr ? __ldg(a.gscale + 1) : 1.f;
+      atomicAdd(a.dbias + col, acc_dq * inv_s);
+      atomicAdd(a.dbias + 64 * a.H + col, acc_dk * inv_s);
+      atomicAdd(a.dbias + 2 * 64 * a.H + col, acc_dv * inv_s);
     }
   }
 
@@ -876,8 +873,8 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
 }
 
 // delta[(b*H + h)*T + t] = sum_d dO[b*T + t, h*64 + d] * O[b*T + t, h*64 + d]      (two planes of each; H = 4)
-__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t do_ps,
-                                                         const __nv_bfloat16* __restrict__ out, int64_t o_ps,
+__global__ void __launch_bounds__(256) attn_delta_kernel(const elem_t* __restrict__ dout, int64_t do_ps,
+                                                         const elem_t* __restrict__ out, int64_t o_ps,
                                                          float* __restrict__ delta, int64_t tokens, int T) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -903,7 +900,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 // [2 planes][B*T, 256]; dqkv: [2 planes][B*T, 768] (every element of the Q | K | V columns is written); dbias [768] +=.
 int attn_train_bwd(const void* qkv, int64_t qkv_ps, const void* out, int64_t out_ps, const void* dout, int64_t dout_ps,
                    const float* stats, const uint32_t* mbits, float* delta, void* dqkv, int64_t dqkv_ps, float* dbias,
-                   DropCfg drop, int B, int H, int T, int Tp, cudaStream_t st) {
+                   const float* gscale, DropCfg drop, int B, int H, int T, int Tp, cudaStream_t st) {
   SPK_CHECK(H == 4, "attn_train_bwd: 4 heads of 64");
   SPK_CHECK(T >= 1 && T <= ATB_MAXT, "attn_train_bwd: T=%d outside [1, %d]", T, ATB_MAXT);
   SPK_CHECK(drop.thresh == 0 || mbits != nullptr, "attn_train_bwd: dropout needs the forward's keep bits");
@@ -911,8 +908,8 @@ int attn_train_bwd(const void* qkv, int64_t qkv_ps, const void* out, int64_t out
   {
     ProfScope prof("attn_delta", 0, 2.0 * tokens * 256 * 2 * 2 + 4.0 * tokens * H, st);
     const int blocks = static_cast<int>(std::min<int64_t>((tokens + 7) / 8, 148 * 8));
-    attn_delta_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dout), dout_ps,
-                                              reinterpret_cast<const __nv_bfloat16*>(out), out_ps, delta, tokens, T);
+    attn_delta_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const elem_t*>(dout), dout_ps,
+                                              reinterpret_cast<const elem_t*>(out), out_ps, delta, tokens, T);
     SPK_CUDA(cudaGetLastError());
   }
   AttnTrainBwdArgs a;
@@ -925,9 +922,10 @@ int attn_train_bwd(const void* qkv, int64_t qkv_ps, const void* out, int64_t out
   a.stats = reinterpret_cast<const float2*>(stats);
   a.delta = delta;
   a.mbits = drop.thresh != 0 ? reinterpret_cast<const uint16_t*>(mbits) : nullptr;
-  a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  a.dqkv = reinterpret_cast<elem_t*>(dqkv);
   a.dqkv_ps = dqkv_ps;
   a.dbias = dbias;
+  a.gscale = gscale;
   a.inv_keep = drop.thresh != 0 ? drop.inv_keep : 1.f;
   a.timeline = g_attn_timeline;
   a.timeline_slots = g_attn_timeline_slots;
@@ -936,11 +934,11 @@ int attn_train_bwd(const void* qkv, int64_t qkv_ps, const void* out, int64_t out
   const int64_t strides[3] = {ld, 64, static_cast<int64_t>(T) * ld};
   const int64_t ostrides[3] = {64 * H, 64, static_cast<int64_t>(T) * 64 * H};
   for (int p = 0; p < 2; ++p) {
-    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(qkv) + p * qkv_ps;
+    const elem_t* base = reinterpret_cast<const elem_t*>(qkv) + p * qkv_ps;
     SPK_TRY(encode_map_4d(&a.q_map[p], base, dims, strides, a.Tk64));
     SPK_TRY(encode_map_4d(&a.k_map[p], base + 64 * H, dims, strides, 128));
     SPK_TRY(encode_map_4d(&a.v_map[p], base + 2 * 64 * H, dims, strides, 128));
-    SPK_TRY(encode_map_4d(&a.do_map[p], reinterpret_cast<const __nv_bfloat16*>(dout) + p * dout_ps, dims, ostrides, a.Tk64));
+    SPK_TRY(encode_map_4d(&a.do_map[p], reinterpret_cast<const elem_t*>(dout) + p * dout_ps, dims, ostrides, a.Tk64));
   }
   static PerDeviceOnce once;
   SPK_TRY(once.run([]() -> int {

@@ -1,7 +1,7 @@
 // Shared host/device helpers: error reporting, split-bf16 tensors, Philox dropout masks.
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -75,49 +75,53 @@ struct PerDeviceOnce {
     if (_r != 0) return _r;  \
   } while (0)
 
-// ----------------------------------------------------------------------------- split-bf16 tensors
-// Every activation / gradient that feeds a tensor-core GEMM is stored as 1..3 bf16 "planes":
-//   planes = 1  x ~= hi                (8 mantissa bits;  inference)
-//   planes = 2  x ~= hi + lo           (~16 bits; backward pass: Ah*Bh + Ah*Bl + Al*Bh, 3 MMAs)
-//   planes = 3  x ~= hi + mid + lo     (~24 bits = fp32; training forward, 6 MMAs) -- needed because a
-//               forward error delta flips ~delta of the ReLU gates and the gradient error grows like
-//               sqrt(delta) (DESIGN.md "precision"), so grad parity <= 1e-3 needs an fp32-accurate forward.
-// Plane p of a tensor with `plane_stride` elements starts at base + p * plane_stride; a tensor
-// written with 3 planes can be read with 2 (the backward pass does).
+// ----------------------------------------------------------------------------- split-fp16 tensors
+// Every activation / gradient that feeds a tensor-core GEMM is stored as 1..3 fp16 "planes":
+//   planes = 1  x ~= hi                (11 significant bits; inference)
+//   planes = 2  x ~= hi + lo           (22 bits ~ fp32: Ah*Bh + Ah*Bl + Al*Bh, 3 MMAs; training, forward and backward)
+//   planes = 3  x ~= hi + mid + lo     (33 bits; six MMAs -- kept for cross-checks, it buys nothing over two planes)
+// fp16 rather than bf16 because TWO fp16 planes already carry an fp32 mantissa (two bf16 planes carry 16 bits, which
+// flips ReLU gates and costs gradient parity, so the bf16 training forward needed three planes and six MMAs per
+// product -- DESIGN.md "precision").  The price is range: values saturate at +-65504 instead of overflowing to inf
+// (activations of a post-LN encoder stay orders of magnitude below that), tiny values keep an ABSOLUTE precision of
+// 2^-25 (the fp16 subnormal step), and gradients are carried scaled by a power of two chosen per backward pass from
+// max |dL/d dvec| (encoder.cu: grad_scale_kernel) so that they sit in the middle of the fp16 range.
+// Plane p of a tensor with `plane_stride` elements starts at base + p * plane_stride; a tensor written with 3 planes can
+// be read with 2.
+typedef __half elem_t;
 
-__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// two fp32 -> one 32-bit word of two fp16 (a in the low half), round to nearest, saturating to +-65504 (never inf)
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float bf16lo_to_f(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16hi_to_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ float lo_to_f(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xFFFFu))); }
+__device__ __forceinline__ float hi_to_f(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))); }
+__device__ __forceinline__ elem_t to_elem(float x) { return __ushort_as_half(static_cast<unsigned short>(pack2(x, 0.f) & 0xFFFFu)); }
 
 // Load 8 consecutive elements (16 B per plane, must be 16-B aligned) of a split tensor as fp32.
-__device__ __forceinline__ void load8_split(const __nv_bfloat16* base, size_t plane_stride, int planes, size_t off,
+__device__ __forceinline__ void load8_split(const elem_t* base, size_t plane_stride, int planes, size_t off,
                                             float (&v)[8]) {
   uint4 h = *reinterpret_cast<const uint4*>(base + off);
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    v[2 * i] = bf16lo_to_f(hw[i]);
-    v[2 * i + 1] = bf16hi_to_f(hw[i]);
+    v[2 * i] = lo_to_f(hw[i]);
+    v[2 * i + 1] = hi_to_f(hw[i]);
   }
   for (int p = 1; p < planes; ++p) {
     uint4 l = *reinterpret_cast<const uint4*>(base + p * plane_stride + off);
     const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      v[2 * i] += bf16lo_to_f(lw[i]);
-      v[2 * i + 1] += bf16hi_to_f(lw[i]);
+      v[2 * i] += lo_to_f(lw[i]);
+      v[2 * i + 1] += hi_to_f(lw[i]);
     }
   }
 }
-// Store 8 consecutive fp32 values as split planes (16-B aligned): plane p holds bf16(residual after planes < p).
-__device__ __forceinline__ void store8_split(__nv_bfloat16* base, size_t plane_stride, int planes, size_t off,
+// Store 8 consecutive fp32 values as split planes (16-B aligned): plane p holds fp16(residual after planes < p).
+__device__ __forceinline__ void store8_split(elem_t* base, size_t plane_stride, int planes, size_t off,
                                              const float (&v)[8]) {
   float r[8];
 #pragma unroll
@@ -126,24 +130,23 @@ __device__ __forceinline__ void store8_split(__nv_bfloat16* base, size_t plane_s
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 q = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&q);
-      r[2 * i] -= __bfloat162float(q.x);
-      r[2 * i + 1] -= __bfloat162float(q.y);
+      w[i] = pack2(r[2 * i], r[2 * i + 1]);
+      r[2 * i] -= lo_to_f(w[i]);
+      r[2 * i + 1] -= hi_to_f(w[i]);
     }
     *reinterpret_cast<uint4*>(base + p * plane_stride + off) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
-__device__ __forceinline__ float load1_split(const __nv_bfloat16* base, size_t plane_stride, int planes, size_t off) {
-  float v = __bfloat162float(base[off]);
-  for (int p = 1; p < planes; ++p) v += __bfloat162float(base[p * plane_stride + off]);
+__device__ __forceinline__ float load1_split(const elem_t* base, size_t plane_stride, int planes, size_t off) {
+  float v = __half2float(base[off]);
+  for (int p = 1; p < planes; ++p) v += __half2float(base[p * plane_stride + off]);
   return v;
 }
-__device__ __forceinline__ void store1_split(__nv_bfloat16* base, size_t plane_stride, int planes, size_t off, float x) {
+__device__ __forceinline__ void store1_split(elem_t* base, size_t plane_stride, int planes, size_t off, float x) {
   for (int p = 0; p < planes; ++p) {
-    const __nv_bfloat16 q = __float2bfloat16_rn(x);
+    const elem_t q = to_elem(x);
     base[p * plane_stride + off] = q;
-    x -= __bfloat162float(q);
+    x -= __half2float(q);
   }
 }
 

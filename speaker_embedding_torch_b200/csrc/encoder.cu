@@ -16,14 +16,14 @@ int attn_row0_fwd(const void* q0, int64_t q_ps, const void* kv, int64_t kv_ps, i
                   float* p0, float* pd0, DropCfg drop, uint32_t site, int B, int H, int T, int Tp, cudaStream_t st);
 int attn_row0_bwd(const void* datt0, int64_t da_ps, int g_planes, const void* q0, int64_t q_ps, const void* kv,
                   int64_t kv_ps, int planes, const float* p0, const float* pd0, void* dq0, int64_t dq_ps, void* dkv,
-                  int64_t dkv_ps, float* dbias, int B, int H, int T, int Tp, cudaStream_t st);
+                  int64_t dkv_ps, float* dbias, const float* gscale, int B, int H, int T, int Tp, cudaStream_t st);
 int attn_fused_fwd(const void* qkv, void* out, int64_t out_ld, int B, int H, int T, cudaStream_t st);
 int attn_train_max_frames(int planes);
 int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64_t out_ps, int64_t out_ld, float* stats,
                    uint32_t* mbits, DropCfg drop, uint32_t site, int B, int H, int T, int Tp, cudaStream_t st);
 int attn_train_bwd(const void* qkv, int64_t qkv_ps, const void* out, int64_t out_ps, const void* dout, int64_t dout_ps,
                    const float* stats, const uint32_t* mbits, float* delta, void* dqkv, int64_t dqkv_ps, float* dbias,
-                   DropCfg drop, int B, int H, int T, int Tp, cudaStream_t st);
+                   const float* gscale, DropCfg drop, int B, int H, int T, int Tp, cudaStream_t st);
 int rows_add(void* dst, int64_t d_ps, int64_t dst_row_step, const void* src, int64_t s_ps, int planes, int rows,
              cudaStream_t st);
 
@@ -52,6 +52,7 @@ struct Plan {
   int B, T, S, P, Tp, H, D, F, C, L;
   int64_t Mt, BH;
   bool keep, prune, fused_infer, fused_train;
+  size_t gscale;      // backward: (S, 1 / S), the power-of-two scale the gradient planes are carried at
   bool attn_tr;       // the dense layers of this training plan use the fused attention kernels (attn_train.cu)
   size_t adelta;      // fused training attention backward: delta = rowsum(dO * O), [B*H*T] fp32
   LastBufs last;
@@ -103,7 +104,7 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int Pflag
   SPK_CHECK(B >= 1 && T >= 1 && T <= c.max_pos && T <= 1024, "encoder: frames %d outside [1, %d]", T,
             c.max_pos < 1024 ? c.max_pos : 1024);
   SPK_CHECK(S >= 1 && B % S == 0, "encoder: batch %d is not a multiple of samples %d", B, S);
-  SPK_CHECK(P >= 1 && P <= 3, "encoder: precision must be 1 (bf16), 2 (hi+lo) or 3 (hi+mid+lo)");
+  SPK_CHECK(P >= 1 && P <= 3, "encoder: precision must be 1 (fp16), 2 (hi+lo) or 3 (hi+mid+lo)");
   pl.B = B; pl.T = T; pl.S = S; pl.P = P; pl.Tp = (T + 7) / 8 * 8;
   pl.H = c.heads; pl.D = c.emb; pl.F = c.ffn; pl.C = c.mel_dim; pl.L = c.layers;
   pl.Mt = static_cast<int64_t>(B) * T;
@@ -185,6 +186,7 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int Pflag
     pl.dqkv = take_split(cur, Mt * 3 * D, Pb);
     pl.ds = take_split(cur, score_elems, Pb);
     pl.adelta = take_f32(cur, pl.BH * T);
+    pl.gscale = take_f32(cur, 64);
     // compact [B, 256] gradient of the last layer's single query row (its own buffer: scr is BH*T*Tp elements per
     // plane, smaller than B*256 for T < 8)
     if (pl.prune) pl.dq0 = take_split(cur, static_cast<int64_t>(B) * D, Pb);
@@ -231,9 +233,44 @@ int encoder_debug_layout(const spk_encoder_config& c, int B, int T, int S, int P
 }
 
 // ------------------------------------------------------------------------------------------------
+// Gradient scale of one backward pass.  The gradient tensors live in fp16 planes (common.cuh): they are carried
+// multiplied by S = 2^k, k chosen so that max |dL/d dvec| * S lands in [2^11, 2^12) -- four binades of headroom below
+// the fp16 maximum for growth inside the encoder (conversions saturate, they never produce inf), and as much range as
+// possible below: a pair of fp16 planes carries 22 bits only down to 0.125, smaller values keep an ABSOLUTE precision of
+// 2^-25, so the measured gradient error falls with S (2 x 2 x 1024 frames: 1.5e-3 at 2^8, 1.5e-4 at 2^12, 7e-5 at 2^14;
+// tools/grad_probe.py).  Everything downstream of the head is linear in the gradient, so S travels through untouched; the kernels
+// that meet unscaled quantities (parameter gradients: weight-gradient GEMMs, bias column sums, LayerNorm affine
+// gradients, alpha) multiply by 1 / S, read from this buffer.  S is a device scalar: no host synchronisation.
+static int g_grad_scale_log2 = 12;    // spk_set_option("grad_scale_log2", k): max |dL/d dvec| * S lands in [2^(k-1), 2^k)
+void encoder_set_grad_scale_log2(int k) { g_grad_scale_log2 = k < -8 ? -8 : (k > 15 ? 15 : k); }
+__global__ void __launch_bounds__(256) grad_scale_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out,
+                                                         int target_log2) {
+  __shared__ float red[8];
+  float mx = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) mx = fmaxf(mx, fabsf(g[i]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]);
+    float s = 1.f;
+    if (m > 0.f && isfinite(m)) {
+      int e;
+      frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+      int k = target_log2 - e;             // m * 2^k in [2^(target-1), 2^target)
+      k = k < -24 ? -24 : (k > 40 ? 40 : k);
+      s = ldexpf(1.f, k);
+    }
+    out[0] = s;
+    out[1] = 1.f / s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // d-vector head (Modules.py:54-57): final LayerNorm of the t = 0 token of every slice, mean over the
 // `samples` slices of an utterance, 256x256 projection (fp32), L2 normalisation.
-__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ h, int64_t ps, int planes,
+__global__ void __launch_bounds__(256) head_fwd_kernel(const elem_t* __restrict__ h, int64_t ps, int planes,
                                                        int T, int S, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ wp,
                                                        const float* __restrict__ bp, float* __restrict__ hn,
@@ -292,12 +329,12 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
 // Backward of the head for one utterance: d_dvec -> de (pre-normalisation), d_emean, final-LN backward
 // into the t = 0 rows of dH (pre-zeroed), dgamma/dbeta of the final LayerNorm.
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ g_dvec, const float* __restrict__ epre,
-                                                       const float* __restrict__ wp, const __nv_bfloat16* __restrict__ h,
+                                                       const float* __restrict__ wp, const elem_t* __restrict__ h,
                                                        int64_t h_ps, int planes, const float2* __restrict__ hst,
                                                        const float* __restrict__ gamma, int T, int S,
-                                                       float* __restrict__ de_out, __nv_bfloat16* __restrict__ dh,
+                                                       float* __restrict__ de_out, elem_t* __restrict__ dh,
                                                        int64_t dh_ps, float* __restrict__ dgamma,
-                                                       float* __restrict__ dbeta) {
+                                                       float* __restrict__ dbeta, const float* __restrict__ gscale) {
   __shared__ float red[8];
   __shared__ float des[256];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -343,7 +380,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     const float gd = dm * gam;
     const float m1 = bsum(gd) * (1.f / 256.f);
     const float m2 = bsum(gd * xh) * (1.f / 256.f);
-    store1_split(dh, dh_ps, planes, off, ms.y * (gd - m1 - xh * m2));
+    store1_split(dh, dh_ps, planes, off, ms.y * (gd - m1 - xh * m2) * __ldg(gscale));   // enters the encoder scaled by S
   }
   atomicAdd(dgamma + tid, ag);
   atomicAdd(dbeta + tid, ab);
@@ -371,8 +408,8 @@ struct Ctx {
   char* ws;
   cudaStream_t st;
   int P;
-  __nv_bfloat16* ptr(const Split& s, int64_t elem_off = 0) const {
-    return reinterpret_cast<__nv_bfloat16*>(ws + s.off) + elem_off;
+  elem_t* ptr(const Split& s, int64_t elem_off = 0) const {
+    return reinterpret_cast<elem_t*>(ws + s.off) + elem_off;
   }
   float* f32(size_t off) const { return reinterpret_cast<float*>(ws + off); }
   SplitMat mat(const Split& s, int64_t elem_off, int64_t rows, int64_t cols, int64_t ld, int64_t sb0 = 0,
@@ -403,7 +440,7 @@ int wgrad_ksplit(int64_t K, int M, int N) {
 
 // dW[M_out, N_in] += dY^T[M_out, tokens] * X[tokens, N_in]   (both operands read MN-major, split-K, fp32 atomics)
 int wgrad(const Ctx& c, const Split& dy, int64_t dy_cols, const Split& x, int64_t x_cols, float* dw,
-          const char* tag) {
+          const char* tag, const float* inv_scale) {
   GemmProblem g;
   g.tag = tag;
   g.A = c.mat(dy, 0, c.pl.Mt, dy_cols, dy_cols);
@@ -412,6 +449,7 @@ int wgrad(const Ctx& c, const Split& dy, int64_t dy_cols, const Split& x, int64_
   g.M = static_cast<int>(dy_cols); g.N = static_cast<int>(x_cols); g.K = static_cast<int>(c.pl.Mt);
   g.ksplit = wgrad_ksplit(c.pl.Mt, g.M, g.N);
   g.epi.flags = EPI_OUT_ATOMIC;
+  g.epi.alpha_ptr = inv_scale;       // dY arrives scaled by S (grad_scale_kernel)
   g.epi.out = dw; g.epi.out_ld = x_cols;
   return gemm_run(g, c.st);
 }
@@ -645,6 +683,16 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
   const int Tp = pl.Tp, H = pl.H;
   const DropCfg drop_pe = make_drop(seed, cfg.pe_dropout, training != 0);
   const DropCfg drop = make_drop(seed, cfg.dropout, training != 0);
+  // gradient scale of this pass (device scalars S, 1 / S) and a gemm_run that hands 1 / S to every epilogue that
+  // produces parameter gradients (fp32 atomics of the weight gradients, fused bias column sums)
+  float* gs = c.f32(pl.gscale);
+  auto run = [&](GemmProblem& g) {
+    if (g.epi.flags & EPI_OUT_ATOMIC) g.epi.alpha_ptr = gs + 1;
+    if (g.epi.flags & EPI_COLSUM) g.epi.colsum_scale_ptr = gs + 1;
+    return gemm_run(g, st);
+  };
+  grad_scale_kernel<<<1, 256, 0, st>>>(d_dvec, static_cast<int64_t>(B / S) * 256, gs, g_grad_scale_log2);
+  SPK_CUDA(cudaGetLastError());
 
   // ---- head
   const Split& hl = pl.prune ? pl.last.hout : pl.Lb[pl.L - 1].hout;
@@ -656,7 +704,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
   ProfScope prof_hb("head_bwd", 4.0 * (B / S) * 256 * 256, 4.0 * B * 256 * 2, st);
   head_bwd_kernel<<<B / S, 256, 0, st>>>(d_dvec, c.f32(pl.epre), w.proj_w, c.ptr(hl), hl.ps, P,
                                          reinterpret_cast<const float2*>(c.f32(pl.hst)), w.norm_w, head_T, S, c.f32(pl.de),
-                                         c.ptr(dhead), dhead.ps, gr.norm_w, gr.norm_b);
+                                         c.ptr(dhead), dhead.ps, gr.norm_w, gr.norm_b, gs);
   SPK_CUDA(cudaGetLastError());
   head_wgrad_kernel<<<256, 256, 0, st>>>(c.f32(pl.de), c.f32(pl.emean), B / S, gr.proj_w, gr.proj_b);
   SPK_CUDA(cudaGetLastError());
@@ -681,10 +729,10 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.ksplit = wgrad_ksplit(B, g.M, g.N);
       g.epi.flags = EPI_OUT_ATOMIC;
       g.epi.out = dw; g.epi.out_ld = x_cols;
-      return gemm_run(g, st);
+      return run(g);
     };
     SPK_TRY(ln_bwd(c.ptr(pl.dh_b), pl.dh_b.ps, P, c.ptr(lb.z2), lb.z2.ps, P, c.f32(lb.st2), lw.norm2_w, c.ptr(pl.dz),
-                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 4 + 4 * l, lg.norm2_w, lg.norm2_b, lg.linear2_b, B, st));
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 4 + 4 * l, lg.norm2_w, lg.norm2_b, lg.linear2_b, B, gs, st));
     SPK_TRY(small_wgrad(dy, D, lb.f, F, F, lg.linear2_w, "gemm.last.bwd.ffn2_wgrad"));
     {
       GemmProblem g;
@@ -698,7 +746,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.epi.gate = c.ptr(lb.f); g.epi.gate_plane_stride = lb.f.ps; g.epi.gate_ld = F; g.epi.gate_planes = 1;
       g.epi.gate_scale = drop.inv_keep;
       c.out(g.epi, pl.df, 0, F);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     SPK_TRY(small_wgrad(pl.df, F, lb.h1, D, D, lg.linear1_w, "gemm.last.bwd.ffn1_wgrad"));
     {
@@ -711,10 +759,10 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.epi.flags = EPI_RES;
       c.res(g.epi, pl.dz, D);
       c.out(g.epi, pl.dh_b, 0, D);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     SPK_TRY(ln_bwd(c.ptr(pl.dh_b), pl.dh_b.ps, P, c.ptr(lb.z1), lb.z1.ps, P, c.f32(lb.st1), lw.norm1_w, c.ptr(pl.dz),
-                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 2 + 4 * l, lg.norm1_w, lg.norm1_b, lg.out_proj_b, B, st));
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 2 + 4 * l, lg.norm1_w, lg.norm1_b, lg.out_proj_b, B, gs, st));
     SPK_TRY(small_wgrad(dy, D, lb.att0, D, D, lg.out_proj_w, "gemm.last.bwd.out_wgrad"));
     {
       GemmProblem g;
@@ -724,12 +772,12 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.b_mn = true;
       g.planes = P; g.M = B; g.N = (int)D; g.K = (int)D;
       c.out(g.epi, pl.datt, 0, D);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     // single-query attention backward: dq0 (compact [B, 256]), dK | dV -> dqkv viewed as [Mt, 512]
     SPK_TRY(attn_row0_bwd(c.ptr(pl.datt), pl.datt.ps, P, c.ptr(lb.q0), lb.q0.ps, c.ptr(lb.kv), lb.kv.ps, P_fwd,
                           c.f32(lb.p0), c.f32(lb.pd0), c.ptr(pl.dq0), pl.dq0.ps, c.ptr(pl.dqkv), pl.dqkv.ps,
-                          lg.in_proj_b, B, H, T, Tp, st));
+                          lg.in_proj_b, gs, B, H, T, Tp, st));
     SPK_TRY(small_wgrad(pl.dq0, D, hin, D, (int64_t)T * D, lg.in_proj_w, "gemm.last.bwd.q_wgrad"));
     {  // dW[K|V rows] = dKV^T hin
       GemmProblem g;
@@ -741,7 +789,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.ksplit = wgrad_ksplit(Mt, g.M, g.N);
       g.epi.flags = EPI_OUT_ATOMIC;
       g.epi.out = lg.in_proj_w + D * D; g.epi.out_ld = D;
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     {  // dH(in) = dKV W[K|V rows]  for every frame
       GemmProblem g;
@@ -751,7 +799,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.b_mn = true;
       g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)(2 * D);
       c.out(g.epi, pl.dh_a, 0, D);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     {  // t = 0 rows additionally receive dq0 Wq and the residual path dZ1
       GemmProblem g;
@@ -763,7 +811,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.epi.flags = EPI_RES;
       c.res(g.epi, pl.dz, D);
       c.out(g.epi, pl.dh_b, 0, D);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     SPK_TRY(rows_add(c.ptr(pl.dh_a), pl.dh_a.ps, T, c.ptr(pl.dh_b), pl.dh_b.ps, P, B, st));
   }
@@ -776,8 +824,8 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     const Split& dy_ffn = drop.thresh ? pl.dzd : pl.dz;
     // ---- LayerNorm2 backward: dH(out) -> dZ2 (residual path) and dZ2 * mask (FFN path)
     SPK_TRY(ln_bwd(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.ptr(b.z2), b.z2.ps, P, c.f32(b.st2), lw.norm2_w, c.ptr(pl.dz),
-                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 4 + 4 * l, lg.norm2_w, lg.norm2_b, lg.linear2_b, Mt, st));
-    SPK_TRY(wgrad(c, dy_ffn, D, b.f, F, lg.linear2_w, "gemm.bwd.ffn2_wgrad"));
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 4 + 4 * l, lg.norm2_w, lg.norm2_b, lg.linear2_b, Mt, gs, st));
+    SPK_TRY(wgrad(c, dy_ffn, D, b.f, F, lg.linear2_w, "gemm.bwd.ffn2_wgrad", gs + 1));
     {  // dU = (dY2 W2) * 1[f > 0] / (1 - p)
       GemmProblem g;
       g.tag = "gemm.bwd.ffn2_dgrad";
@@ -790,9 +838,9 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.epi.gate_bits = reinterpret_cast<uint32_t*>(c.f32(b.fbits));   // written by the forward FFN1 epilogue
       g.epi.gate_scale = drop.inv_keep;
       c.out(g.epi, pl.df, 0, F);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
-    SPK_TRY(wgrad(c, pl.df, F, b.h1, D, lg.linear1_w, "gemm.bwd.ffn1_wgrad"));
+    SPK_TRY(wgrad(c, pl.df, F, b.h1, D, lg.linear1_w, "gemm.bwd.ffn1_wgrad", gs + 1));
     {  // dH1 = dU W1 + dZ2
       GemmProblem g;
       g.tag = "gemm.bwd.ffn1_dgrad";
@@ -803,13 +851,13 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.epi.flags = EPI_RES;
       c.res(g.epi, pl.dz, D);
       c.out(g.epi, pl.dh_b, 0, D);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     // ---- LayerNorm1 backward
     const Split& dy_att = drop.thresh ? pl.dzd : pl.dz;
     SPK_TRY(ln_bwd(c.ptr(pl.dh_b), pl.dh_b.ps, P, c.ptr(b.z1), b.z1.ps, P, c.f32(b.st1), lw.norm1_w, c.ptr(pl.dz),
-                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 2 + 4 * l, lg.norm1_w, lg.norm1_b, lg.out_proj_b, Mt, st));
-    SPK_TRY(wgrad(c, dy_att, D, b.att, D, lg.out_proj_w, "gemm.bwd.out_wgrad"));
+                   pl.dz.ps, P, c.ptr(pl.dzd), drop, 2 + 4 * l, lg.norm1_w, lg.norm1_b, lg.out_proj_b, Mt, gs, st));
+    SPK_TRY(wgrad(c, dy_att, D, b.att, D, lg.out_proj_w, "gemm.bwd.out_wgrad", gs + 1));
     {  // dATT = dY1 Wo
       GemmProblem g;
       g.tag = "gemm.bwd.out_dgrad";
@@ -818,13 +866,13 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.b_mn = true;
       g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = (int)D;
       c.out(g.epi, pl.datt, 0, D);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     // ---- attention backward, per (slice, head)
     if (pl.attn_tr) {
       SPK_TRY(attn_train_bwd(c.ptr(b.qkv), b.qkv.ps, c.ptr(b.att), b.att.ps, c.ptr(pl.datt), pl.datt.ps, c.f32(b.astat),
                              reinterpret_cast<const uint32_t*>(c.f32(b.abits)), c.f32(pl.adelta), c.ptr(pl.dqkv),
-                             pl.dqkv.ps, lg.in_proj_b, drop, B, H, T, Tp, st));
+                             pl.dqkv.ps, lg.in_proj_b, gs, drop, B, H, T, Tp, st));
     } else {
     const Split& pdrop = drop.thresh ? b.pd : b.p;
     const int64_t sP0 = (int64_t)T * Tp, sP1 = (int64_t)H * T * Tp;
@@ -838,7 +886,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
       g.epi.flags = EPI_COLSUM; g.epi.colsum = lg.in_proj_b + 2 * D; g.epi.colsum_sb0 = 64;
       c.out(g.epi, pl.dqkv, 2 * D, 3 * D, sQ0, sQ1);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     {  // dP_drop = dO V^T
       GemmProblem g;
@@ -849,7 +897,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       c.out(g.epi, pl.scr, 0, Tp, sP0, sP1);
       if (P >= 2) g.epi.flags |= EPI_OUT_F32;
       if (P >= 2) g.block_n = 64;   // as for QK^T
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     SPK_TRY(softmax_bwd(c.ptr(b.p), c.ptr(pl.scr), P >= 2 ? reinterpret_cast<const float*>(c.ptr(pl.scr)) : nullptr,
                         b.p.ps, P, c.ptr(pl.ds), drop, 1 + 4 * l, 0.125f, pl.BH * T, T, Tp, st));
@@ -862,7 +910,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
       g.epi.flags = EPI_COLSUM; g.epi.colsum = lg.in_proj_b; g.epi.colsum_sb0 = 64;
       c.out(g.epi, pl.dqkv, 0, 3 * D, sQ0, sQ1);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     {  // dK = dS^T Q
       GemmProblem g;
@@ -873,11 +921,11 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.planes = P; g.M = T; g.N = 64; g.K = T; g.nb0 = H; g.nb1 = B;
       g.epi.flags = EPI_COLSUM; g.epi.colsum = lg.in_proj_b + D; g.epi.colsum_sb0 = 64;
       c.out(g.epi, pl.dqkv, D, 3 * D, sQ0, sQ1);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
     }
     // ---- in-proj
-    SPK_TRY(wgrad(c, pl.dqkv, 3 * D, hin, D, lg.in_proj_w, "gemm.bwd.qkv_wgrad"));
+    SPK_TRY(wgrad(c, pl.dqkv, 3 * D, hin, D, lg.in_proj_w, "gemm.bwd.qkv_wgrad", gs + 1));
     {  // dH(in) = dQKV Win + dZ1
       GemmProblem g;
       g.tag = "gemm.bwd.qkv_dgrad";
@@ -888,11 +936,11 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       g.epi.flags = EPI_RES;
       c.res(g.epi, pl.dz, D);
       c.out(g.epi, pl.dh_a, 0, D);
-      SPK_TRY(gemm_run(g, st));
+      SPK_TRY(run(g));
     }
   }
   // ---- embedding: positional alpha, prenet weight / bias  (ReLU gate recomputed from x0 W^T + b)
-  SPK_TRY(pe_alpha_grad(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.f32(pl.pe_t), drop_pe, 0, gr.pe_alpha, Mt, T, st));
+  SPK_TRY(pe_alpha_grad(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.f32(pl.pe_t), drop_pe, 0, gr.pe_alpha, Mt, T, gs, st));
   {
     GemmProblem g;
     g.tag = "gemm.bwd.prenet_gate";
@@ -905,9 +953,9 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
     g.epi.bias = w.prenet_b; g.epi.drop = drop_pe; g.epi.drop_site = 0;
     c.res(g.epi, pl.dh_a, D);
     c.out(g.epi, pl.dh_b, 0, D);
-    SPK_TRY(gemm_run(g, st));
+    SPK_TRY(run(g));
   }
-  SPK_TRY(wgrad(c, pl.dh_b, D, pl.x0, pl.C, gr.prenet_w, "gemm.bwd.prenet_wgrad"));
+  SPK_TRY(wgrad(c, pl.dh_b, D, pl.x0, pl.C, gr.prenet_w, "gemm.bwd.prenet_wgrad", gs + 1));
   return 0;
 }
 

@@ -18,4 +18,5 @@ void encoder_set_prune(bool on);
 void encoder_set_fused_attn(bool on);
 void encoder_set_fused_train_attn(bool on);
 int encoder_plan_flags();
+void encoder_set_grad_scale_log2(int k);
 }  // namespace spk

@@ -63,8 +63,8 @@ size_t ge2e_tc_workspace_bytes(int N, int M) { return tc_plan(N, M).total; }
 
 // ---- prep: one block (256 threads = 8 warps) per speaker
 __global__ void __launch_bounds__(256) ge2e_prep_kernel(const float* __restrict__ E, int N, int M,
-                                                        __nv_bfloat16* __restrict__ ehat, int64_t e_ps,
-                                                        __nv_bfloat16* __restrict__ chat, int64_t c_ps,
+                                                        elem_t* __restrict__ ehat, int64_t e_ps,
+                                                        elem_t* __restrict__ chat, int64_t c_ps,
                                                         float* __restrict__ chat32, float* __restrict__ einv,
                                                         float* __restrict__ cinv, float* __restrict__ scal, float eps) {
   __shared__ float part[8][TD];
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) ge2e_prep_kernel(const float* __restrict_
     if (lane == 0) einv[row] = inv;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] *= inv;
-    store8_split(ehat, e_ps, 3, row * TD + lane * 8, v);
+    store8_split(ehat, e_ps, 2, row * TD + lane * 8, v);      // two fp16 planes carry an fp32 mantissa
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) part[warp][lane * 8 + i] = cp[i];
@@ -102,14 +102,14 @@ __global__ void __launch_bounds__(256) ge2e_prep_kernel(const float* __restrict_
   const float nrm = fmaxf(sqrtf(tot), eps);
   const float ch = cv / nrm;
   chat32[static_cast<int64_t>(k) * TD + tid] = ch;
-  store1_split(chat, c_ps, 3, static_cast<int64_t>(k) * TD + tid, ch);
+  store1_split(chat, c_ps, 2, static_cast<int64_t>(k) * TD + tid, ch);
   if (tid == 0) cinv[k] = 1.f / nrm;
 }
 
 // ---- rows: one warp per embedding row; lane handles columns lane*8 + 256*c
 __global__ void __launch_bounds__(256) ge2e_rows_kernel(const float* __restrict__ S, int64_t NM, int N, int Np, int M,
                                                         const float* __restrict__ w_ptr, const float* __restrict__ b_ptr,
-                                                        __nv_bfloat16* __restrict__ G, int64_t g_ps,
+                                                        elem_t* __restrict__ G, int64_t g_ps,
                                                         float* __restrict__ scal, int need_grad) {
   __shared__ float red[3][8];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -154,10 +154,11 @@ __global__ void __launch_bounds__(256) ge2e_rows_kernel(const float* __restrict_
           g[i] = 0.f;
           if (c0 + i < N) {
             const float p = expf(w * v[i] - b - lse);
-            const float pm = (p - (c0 + i == label ? 1.f : 0.f)) * inv_nm;
+            const float pm1 = p - (c0 + i == label ? 1.f : 0.f);
+            const float pm = pm1 * inv_nm;
             dw_acc += pm * v[i];
             db_acc -= pm;
-            g[i] = w * pm;
+            g[i] = w * pm1;      // G * NM: O(w), well inside the fp16 planes' range; 1 / NM is the GEMMs' alpha
           }
         }
         store8_split(G, g_ps, 2, r * Np + c0, g);
@@ -224,7 +225,7 @@ int ge2e_tc(const float* E, int N, int M, const float* w, const float* b, float*
     return SPK_ENOMEM;
   }
   char* ws = reinterpret_cast<char*>(ws_v);
-  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  auto bf = [&](size_t off) { return reinterpret_cast<elem_t*>(ws + off); };
   auto fp = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   const int need_grad = dE != nullptr;
   const int64_t NM = pl.NM;
@@ -240,7 +241,7 @@ int ge2e_tc(const float* E, int N, int M, const float* w, const float* b, float*
     g.tag = "ge2e_tc.gemm_s";
     g.A.base = bf(pl.ehat); g.A.plane_stride = pl.ehat_ps; g.A.rows = NM; g.A.cols = TD; g.A.ld = TD;
     g.B.base = bf(pl.chat); g.B.plane_stride = pl.chat_ps; g.B.rows = N; g.B.cols = TD; g.B.ld = TD;
-    g.planes = 3; g.M = static_cast<int>(NM); g.N = static_cast<int>(pl.Np); g.K = TD;
+    g.planes = 2; g.M = static_cast<int>(NM); g.N = static_cast<int>(pl.Np); g.K = TD;
     g.epi.flags = EPI_OUT_F32;
     g.epi.out = fp(pl.s); g.epi.out_ld = pl.Np;
     SPK_TRY(gemm_run(g, st));
@@ -261,6 +262,7 @@ int ge2e_tc(const float* E, int N, int M, const float* w, const float* b, float*
       g.b_mn = true;
       g.planes = 2; g.M = static_cast<int>(NM); g.N = TD; g.K = N;
       g.epi.flags = EPI_OUT_F32;
+      g.epi.alpha = 1.f / static_cast<float>(NM);
       g.epi.out = fp(pl.dehat); g.epi.out_ld = TD;
       SPK_TRY(gemm_run(g, st));
     }
@@ -277,6 +279,7 @@ int ge2e_tc(const float* E, int N, int M, const float* w, const float* b, float*
       int ks = (2 * device_sm_count() + tiles - 1) / tiles;
       g.ksplit = ks > kb ? kb : (ks < 1 ? 1 : ks);
       g.epi.flags = EPI_OUT_ATOMIC;
+      g.epi.alpha = 1.f / static_cast<float>(NM);
       g.epi.out = fp(pl.dchat); g.epi.out_ld = TD;
       SPK_TRY(gemm_run(g, st));
     }

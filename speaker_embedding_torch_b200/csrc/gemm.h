@@ -36,6 +36,8 @@ enum : uint32_t {
 struct GemmEpilogue {
   uint32_t flags = 0;
   float alpha = 1.f;             // v = alpha * acc first
+  const float* alpha_ptr = nullptr;   // optional device scalar multiplied into alpha (the backward pass's 1 / gradient scale)
+  const float* colsum_scale_ptr = nullptr;   // optional device scalar applied to the fused column sums
   const float* bias = nullptr;   // [N] fp32
   const float* pe_t = nullptr;   // [pe_T, N] fp32
   const float* pe_alpha = nullptr;

@@ -91,7 +91,7 @@ __device__ __forceinline__ CoopIO make_coop(int lane, int64_t boff, int64_t row0
 // All planes' global loads are issued before the first wait so up to 12 x 16 B per lane are in flight.
 __device__ __forceinline__ void load_aux_tile(uint32_t stage, int lane, const void* base_v, int64_t ps, int planes,
                                               const CoopIO& io, int col0, int N, float (&r)[32]) {
-  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(base_v) + io.off0 + col0;
+  const elem_t* base = reinterpret_cast<const elem_t*>(base_v) + io.off0 + col0;
   const bool col_ok = col0 + (lane & 3) * 8 < N;
 #pragma unroll
   for (int i = 0; i < 32; ++i) r[i] = 0.f;
@@ -130,8 +130,8 @@ __device__ __forceinline__ void load_aux_tile(uint32_t stage, int lane, const vo
             const uint32_t ww[4] = {w0, w1, w2, w3};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              r[cc * 8 + 2 * i] += bf16lo_to_f(ww[i]);
-              r[cc * 8 + 2 * i + 1] += bf16hi_to_f(ww[i]);
+              r[cc * 8 + 2 * i] += lo_to_f(ww[i]);
+              r[cc * 8 + 2 * i + 1] += hi_to_f(ww[i]);
             }
           }
           __syncwarp();
@@ -156,7 +156,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // waited for the previous one to release its operands).
 __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void* base_v, int64_t ps, int planes,
                                                  const CoopIO& io, int col0, int N, float (&v)[32]) {
-  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(base_v) + io.off0 + col0;
+  elem_t* base = reinterpret_cast<elem_t*>(base_v) + io.off0 + col0;
   const bool col_ok = col0 + (lane & 3) * 8 < N;
   const uint32_t own = stage + lane * 64, sw = ((lane >> 1) & 3) << 4;   // own + ((cc << 4) ^ sw) == stage_off(lane, cc)
   const uint32_t coop = stage + stage_off(lane >> 2, lane & 3);          // + it * 512: the swizzle term does not depend on it
@@ -165,8 +165,7 @@ __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void*
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      __nv_bfloat162 q = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&q);
+      w[i] = pack2(v[2 * i], v[2 * i + 1]);
     }
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) sts128(own + ((cc << 4) ^ sw), w[4 * cc], w[4 * cc + 1], w[4 * cc + 2], w[4 * cc + 3]);
@@ -177,8 +176,8 @@ __device__ __forceinline__ void store_split_tile(uint32_t stage, int lane, void*
     if (more) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        v[2 * i] -= bf16lo_to_f(w[i]);
-        v[2 * i + 1] -= bf16hi_to_f(w[i]);
+        v[2 * i] -= lo_to_f(w[i]);
+        v[2 * i + 1] -= hi_to_f(w[i]);
       }
     }
 #pragma unroll
@@ -244,7 +243,7 @@ __device__ __forceinline__ void store_f32_tile(uint32_t stage, int lane, float* 
 
 // colsum[col0 + c] += sum over the warp's 32 rows of v[.][c]   (bias gradients, fused)
 __device__ __forceinline__ void colsum_tile(uint32_t stage, int lane, float* colsum, int col0, int N,
-                                            const float (&v)[32]) {
+                                            const float (&v)[32], float scale) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -260,7 +259,7 @@ __device__ __forceinline__ void colsum_tile(uint32_t stage, int lane, float* col
       sacc += x;
     }
     sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
-    if (rh == 0 && col0 + h * 16 + cl < N) atomicAdd(colsum + col0 + h * 16 + cl, sacc);
+    if (rh == 0 && col0 + h * 16 + cl < N) atomicAdd(colsum + col0 + h * 16 + cl, sacc * scale);
     __syncwarp();
   }
 }
@@ -271,14 +270,15 @@ template <uint32_t CT>
 __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage, uint32_t bias_s, int lane, int M, int N,
                                            int64_t row0, int64_t batch, int64_t out_boff, const CoopIO& io_out,
                                            const CoopIO& io_res, const CoopIO& io_gate, int64_t cs_boff, int col0,
-                                           const uint32_t (&acc)[32], float pe_alpha, uint32_t gate_word) {
+                                           const uint32_t (&acc)[32], float pe_alpha, uint32_t gate_word, float alpha,
+                                           float cs_scale) {
   const uint32_t f = e.flags & CT;
   const int64_t row = row0 + lane;
   const bool row_ok = row < M;
   float v[32];
-  if (e.alpha != 1.f) {
+  if (alpha != 1.f) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = e.alpha * __uint_as_float(acc[i]);
+    for (int i = 0; i < 32; ++i) v[i] = alpha * __uint_as_float(acc[i]);
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
@@ -360,7 +360,7 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = 0.f;
     }
-    colsum_tile(stage, lane, e.colsum + cs_boff, col0, N, v);
+    colsum_tile(stage, lane, e.colsum + cs_boff, col0, N, v, cs_scale);
   }
   if (f & EPI_OUT_ATOMIC) {
     store_f32_tile<true>(stage, lane, reinterpret_cast<float*>(e.out), e.out_ld, out_boff, row0, col0, M, N, v);
@@ -376,7 +376,8 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
 template <uint32_t CT, int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t stage_buf, uint32_t bias_buf, int lane, int cgroup,
                                               uint32_t t_row, int M, int N, int64_t row0, int64_t batch, int64_t out_boff,
-                                              int64_t res_boff, int64_t cs_boff, int tn, float pe_alpha) {
+                                              int64_t res_boff, int64_t cs_boff, int tn, float pe_alpha, float alpha,
+                                              float cs_scale) {
   const CoopIO io_out = make_coop(lane, out_boff, row0, e.out_ld, M, (e.flags & EPI_OUT_F32) ? 4 : 8);
   CoopIO io_res = io_out, io_gate = io_out;
   if constexpr ((CT & (EPI_RES | EPI_ACC_GATES_AUX)) != 0) {
@@ -401,7 +402,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t st
     if (use_bits && cn < BLOCK_N / 32 && tn * BLOCK_N + cn * 32 < N) next_word = __ldg(bits_row + static_cast<int64_t>(cn) * M);
     tmem_ld_wait();
     epilogue32<CT>(e, stage_buf, bias_buf + (c >> 1) * 128, lane, M, N, row0, batch, out_boff, io_out, io_res, io_gate,
-                   cs_boff, col0, r, pe_alpha, word);
+                   cs_boff, col0, r, pe_alpha, word, alpha, cs_scale);
   }
 }
 
@@ -410,7 +411,7 @@ template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
 __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(const __grid_constant__ GemmKernelArgs args) {
   using Cfg = TileCfg<PLANES, BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+  constexpr uint32_t IDESC = umma_idesc_f16(BLOCK_M, BLOCK_N, A_MN, B_MN);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
                                          : umma_smem_desc(a_base + k * (UMMA_K * 2), 16, 1024);
                 const uint64_t db = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                          : umma_smem_desc(b_base + k * (UMMA_K * 2), 16, 1024);
-                umma_bf16(d_tmem, da, db, IDESC, accumulate);
+                umma_f16(d_tmem, da, db, IDESC, accumulate);
                 accumulate = 1;
               }
             }
@@ -555,6 +556,8 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
     const int cgroup = (warp - 4) >> 2;    // this warp handles the 32-column chunks with (c & 1) == cgroup
     const GemmEpilogue& e = args.epi;
     const float pe_alpha = (e.flags & EPI_PE) ? __ldg(e.pe_alpha) : 0.f;
+    const float alpha = e.alpha * (e.alpha_ptr != nullptr ? __ldg(e.alpha_ptr) : 1.f);
+    const float cs_scale = e.colsum_scale_ptr != nullptr ? __ldg(e.colsum_scale_ptr) : 1.f;
     const uint32_t stage_buf = epi_stage_base + (warp - 4) * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
     const uint32_t bias_buf = stage_buf + EPI_STAGE_BYTES;
     int it = 0;
@@ -589,16 +592,16 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
         constexpr uint32_t CT_BWD = EPI_GATE_BITS | EPI_COLSUM | EPI_RES | EPI_OUT_F32;   // data gradients
         if ((e.flags & ~CT_LEAN) == 0)
           epilogue_tile<CT_LEAN, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
-                                          cs_boff, tn, pe_alpha);
+                                          cs_boff, tn, pe_alpha, alpha, cs_scale);
         else if ((e.flags & ~CT_FWD) == 0)
           epilogue_tile<CT_FWD, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
-                                         cs_boff, tn, pe_alpha);
+                                         cs_boff, tn, pe_alpha, alpha, cs_scale);
         else if (PLANES >= 2 && (e.flags & ~CT_BWD) == 0)
           epilogue_tile<(PLANES >= 2 ? CT_BWD : 0xFFFFFFFFu), BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0,
-                                                                       t, out_boff, res_boff, cs_boff, tn, pe_alpha);
+                                                                       t, out_boff, res_boff, cs_boff, tn, pe_alpha, alpha, cs_scale);
         else
           epilogue_tile<0xFFFFFFFFu, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff,
-                                              res_boff, cs_boff, tn, pe_alpha);
+                                              res_boff, cs_boff, tn, pe_alpha, alpha, cs_scale);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -646,7 +649,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
   using Cfg = PairCfg<PLANES, BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int HALF_N = BLOCK_N / 2;
-  constexpr uint32_t IDESC = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N, false, B_MN);
+  constexpr uint32_t IDESC = umma_idesc_f16(2 * BLOCK_M, BLOCK_N, false, B_MN);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -776,7 +779,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
                   const uint64_t da = umma_smem_desc(a_base + k * (UMMA_K * 2), 16, 1024);
                   const uint64_t db = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                            : umma_smem_desc(b_base + k * (UMMA_K * 2), 16, 1024);
-                  umma_bf16_pair(d_tmem, da, db, IDESC, accumulate);
+                  umma_f16_pair(d_tmem, da, db, IDESC, accumulate);
                   accumulate = 1;
                 }
               }
@@ -806,6 +809,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
     const int cgroup = (warp - 4) >> 2;
     const GemmEpilogue& e = args.epi;
     const float pe_alpha = (e.flags & EPI_PE) ? __ldg(e.pe_alpha) : 0.f;
+    const float alpha = e.alpha * (e.alpha_ptr != nullptr ? __ldg(e.alpha_ptr) : 1.f);
+    const float cs_scale = e.colsum_scale_ptr != nullptr ? __ldg(e.colsum_scale_ptr) : 1.f;
     const uint32_t stage_buf = epi_stage_base + (warp - 4) * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
     const uint32_t bias_buf = stage_buf + EPI_STAGE_BYTES;
     int it = 0;
@@ -839,16 +844,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
         constexpr uint32_t CT_BWD = EPI_GATE_BITS | EPI_COLSUM | EPI_RES | EPI_OUT_F32;   // data gradients
         if ((e.flags & ~CT_LEAN) == 0)
           epilogue_tile<CT_LEAN, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
-                                          cs_boff, tn, pe_alpha);
+                                          cs_boff, tn, pe_alpha, alpha, cs_scale);
         else if ((e.flags & ~CT_FWD) == 0)
           epilogue_tile<CT_FWD, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff, res_boff,
-                                         cs_boff, tn, pe_alpha);
+                                         cs_boff, tn, pe_alpha, alpha, cs_scale);
         else if (PLANES >= 2 && (e.flags & ~CT_BWD) == 0)
           epilogue_tile<(PLANES >= 2 ? CT_BWD : 0xFFFFFFFFu), BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0,
-                                                                       t, out_boff, res_boff, cs_boff, tn, pe_alpha);
+                                                                       t, out_boff, res_boff, cs_boff, tn, pe_alpha, alpha, cs_scale);
         else
           epilogue_tile<0xFFFFFFFFu, BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, t_row, args.M, args.N, row0, t, out_boff,
-                                              res_boff, cs_boff, tn, pe_alpha);
+                                              res_boff, cs_boff, tn, pe_alpha, alpha, cs_scale);
       }
       tc_fence_before();
       mbar_arrive(tlocal_bar(acc));
@@ -915,7 +920,7 @@ static int make_map(CUtensorMap* map, const SplitMat& m, int plane, int nb0, int
   cuuint64_t strides[3] = {(cuuint64_t)(m.ld * 2), (cuuint64_t)(s0 * 2), (cuuint64_t)(s1 * 2)};
   cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SPK_CHECK(r == CUDA_SUCCESS,
@@ -934,7 +939,7 @@ int encode_map_4d(CUtensorMap* map, const void* base, const int64_t dims[4], con
   SPK_CHECK(st[0] % 16 == 0 && st[1] % 16 == 0 && st[2] % 16 == 0, "tensor map strides must be multiples of 16 bytes");
   cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, st, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), d, st, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SPK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);

@@ -9,7 +9,7 @@ namespace spk {
 
 // ------------------------------------------------------------------------------------------------
 // fp32 weights -> split-bf16 planes, all matrices in one launch.
-__global__ void pack_weights_kernel(const __grid_constant__ PackTable tab, __nv_bfloat16* dst, int64_t plane_stride,
+__global__ void pack_weights_kernel(const __grid_constant__ PackTable tab, elem_t* dst, int64_t plane_stride,
                                     int planes) {
   for (int s = 0; s < tab.count; ++s) {
     const float* src = tab.seg[s].src;
@@ -20,7 +20,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackTable tab, __nv_
 }
 int pack_weights(const PackTable& tab, void* dst, int64_t plane_stride, int planes, cudaStream_t st) {
   ProfScope prof("pack_weights", 0, 0, st);
-  pack_weights_kernel<<<296, 256, 0, st>>>(tab, reinterpret_cast<__nv_bfloat16*>(dst), plane_stride, planes);
+  pack_weights_kernel<<<296, 256, 0, st>>>(tab, reinterpret_cast<elem_t*>(dst), plane_stride, planes);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -30,7 +30,7 @@ int pack_weights(const PackTable& tab, void* dst, int64_t plane_stride, int plan
 // [ (b % spw) * hop, + T ) of a [windows, C, L] tensor in fp32 or fp16 (frames contiguous): the overlapping-slice
 // collation and the fp16 -> fp32 upcast of the reference's inference collater happen in this load.
 template <int C, typename TIn>
-__global__ void mel_pack_kernel(const TIn* __restrict__ mel, __nv_bfloat16* __restrict__ out, int64_t plane_stride,
+__global__ void mel_pack_kernel(const TIn* __restrict__ mel, elem_t* __restrict__ out, int64_t plane_stride,
                                 int planes, int T, int L, int hop, int spw) {
   __shared__ float tile[C][33];
   const int b = blockIdx.y;
@@ -62,7 +62,7 @@ int mel_pack(const spk_mel_view& mel, void* out, int64_t plane_stride, int plane
             "mel view: %d slices of %d frames at hop %d do not fit a %d-frame window", mel.slices_per_window, T, mel.hop,
             mel.window_frames);
   dim3 grid((T + 31) / 32, B);
-  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  auto* o = reinterpret_cast<elem_t*>(out);
   if (mel.dtype == 0)
     mel_pack_kernel<80, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(mel.data), o, plane_stride, planes, T,
                                                      mel.window_frames, mel.hop, mel.slices_per_window);
@@ -80,7 +80,7 @@ int mel_pack(const spk_mel_view& mel, void* out, int64_t plane_stride, int plane
 // load that packs the token-major operand planes.  Host-side padded / cropped copies never exist.
 template <int C, typename TIn>
 __global__ void mel_pack_ragged_kernel(const TIn* __restrict__ mel, const int32_t* __restrict__ table, int64_t total,
-                                       __nv_bfloat16* __restrict__ out, int64_t plane_stride, int planes, int T) {
+                                       elem_t* __restrict__ out, int64_t plane_stride, int planes, int T) {
   __shared__ float tile[C][33];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 32;
@@ -123,7 +123,7 @@ int mel_pack_ragged(const spk_mel_ragged& mel, void* out, int64_t plane_stride, 
   SPK_CHECK(mel.data != nullptr && mel.table != nullptr && (mel.dtype == 0 || mel.dtype == 1) && mel.total_frames > 0,
             "ragged mel: data / table missing or dtype not 0 (fp32) / 1 (fp16)");
   dim3 grid((T + 31) / 32, B);
-  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  auto* o = reinterpret_cast<elem_t*>(out);
   if (mel.dtype == 0)
     mel_pack_ragged_kernel<80, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(mel.data), mel.table,
                                                             mel.total_frames, o, plane_stride, planes, T);
@@ -159,9 +159,9 @@ int pe_transpose(const float* pe, float* pe_t, int D, int max_pos, int T, cudaSt
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over D = 256, one warp per row.
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ z, int64_t z_ps, int z_planes,
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const elem_t* __restrict__ z, int64_t z_ps, int z_planes,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                     __nv_bfloat16* __restrict__ y, int64_t y_ps, int y_planes,
+                                                     elem_t* __restrict__ y, int64_t y_ps, int y_planes,
                                                      float2* __restrict__ stats, int64_t rows, int64_t row_stride_rows,
                                                      float eps) {
   const int lane = threadIdx.x & 31;
@@ -192,8 +192,8 @@ int ln_fwd(const void* z, int64_t z_ps, int z_planes, int64_t z_row_step, const 
            void* y, int64_t y_ps, int y_planes, float* stats, int64_t rows, cudaStream_t st) {
   ProfScope prof("ln_fwd", 0, 512.0 * rows * (z_planes + y_planes), st);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
-  ln_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(z), z_ps, z_planes, gamma, beta,
-                                        reinterpret_cast<__nv_bfloat16*>(y), y_ps, y_planes,
+  ln_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const elem_t*>(z), z_ps, z_planes, gamma, beta,
+                                        reinterpret_cast<elem_t*>(y), y_ps, y_planes,
                                         reinterpret_cast<float2*>(stats), rows, z_row_step, 1e-5f);
   SPK_CUDA(cudaGetLastError());
   return 0;
@@ -201,13 +201,14 @@ int ln_fwd(const void* z, int64_t z_ps, int z_planes, int64_t z_row_step, const 
 
 // dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma ; dgamma += dy * xhat ; dbeta += dy
 // Optionally also writes dz_drop = dz * keep(site) (the gradient that enters the sub-layer's GEMMs).
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_ps, int dy_planes,
-                                                     const __nv_bfloat16* __restrict__ z, int64_t z_ps, int z_planes,
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const elem_t* __restrict__ dy, int64_t dy_ps, int dy_planes,
+                                                     const elem_t* __restrict__ z, int64_t z_ps, int z_planes,
                                                      const float2* __restrict__ stats, const float* __restrict__ gamma,
-                                                     __nv_bfloat16* __restrict__ dz, int64_t dz_ps, int dz_planes,
-                                                     __nv_bfloat16* __restrict__ dz_drop, DropCfg drop, uint32_t site,
+                                                     elem_t* __restrict__ dz, int64_t dz_ps, int dz_planes,
+                                                     elem_t* __restrict__ dz_drop, DropCfg drop, uint32_t site,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                     float* __restrict__ dbias, int64_t rows) {
+                                                     float* __restrict__ dbias, int64_t rows,
+                                                     const float* __restrict__ gscale) {
   __shared__ float red[3][8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
       if (p < planes) {
         const uint32_t w[4] = {raw[p].x, raw[p].y, raw[p].z, raw[p].w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { v[2 * i] += bf16lo_to_f(w[i]); v[2 * i + 1] += bf16hi_to_f(w[i]); }
+        for (int i = 0; i < 4; ++i) { v[2 * i] += lo_to_f(w[i]); v[2 * i + 1] += hi_to_f(w[i]); }
       }
     }
   };
@@ -281,21 +282,22 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
   float sg = 0.f, sb = 0.f, sz = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) { sg += red[0][w][threadIdx.x]; sb += red[1][w][threadIdx.x]; sz += red[2][w][threadIdx.x]; }
-  atomicAdd(dgamma + threadIdx.x, sg);
-  atomicAdd(dbeta + threadIdx.x, sb);
-  if (dbias != nullptr) atomicAdd(dbias + threadIdx.x, sz);
+  const float inv_s = gscale != nullptr ? __ldg(gscale + 1) : 1.f;     // the gradients arrive scaled by gscale[0]
+  atomicAdd(dgamma + threadIdx.x, sg * inv_s);
+  atomicAdd(dbeta + threadIdx.x, sb * inv_s);
+  if (dbias != nullptr) atomicAdd(dbias + threadIdx.x, sz * inv_s);
 }
 int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t z_ps, int z_planes, const float* stats,
            const float* gamma, void* dz, int64_t dz_ps, int dz_planes, void* dz_drop, DropCfg drop, uint32_t site,
-           float* dgamma, float* dbeta, float* dbias, int64_t rows, cudaStream_t st) {
+           float* dgamma, float* dbeta, float* dbias, int64_t rows, const float* gscale, cudaStream_t st) {
   ProfScope prof("ln_bwd", 0, 512.0 * rows * (dy_planes + z_planes + dz_planes * (drop.thresh ? 2 : 1)), st);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 6));
-  ln_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ps, dy_planes,
-                                        reinterpret_cast<const __nv_bfloat16*>(z), z_ps, z_planes,
+  ln_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const elem_t*>(dy), dy_ps, dy_planes,
+                                        reinterpret_cast<const elem_t*>(z), z_ps, z_planes,
                                         reinterpret_cast<const float2*>(stats), gamma,
-                                        reinterpret_cast<__nv_bfloat16*>(dz), dz_ps, dz_planes,
-                                        (drop.thresh != 0) ? reinterpret_cast<__nv_bfloat16*>(dz_drop) : nullptr, drop,
-                                        site, dgamma, dbeta, dbias, rows);
+                                        reinterpret_cast<elem_t*>(dz), dz_ps, dz_planes,
+                                        (drop.thresh != 0) ? reinterpret_cast<elem_t*>(dz_drop) : nullptr, drop,
+                                        site, dgamma, dbeta, dbias, rows, gscale);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -304,9 +306,9 @@ int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t 
 // Row softmax over the first T of Tp columns (Tp % 8 == 0, Tp <= 1024); one warp per row.
 // Writes P (and P_drop = P * keep / (1-p) when dropout is on); pad columns are written as zeros.
 template <int CH>
-__global__ void __launch_bounds__(256) softmax_fwd_kernel(const __nv_bfloat16* __restrict__ s,
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const elem_t* __restrict__ s,
                                                           const float* __restrict__ s_f32, int64_t ps, int planes,
-                                                          __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ p_drop,
+                                                          elem_t* __restrict__ p, elem_t* __restrict__ p_drop,
                                                           DropCfg drop, uint32_t site, int64_t rows, int T, int Tp) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -386,9 +388,9 @@ int softmax_fwd(const void* s, const float* s_f32, int64_t ps, int planes, void*
   SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
   const int ch = (Tp + 255) / 256;
-  auto* sp = reinterpret_cast<const __nv_bfloat16*>(s);
-  auto* pp = reinterpret_cast<__nv_bfloat16*>(p);
-  auto* pdp = drop.thresh != 0 ? reinterpret_cast<__nv_bfloat16*>(p_drop) : nullptr;
+  auto* sp = reinterpret_cast<const elem_t*>(s);
+  auto* pp = reinterpret_cast<elem_t*>(p);
+  auto* pdp = drop.thresh != 0 ? reinterpret_cast<elem_t*>(p_drop) : nullptr;
   switch (ch) {
     case 1: softmax_fwd_kernel<1><<<blocks, 256, 0, st>>>(sp, s_f32, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
     case 2: softmax_fwd_kernel<2><<<blocks, 256, 0, st>>>(sp, s_f32, ps, planes, pp, pdp, drop, site, rows, T, Tp); break;
@@ -402,9 +404,9 @@ int softmax_fwd(const void* s, const float* s_f32, int64_t ps, int planes, void*
 // dS = scale * P * (dP' - sum_k dP'_k P_k),  dP' = dP_drop * keep/(1-p)
 // dp and ds may alias (in-place): a warp reads its whole row before writing it, so no __restrict__ here.
 template <int CH>
-__global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p,
-                                                          const __nv_bfloat16* dp, const float* dp_f32, int64_t ps,
-                                                          int planes, __nv_bfloat16* ds, DropCfg drop, uint32_t site,
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const elem_t* __restrict__ p,
+                                                          const elem_t* dp, const float* dp_f32, int64_t ps,
+                                                          int planes, elem_t* ds, DropCfg drop, uint32_t site,
                                                           float scale, int64_t rows, int T, int Tp) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
             if (q < planes) {
               const uint32_t w[4] = {np[q].x, np[q].y, np[q].z, np[q].w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { pv[c][2 * i] += bf16lo_to_f(w[i]); pv[c][2 * i + 1] += bf16hi_to_f(w[i]); }
+              for (int i = 0; i < 4; ++i) { pv[c][2 * i] += lo_to_f(w[i]); pv[c][2 * i + 1] += hi_to_f(w[i]); }
             }
           }
           dv[c][0] = n0.x; dv[c][1] = n0.y; dv[c][2] = n0.z; dv[c][3] = n0.w;
@@ -486,9 +488,9 @@ int softmax_bwd(const void* p, const void* dp, const float* dp_f32, int64_t ps, 
   SPK_CHECK(Tp % 8 == 0 && Tp <= 1024 && T <= Tp, "softmax: bad row length T=%d Tp=%d", T, Tp);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
   const int ch = (Tp + 255) / 256;
-  auto* pp = reinterpret_cast<const __nv_bfloat16*>(p);
-  auto* dpp = reinterpret_cast<const __nv_bfloat16*>(dp);
-  auto* dsp = reinterpret_cast<__nv_bfloat16*>(ds);
+  auto* pp = reinterpret_cast<const elem_t*>(p);
+  auto* dpp = reinterpret_cast<const elem_t*>(dp);
+  auto* dsp = reinterpret_cast<elem_t*>(ds);
   switch (ch) {
     case 1: softmax_bwd_kernel<1><<<blocks, 256, 0, st>>>(pp, dpp, dp_f32, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
     case 2: softmax_bwd_kernel<2><<<blocks, 256, 0, st>>>(pp, dpp, dp_f32, ps, planes, dsp, drop, site, scale, rows, T, Tp); break;
@@ -523,7 +525,7 @@ int dropout_keep(uint64_t seed, float p, uint32_t site, uint64_t idx8_begin, int
 
 // ------------------------------------------------------------------------------------------------
 // out[c] += sum_r x[r, c]   (bias gradients).  C % 8 == 0, C <= 1024.
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ps, int planes,
+__global__ void __launch_bounds__(256) colsum_kernel(const elem_t* __restrict__ x, int64_t ps, int planes,
                                                      float* __restrict__ out, int64_t rows, int C, int rows_per_block) {
   const int groups = C / 8;
   const int lanes_r = 256 / groups > 0 ? 256 / groups : 1;   // row lanes per block
@@ -546,15 +548,16 @@ int colsum(const void* x, int64_t ps, int planes, float* out, int64_t rows, int 
   SPK_CHECK(C % 8 == 0 && C / 8 <= 256, "colsum: C=%d unsupported", C);
   const int rpb = 512;
   const int blocks = static_cast<int>((rows + rpb - 1) / rpb);
-  colsum_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ps, planes, out, rows, C, rpb);
+  colsum_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const elem_t*>(x), ps, planes, out, rows, C, rpb);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
 
 // d_alpha += sum over tokens/channels of dH0 * keep(site 0) * pe_t[t]
-__global__ void __launch_bounds__(256) pe_alpha_grad_kernel(const __nv_bfloat16* __restrict__ dh, int64_t ps, int planes,
+__global__ void __launch_bounds__(256) pe_alpha_grad_kernel(const elem_t* __restrict__ dh, int64_t ps, int planes,
                                                             const float* __restrict__ pe_t, DropCfg drop, uint32_t site,
-                                                            float* __restrict__ dalpha, int64_t rows, int T) {
+                                                            float* __restrict__ dalpha, int64_t rows, int T,
+                                                            const float* __restrict__ gscale) {
   __shared__ float red[8];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -580,15 +583,15 @@ __global__ void __launch_bounds__(256) pe_alpha_grad_kernel(const __nv_bfloat16*
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += red[w];
-    atomicAdd(dalpha, s);
+    atomicAdd(dalpha, s * (gscale != nullptr ? __ldg(gscale + 1) : 1.f));
   }
 }
 int pe_alpha_grad(const void* dh, int64_t ps, int planes, const float* pe_t, DropCfg drop, uint32_t site, float* dalpha,
-                  int64_t rows, int T, cudaStream_t st) {
+                  int64_t rows, int T, const float* gscale, cudaStream_t st) {
   ProfScope prof("pe_alpha_grad", 0, 512.0 * rows * planes, st);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 4));
-  pe_alpha_grad_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dh), ps, planes, pe_t, drop, site,
-                                               dalpha, rows, T);
+  pe_alpha_grad_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const elem_t*>(dh), ps, planes, pe_t, drop, site,
+                                               dalpha, rows, T, gscale);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -29,7 +29,7 @@ int ln_fwd(const void* z, int64_t z_ps, int z_planes, int64_t z_row_step, const 
            void* y, int64_t y_ps, int y_planes, float* stats, int64_t rows, cudaStream_t st);
 int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t z_ps, int z_planes, const float* stats,
            const float* gamma, void* dz, int64_t dz_ps, int dz_planes, void* dz_drop, DropCfg drop, uint32_t site,
-           float* dgamma, float* dbeta, float* dbias, int64_t rows, cudaStream_t st);
+           float* dgamma, float* dbeta, float* dbias, int64_t rows, const float* gscale, cudaStream_t st);
 
 // scores / dP come either as split planes (s / dp) or as plain fp32 (s_f32 / dp_f32 != nullptr)
 int softmax_fwd(const void* s, const float* s_f32, int64_t ps, int planes, void* p, void* p_drop, DropCfg drop,
@@ -40,6 +40,6 @@ int softmax_bwd(const void* p, const void* dp, const float* dp_f32, int64_t ps, 
 int dropout_keep(uint64_t seed, float p, uint32_t site, uint64_t idx8_begin, int64_t n8, float* out, cudaStream_t st);
 int colsum(const void* x, int64_t ps, int planes, float* out, int64_t rows, int C, cudaStream_t st);
 int pe_alpha_grad(const void* dh, int64_t ps, int planes, const float* pe_t, DropCfg drop, uint32_t site, float* dalpha,
-                  int64_t rows, int T, cudaStream_t st);
+                  int64_t rows, int T, const float* gscale, cudaStream_t st);
 
 }  // namespace spk

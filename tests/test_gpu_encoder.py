@@ -329,7 +329,11 @@ def test_fused_training_attention_matches_materialised_path(frames, train):
         _native.set_option("fused_training_attention", 1)
     torch.testing.assert_close(res[1][0], res[0][0], atol=3e-6, rtol=0)
     rel = float((res[1][1] - res[0][1]).double().norm() / res[0][1].double().norm())
-    assert rel <= 5e-4, rel           # two approximations of the same gradient; each is held to 1e-3 against the oracle
+    # Two approximations of the same gradient, each held to 1e-3 against the oracle.  Typical agreement is ~3e-5; the
+    # bound leaves room for ONE ReLU gate whose pre-activation lies within the forward rounding error of zero and that
+    # opens in one path only -- at 6 x T x 1024 gates such an element alone moves the gradient by ~1e-3 (the
+    # unmodified reference in fp32 shows the same against its fp64 run: tools/full_parity_probe.py flips).
+    assert rel <= 2e-3, rel
 
 
 def test_fused_training_attention_falls_back_beyond_its_frame_limit():

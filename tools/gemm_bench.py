@@ -12,8 +12,8 @@ from speaker_embedding_torch_b200 import _native as N  # noqa: E402
 
 def run(planes, m, n, k, a_mn=False, b_mn=False, out_f32=False, ksplit=1, block_n=0, bias_relu=False, iters=10):
     dev = "cuda"
-    a = torch.randn((planes, k, m) if a_mn else (planes, m, k), device=dev).to(torch.bfloat16)
-    b = torch.randn((planes, k, n) if b_mn else (planes, n, k), device=dev).to(torch.bfloat16)
+    a = torch.randn((planes, k, m) if a_mn else (planes, m, k), device=dev).to(torch.float16)
+    b = torch.randn((planes, k, n) if b_mn else (planes, n, k), device=dev).to(torch.float16)
     bias = torch.randn(n, device=dev) if bias_relu else None
     atomic = torch.zeros(m, n, device=dev) if ksplit > 1 else None
     for _ in range(3):

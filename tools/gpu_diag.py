@@ -157,6 +157,8 @@ def enc_stage_case(Nspk, M, T, layers=1, precision=3):
     from speaker_embedding_torch_b200.Arg_Parser import default_hyper_parameters
     hp = default_hyper_parameters()
     hp.GE2E.Transformer.Num_Layers = layers
+    N.set_option("prune_last_layer", 0)           # the stage buffers of the last layer are full-size only then
+    N.set_option("fused_training_attention", int(os.environ.get("SPK_DIAG_FUSED", "0")))
     full = synth.make_state(33)
     m = GE2E(hp)
     sd = {k: torch.as_tensor(v) for k, v in full.items() if k in m.state_dict()}
@@ -208,9 +210,11 @@ def enc_stage_case(Nspk, M, T, layers=1, precision=3):
     lref = O.ge2e_loss(dv, M, 10.0, -5.0)
     lref.backward()
 
-    def rel(a, b):
+    def rel(a, b, fit=False):
         a = a.double().cpu().reshape(-1)
         b = b.detach().double().reshape(-1)
+        if fit:     # backward stage buffers are carried at the pass's power-of-two gradient scale: fit it out
+            a = a * (2.0 ** torch.round(torch.log2((a @ b) / (a @ a))))
         return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
 
     def rd(name, rows, cols):
@@ -228,13 +232,26 @@ def enc_stage_case(Nspk, M, T, layers=1, precision=3):
     # backward buffers hold the values of the LAST processed layer (layer 0)
     ds_mine = rd("ds", B * H * T, Tp).view(B, H, T, Tp)[..., :T]
     print("bwd(layer0) dS %.2e dqkv %.2e datt %.2e dZ1 %.2e dU %.2e dH0 %.2e du0 %.2e" % (
-        rel(ds_mine, inter["sraw0"].grad), rel(rd("dqkv", Mt, 3 * D), inter["qkv0"].grad),
-        rel(rd("datt", Mt, D), inter["att0"].grad), rel(rd("dz", Mt, D), inter["z10"].grad),
-        rel(rd("df", Mt, 4 * D), inter["u0"].grad),
-        rel(rd("dh_a", Mt, D), inter["h0"].grad), rel(rd("dh_b", Mt, D), inter["upre"].grad)))
+        rel(ds_mine, inter["sraw0"].grad, True), rel(rd("dqkv", Mt, 3 * D), inter["qkv0"].grad, True),
+        rel(rd("datt", Mt, D), inter["att0"].grad, True), rel(rd("dz", Mt, D), inter["z10"].grad, True),
+        rel(rd("df", Mt, 4 * D), inter["u0"].grad, True),
+        rel(rd("dh_a", Mt, D), inter["h0"].grad, True), rel(rd("dh_b", Mt, D), inter["upre"].grad, True)))
+    # local check of one backward GEMM on this run's own operands: dATT = dZ1 Wo (K = 256, dense rows)
+    dz_mine = rd("dz", Mt, D).double().cpu()
+    datt_mine = rd("datt", Mt, D).double().cpu()
+    wo = sd["transformer.layers.0.self_attn.out_proj.weight"].double()
+    chk = dz_mine @ wo
+    print("   local: dATT vs fp64(dZ1_mine @ Wo) %.2e   (both at the pass's scale)" % (
+        ((datt_mine - chk).norm() / chk.norm()).item()))
+    df_mine = rd("df", Mt, 4 * D).double().cpu()
+    print("   local magnitudes: |dZ1| max %.3e rms %.3e   |dU| max %.3e rms %.3e  frac(|dU|<0.125, nonzero) %.3f" % (
+        dz_mine.abs().max(), dz_mine.pow(2).mean().sqrt(), df_mine.abs().max(), df_mine.pow(2).mean().sqrt(),
+        float(((df_mine.abs() < 0.125) & (df_mine != 0)).double().sum() / max(1.0, float((df_mine != 0).sum())))))
+
     def dist(name, mine, ref):
         mine = mine.double().cpu().reshape(ref.shape)
         ref = ref.detach().double()
+        mine = mine * (2.0 ** torch.round(torch.log2((mine * ref).sum() / (mine * mine).sum())))
         err = (mine - ref).abs()
         mx = ref.abs().max().item()
         big = err > 1e-3 * mx
@@ -256,7 +273,7 @@ def enc_stage_case(Nspk, M, T, layers=1, precision=3):
         i = "qkv".index(sub)
         a = rd("dqkv", Mt, 3 * D)[:, i * D:(i + 1) * D]
         b = inter["qkv0"].grad.reshape(Mt, 3 * D)[:, i * D:(i + 1) * D]
-        print("   d%s %.2e" % (sub, rel(a, b)))
+        print("   d%s %.2e" % (sub, rel(a, b, True)))
     worst = 0.0
     for name, p_ in m.named_parameters():
         r = rel(p_.grad, st[name].grad)
@@ -302,6 +319,7 @@ CASES = {
     "enc_bwd_big_p2": lambda: enc_bwd_case(16, 5, 160, 2),
     "stage_t24": lambda: enc_stage_case(4, 3, 24),
     "stage_t160_l3": lambda: enc_stage_case(4, 3, 160, layers=3),
+    "stage_t160_l2": lambda: enc_stage_case(4, 3, 160, layers=2, precision=2),
     "enc_bwd_small": lambda: enc_bwd_case(3, 2, 24),
     "enc_bwd_mid": lambda: enc_bwd_case(4, 3, 160),
     "enc_bwd_t64": lambda: enc_bwd_case(2, 2, 64),

@@ -12,7 +12,7 @@ from speaker_embedding_torch_b200 import _native as N  # noqa: E402
 def split(x, planes):
     out, r = [], x.float()
     for _ in range(planes):
-        h = r.to(torch.bfloat16)
+        h = r.to(torch.float16)
         out.append(h)
         r = r - h.float()
     return torch.stack(out).contiguous()
