@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
   load8f(q0, q_ps, planes, static_cast<int64_t>(b) * 256 + h * 64 + d8 * 8, q);
   const int64_t kv_row0 = static_cast<int64_t>(b) * T * 512 + h * 64 + d8 * 8;
   // scores
-#pragma unroll 2
+#pragma unroll 4
   for (int t0 = 0; t0 < T; t0 += 4) {
     const int t = min(t0 + g, T - 1);
     float k[8];
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
   __syncwarp();
   // o = sum_t pd_t V_t : each key group accumulates its keys, then the four groups are combined
   float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
+#pragma unroll 4
   for (int t0 = 0; t0 < T; t0 += 4) {
     const int t = t0 + g;
     if (t < T) {
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
   const float* pd = pd0 + bh * Tp;
   // dV rows and dp_t = dO . V_t
   float pd_sum = 0.f;
-#pragma unroll 2
+#pragma unroll 4
   for (int t0 = 0; t0 < T; t0 += 4) {
     const int t = t0 + g;
     const int tc = min(t, T - 1);
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
   ds_sum = warp_sum(ds_sum);
   __syncwarp();
   float dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
+#pragma unroll 4
   for (int t0 = 0; t0 < T; t0 += 4) {
     const int t = t0 + g;
     if (t < T) {

@@ -52,6 +52,7 @@ struct Plan {
   int B, T, S, P, Tp, H, D, F, C, L;
   int64_t Mt, BH;
   bool keep, prune, fused_infer, fused_train;
+  size_t h0bits = 0;  // [256 / 32][Mt] words: prenet ReLU mask
   size_t gscale;      // backward: (S, 1 / S), the power-of-two scale the gradient planes are carried at
   bool attn_tr;       // the dense layers of this training plan use the fused attention kernels (attn_train.cu)
   size_t adelta;      // fused training attention backward: delta = rowsum(dO * O), [B*H*T] fp32
@@ -127,6 +128,7 @@ static int make_plan(const spk_encoder_config& c, int B, int T, int S, int Pflag
   pl.wpack = take_split(cur, w, P);
   pl.x0 = take_split(cur, Mt * pl.C, P);
   pl.h0 = take_split(cur, Mt * D, P);
+  pl.h0bits = keep ? take_f32(cur, Mt * (D / 32)) : 0;     // 1-bit ReLU mask of the prenet (backward)
   pl.pe_t = take_f32(cur, static_cast<int64_t>(T) * D);
   // fused training attention (scores never leave the SM): multi-plane training plans up to 192 frames
   pl.attn_tr = keep && pl.fused_train && P >= 2 && T <= 192 && T <= attn_train_max_frames(P) && pl.H == 4;
@@ -386,18 +388,34 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   atomicAdd(dbeta + tid, ab);
 }
 
-// dWp[n][k] += sum_u de[u][n] * emean[u][k] ; dbp[n] += sum_u de[u][n]     (block n, thread k)
+// dWp[n][k] += sum_u de[u][n] * emean[u][k] ; dbp[n] += sum_u de[u][n]     (block (n, chunk of u), thread k)
+// The u range is cut into gridDim.y chunks (four independent accumulators each) so the 2 x U dependent loads of the
+// first version (132 us at U = 960) become U / 32 rounds; partial sums meet in fp32 atomics.
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ de, const float* __restrict__ emean,
                                                          int64_t U, float* __restrict__ dwp, float* __restrict__ dbp) {
   const int n = blockIdx.x, k = threadIdx.x;
-  float acc = 0.f, accb = 0.f;
-  for (int64_t u = 0; u < U; ++u) {
-    const float d = __ldg(de + u * 256 + n);
-    acc = fmaf(d, __ldg(emean + u * 256 + k), acc);
-    accb += d;
+  const int64_t per = (U + gridDim.y - 1) / gridDim.y;
+  const int64_t u0 = blockIdx.y * per, u1 = (u0 + per < U) ? u0 + per : U;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  int64_t u = u0;
+  for (; u + 4 <= u1; u += 4) {
+    const float d0 = __ldg(de + u * 256 + n), d1 = __ldg(de + (u + 1) * 256 + n);
+    const float d2 = __ldg(de + (u + 2) * 256 + n), d3 = __ldg(de + (u + 3) * 256 + n);
+    a0 = fmaf(d0, __ldg(emean + u * 256 + k), a0);
+    a1 = fmaf(d1, __ldg(emean + (u + 1) * 256 + k), a1);
+    a2 = fmaf(d2, __ldg(emean + (u + 2) * 256 + k), a2);
+    a3 = fmaf(d3, __ldg(emean + (u + 3) * 256 + k), a3);
+    b0 += d0; b1 += d1; b2 += d2; b3 += d3;
   }
-  dwp[n * 256 + k] += acc;
-  if (k == 0) dbp[n] += accb;
+  for (; u < u1; ++u) {
+    const float d = __ldg(de + u * 256 + n);
+    a0 = fmaf(d, __ldg(emean + u * 256 + k), a0);
+    b0 += d;
+  }
+  if (u1 > u0) {
+    atomicAdd(dwp + n * 256 + k, (a0 + a1) + (a2 + a3));
+    if (k == 0) atomicAdd(dbp + n, (b0 + b1) + (b2 + b3));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -499,6 +517,10 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     g.B = c.mat(pl.wpack, pl.w_pre, D, pl.C, pl.C);
     g.planes = P; g.M = (int)Mt; g.N = (int)D; g.K = pl.C;
     g.epi.flags = EPI_BIAS | EPI_RELU | EPI_PE | (drop_pe.thresh ? EPI_DROPOUT : 0);
+    if (pl.keep && P >= 2) {   // the backward gates dH0 with the forward's own ReLU decisions
+      g.epi.flags |= EPI_EMIT_BITS;
+      g.epi.gate_bits = reinterpret_cast<uint32_t*>(c.f32(pl.h0bits));
+    }
     g.epi.bias = w.prenet_b; g.epi.pe_t = c.f32(pl.pe_t); g.epi.pe_alpha = w.pe_alpha; g.epi.pe_T = T;
     g.epi.drop = drop_pe; g.epi.drop_site = 0;
     c.out(g.epi, pl.h0, 0, D);
@@ -706,7 +728,7 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
                                          reinterpret_cast<const float2*>(c.f32(pl.hst)), w.norm_w, head_T, S, c.f32(pl.de),
                                          c.ptr(dhead), dhead.ps, gr.norm_w, gr.norm_b, gs);
   SPK_CUDA(cudaGetLastError());
-  head_wgrad_kernel<<<256, 256, 0, st>>>(c.f32(pl.de), c.f32(pl.emean), B / S, gr.proj_w, gr.proj_b);
+  head_wgrad_kernel<<<dim3(256, 8), 256, 0, st>>>(c.f32(pl.de), c.f32(pl.emean), B / S, gr.proj_w, gr.proj_b);
   SPK_CUDA(cudaGetLastError());
   }
 
@@ -939,21 +961,26 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
       SPK_TRY(run(g));
     }
   }
-  // ---- embedding: positional alpha, prenet weight / bias  (ReLU gate recomputed from x0 W^T + b)
-  SPK_TRY(pe_alpha_grad(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.f32(pl.pe_t), drop_pe, 0, gr.pe_alpha, Mt, T, gs, st));
-  {
-    GemmProblem g;
-    g.tag = "gemm.bwd.prenet_gate";
-    g.A = c.mat(pl.x0, 0, Mt, pl.C, pl.C);
-    g.B = c.mat(pl.wpack, pl.w_pre, D, pl.C, pl.C);
-    // same operand planes as the forward prenet GEMM, so the recomputed ReLU gate is the forward's gate
-    g.planes = P_fwd; g.M = (int)Mt; g.N = (int)D; g.K = pl.C;
-    g.epi.flags = EPI_BIAS | EPI_ACC_GATES_AUX | EPI_COLSUM;
-    g.epi.colsum = gr.prenet_b;
-    g.epi.bias = w.prenet_b; g.epi.drop = drop_pe; g.epi.drop_site = 0;
-    c.res(g.epi, pl.dh_a, D);
-    c.out(g.epi, pl.dh_b, 0, D);
-    SPK_TRY(run(g));
+  // ---- embedding: positional alpha, prenet weight / bias
+  if (P >= 2) {   // one pass over dH0: dropout mask, d_alpha, ReLU gate from the forward's mask bits, bias gradient
+    SPK_TRY(prenet_bwd(c.ptr(pl.dh_a), pl.dh_a.ps, P, reinterpret_cast<const uint32_t*>(c.f32(pl.h0bits)), c.f32(pl.pe_t),
+                       drop_pe, 0, c.ptr(pl.dh_b), pl.dh_b.ps, gr.pe_alpha, gr.prenet_b, Mt, T, gs, st));
+  } else {        // one-plane plans keep no mask: the gate is recomputed from x0 W^T + b
+    SPK_TRY(pe_alpha_grad(c.ptr(pl.dh_a), pl.dh_a.ps, P, c.f32(pl.pe_t), drop_pe, 0, gr.pe_alpha, Mt, T, gs, st));
+    {
+      GemmProblem g;
+      g.tag = "gemm.bwd.prenet_gate";
+      g.A = c.mat(pl.x0, 0, Mt, pl.C, pl.C);
+      g.B = c.mat(pl.wpack, pl.w_pre, D, pl.C, pl.C);
+      // same operand planes as the forward prenet GEMM, so the recomputed ReLU gate is the forward's gate
+      g.planes = P_fwd; g.M = (int)Mt; g.N = (int)D; g.K = pl.C;
+      g.epi.flags = EPI_BIAS | EPI_ACC_GATES_AUX | EPI_COLSUM;
+      g.epi.colsum = gr.prenet_b;
+      g.epi.bias = w.prenet_b; g.epi.drop = drop_pe; g.epi.drop_site = 0;
+      c.res(g.epi, pl.dh_a, D);
+      c.out(g.epi, pl.dh_b, 0, D);
+      SPK_TRY(run(g));
+    }
   }
   SPK_TRY(wgrad(c, pl.dh_b, D, pl.x0, pl.C, gr.prenet_w, "gemm.bwd.prenet_wgrad", gs + 1));
   return 0;

@@ -29,7 +29,8 @@ enum : uint32_t {
   EPI_COLSUM = 1u << 7,     // colsum[col] += sum_rows(v)  (bias gradient fused into the producing GEMM)
   EPI_OUT_F32 = 1u << 8,    // plain fp32 store instead of split planes
   EPI_OUT_ATOMIC = 1u << 9,  // fp32 atomicAdd (split-K weight gradients)
-  EPI_EMIT_BITS = 1u << 10,  // gate_bits[col/32, row]: bit i set iff v[col0 + i] > 0   (forward: ReLU mask for the backward)
+  EPI_EMIT_BITS = 1u << 10,  // gate_bits[col/32, row]: bit i set iff v[col0 + i] > 0   (forward: ReLU mask for the backward;
+                             // with EPI_PE the mask is taken right after the ReLU, otherwise after dropout)
   EPI_GATE_BITS = 1u << 11   // v = bit ? v * gate_scale : 0 from gate_bits (ReLU backward, 1 bit per element)
 };
 

@@ -295,6 +295,12 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
+  if ((f & EPI_EMIT_BITS) && (f & EPI_PE)) {   // prenet: the mask is the ReLU's own (before the positional term and dropout)
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f) ? (1u << i) : 0u;
+    if (row_ok) e.gate_bits[static_cast<int64_t>(col0 >> 5) * M + row] = m;
+  }
   if ((f & EPI_PE) && row_ok) {
     const float* pr = e.pe_t + (row % e.pe_T) * N + col0;
 #pragma unroll
@@ -318,7 +324,7 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
       }
     }
   }
-  if (f & EPI_EMIT_BITS) {          // ReLU mask of the final (post-dropout) activation, 1 bit per element
+  if ((f & EPI_EMIT_BITS) && !(f & EPI_PE)) {   // ReLU mask of the final (post-dropout) activation, 1 bit per element
     uint32_t m = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f) ? (1u << i) : 0u;

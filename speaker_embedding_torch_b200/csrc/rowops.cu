@@ -553,6 +553,70 @@ int colsum(const void* x, int64_t ps, int planes, float* out, int64_t rows, int 
   return 0;
 }
 
+// Embedding backward in one pass over dH0 (replaces pe_alpha_grad + a recomputing GEMM):
+//   g = dH0 * keep(site 0);   d_alpha += sum g * pe_t[t];   dU = g * 1[u > 0] (mask bits written by the forward prenet
+//   epilogue, layout [256 / 32][rows]);   d_bias[col] += sum_rows dU.        Modules.py:50-52,98-105
+__global__ void __launch_bounds__(256) prenet_bwd_kernel(const elem_t* __restrict__ dh, int64_t ps, int planes,
+                                                         const uint32_t* __restrict__ bits, const float* __restrict__ pe_t,
+                                                         DropCfg drop, uint32_t site, elem_t* __restrict__ du, int64_t du_ps,
+                                                         float* __restrict__ dalpha, float* __restrict__ dbias, int64_t rows,
+                                                         int T, const float* __restrict__ gscale) {
+  __shared__ float red[8];
+  __shared__ float cs[8][256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float acc = 0.f, col[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) col[i] = 0.f;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float d[8];
+    load8_split(dh, ps, planes, r * 256 + lane * 8, d);
+    const uint32_t word = __ldg(bits + static_cast<int64_t>(lane >> 2) * rows + r) >> ((lane & 3) * 8);
+    if (drop.thresh != 0) {
+      float k8[8];
+      const uint64_t idx = static_cast<uint64_t>(r) * 256 + lane * 8;
+      dropout_scale8(drop.seed, site, idx >> 3, drop.thresh, drop.inv_keep, k8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] *= k8[i];
+    }
+    const float4* pr = reinterpret_cast<const float4*>(pe_t + (r % T) * 256 + lane * 8);
+    const float4 p0 = __ldg(pr), p1 = __ldg(pr + 1);
+    acc += d[0] * p0.x + d[1] * p0.y + d[2] * p0.z + d[3] * p0.w + d[4] * p1.x + d[5] * p1.y + d[6] * p1.z + d[7] * p1.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      d[i] = ((word >> i) & 1u) ? d[i] : 0.f;
+      col[i] += d[i];
+    }
+    store8_split(du, du_ps, planes, r * 256 + lane * 8, d);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) red[wib] = acc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cs[wib][lane * 8 + i] = col[i];
+  __syncthreads();
+  const float inv_s = gscale != nullptr ? __ldg(gscale + 1) : 1.f;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += cs[w][threadIdx.x];
+  atomicAdd(dbias + threadIdx.x, s * inv_s);
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += red[w];
+    atomicAdd(dalpha, a * inv_s);
+  }
+}
+int prenet_bwd(const void* dh, int64_t ps, int planes, const uint32_t* bits, const float* pe_t, DropCfg drop, uint32_t site,
+               void* du, int64_t du_ps, float* dalpha, float* dbias, int64_t rows, int T, const float* gscale,
+               cudaStream_t st) {
+  ProfScope prof("prenet_bwd", 0, 1024.0 * rows * planes + 32.0 * rows, st);
+  const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 4));
+  prenet_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const elem_t*>(dh), ps, planes, bits, pe_t, drop, site,
+                                            reinterpret_cast<elem_t*>(du), du_ps, dalpha, dbias, rows, T, gscale);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // d_alpha += sum over tokens/channels of dH0 * keep(site 0) * pe_t[t]
 __global__ void __launch_bounds__(256) pe_alpha_grad_kernel(const elem_t* __restrict__ dh, int64_t ps, int planes,
                                                             const float* __restrict__ pe_t, DropCfg drop, uint32_t site,
