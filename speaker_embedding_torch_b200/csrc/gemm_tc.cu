@@ -30,13 +30,16 @@ constexpr int BLOCK_K = 64;              // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in limit per CTA
 constexpr int BAR_BYTES = 256;
-constexpr int NUM_EPI_WARPS = 8;         // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int NUM_EPI_WARPS = 12;        // three warps per TMEM lane quarter, round-robin over the 32-column chunks
+constexpr int EPI_CG = NUM_EPI_WARPS / 4;  // column groups
 constexpr int EPI_STAGE_BYTES = 2176;    // per warp: bf16 tile 32 x 32 (2 KB) or fp32 tile 32 x 17
 constexpr int EPI_BIAS_BYTES = 512;      // per warp: the bias of its (up to four) 32-column chunks of the current tile
 constexpr int EPI_SMEM = NUM_EPI_WARPS * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
-// setmaxnreg: the CTA's register pool is its launch allocation, 384 x 168 >= 128 x 48 + 256 x 224 (a larger request
-// spins forever): warps 0-3 (TMA / MMA / TMEM / idle) keep 48 registers, the epilogue warps get 224.
-constexpr int LAUNCH_REGS = 168, CTRL_REGS = 48, EPI_REGS = 224;
+// setmaxnreg: the CTA's register pool is its launch allocation, 512 x 128 >= 128 x 40 + 384 x 152 (a larger request
+// spins forever): warps 0-3 (TMA / MMA / TMEM / idle) keep 40 registers, the epilogue warps get 152.  (Round 1 ran 8
+// epilogue warps at 224 registers: the epilogue is a latency-bound chain per 32 x 32 chunk -- ncu r02: 14 cycles per
+// issued instruction with two warps per scheduler -- so a third warp per scheduler buys more than the registers did.)
+constexpr int LAUNCH_REGS = 128, CTRL_REGS = 40, EPI_REGS = 152;
 
 struct GemmKernelArgs {
   CUtensorMap a_map[3];
@@ -407,7 +410,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t st
     const int cn = c + NUM_EPI_WARPS / 4;
     if (use_bits && cn < BLOCK_N / 32 && tn * BLOCK_N + cn * 32 < N) next_word = __ldg(bits_row + static_cast<int64_t>(cn) * M);
     tmem_ld_wait();
-    epilogue32<CT>(e, stage_buf, bias_buf + (c >> 1) * 128, lane, M, N, row0, batch, out_boff, io_out, io_res, io_gate,
+    epilogue32<CT>(e, stage_buf, bias_buf + (c / EPI_CG) * 128, lane, M, N, row0, batch, out_boff, io_out, io_res, io_gate,
                    cs_boff, col0, r, pe_alpha, word, alpha, cs_scale);
   }
 }
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
     // ===================================================================== epilogue
     setmaxnreg_inc<EPI_REGS>();
     const int w = (warp - 4) & 3;          // TMEM lane quarter (warp % 4) -> accumulator rows 32w .. 32w+31
-    const int cgroup = (warp - 4) >> 2;    // this warp handles the 32-column chunks with (c & 1) == cgroup
+    const int cgroup = (warp - 4) >> 2;    // this warp handles the 32-column chunks with c % EPI_CG == cgroup
     const GemmEpilogue& e = args.epi;
     const float pe_alpha = (e.flags & EPI_PE) ? __ldg(e.pe_alpha) : 0.f;
     const float alpha = e.alpha * (e.alpha_ptr != nullptr ? __ldg(e.alpha_ptr) : 1.f);
@@ -575,9 +578,9 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
       const int i0 = t % args.nb0, i1 = t / args.nb0;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      if (e.flags & EPI_BIAS) {   // bias of this warp's chunks (cgroup + 2 j) -> shared memory, before the accumulator is due
+      if (e.flags & EPI_BIAS) {   // bias of this warp's chunks (cgroup + EPI_CG j) -> shared memory, before the accumulator is due
         const int j = lane >> 3;
-        const int cloc = cgroup * 32 + j * 64;
+        const int cloc = (cgroup + j * EPI_CG) * 32;
         const int col = tn * BLOCK_N + cloc + (lane & 7) * 4;
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cloc < BLOCK_N && col < args.N) b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
@@ -829,7 +832,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
       const uint32_t acc_phase = (it >> 1) & 1;
       if (e.flags & EPI_BIAS) {
         const int j = lane >> 3;
-        const int cloc = cgroup * 32 + j * 64;
+        const int cloc = (cgroup + j * EPI_CG) * 32;
         const int col = tn * BLOCK_N + cloc + (lane & 7) * 4;
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cloc < BLOCK_N && col < args.N) b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
