@@ -1071,8 +1071,13 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
 
   SPK_TRY(configure_all());
 
+  // Problems with few rows (the pruned last layer: M = slices) are latency-bound: 256-wide tiles would put them on 8-32
+  // CTAs that each walk the whole K loop; 64-wide single-CTA tiles spread the same work over 4x as many SMs.
+  int req_bn = p.block_n;
+  if (req_bn == 0 && !p.a_mn && p.ksplit <= 1 && p.nb0 * p.nb1 == 1 && p.M <= 2048 && p.N >= 128) req_bn = 64;
+
   // CTA-pair path: K-major A, two or three planes, no split-K, 256-wide N tiles
-  if (g_cta_pairs && !p.a_mn && p.planes >= 2 && p.ksplit <= 1 && p.block_n == 0 && p.N % 128 == 0 && p.M >= 256) {
+  if (g_cta_pairs && !p.a_mn && p.planes >= 2 && p.ksplit <= 1 && req_bn == 0 && p.N % 128 == 0 && p.M >= 256) {
     constexpr int BN = 256;
     GemmKernelArgs a;
     memset(&a, 0, sizeof(a));
@@ -1107,7 +1112,7 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
     return launch_pair<false, 2, BN>(a, pairs, stream);
   }
 
-  int bn = p.block_n;
+  int bn = req_bn;
   if (bn == 0) bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : (p.N <= 192 ? 192 : 256));
   if (p.planes == 3 && bn > 128) bn = 128;
 
