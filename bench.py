@@ -425,7 +425,7 @@ def run_native(args):
         tflops = r["flops"] / r["launches"] / (per_launch_ms * 1e-3) / 1e12
         gbs = r["bytes"] / r["launches"] / (per_launch_ms * 1e-3) / 1e9
         # every dense contraction of the encoder is charged against the sustained bf16 tensor peak with its
-        # bf16 dense FLOP count (the extra MMAs of the split-plane products are not credited); row kernels against HBM
+        # 16-bit dense FLOP count (the extra MMAs of the split-plane products are not credited); row kernels against HBM
         tensor_bound = is_contraction(tag) and r["flops"] > 0
         roof = {"kernel": tag, "bound": "tensor" if tensor_bound else "hbm",
                 "achieved": tflops if tensor_bound else gbs, "peak": pk["tf_sus"] if tensor_bound else pk["hbm"],

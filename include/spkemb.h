@@ -76,7 +76,7 @@ typedef struct spk_encoder_params {
   float* proj_b;     /* [emb] */
 } spk_encoder_params;
 
-/* precision (low 8 bits): 1 = bf16 operands (inference), 2 = split-bf16 hi+lo (3 MMAs per product), 3 = hi+mid+lo
+/* precision (low 8 bits): 1 = fp16 operands (inference), 2 = split-fp16 hi+lo (3 MMAs per product), 3 = hi+mid+lo
  * (6 MMAs, fp32-equivalent forward; the backward pass then reads two of the three planes).
  * Upper bits: the library options that shape the workspace (SPK_PLAN_*).  A caller that wants its backward call to
  * be immune to spk_set_option() between forward and backward passes `precision | spk_plan_flags()` to
@@ -188,7 +188,7 @@ int spk_optim_step(const spk_optim_tensors* tensors, int kind, int64_t step, flo
                    float beta2, float eps, float weight_decay, float max_grad_norm, float grad_scale,
                    float* norm_scratch, int phase, int chunk, int nchunks, void* stream);
 
-/* Diagnostic / benchmark entry: one tensor-core GEMM on split-bf16 operands,
+/* Diagnostic / benchmark entry: one tensor-core GEMM on split-fp16 operands,
  * D[M,N] = A * B^T (+ bias, ReLU), used by the GEMM parity tests and the roofline bench. */
 typedef struct spk_gemm_desc {
   const void* a; int64_t a_plane_stride, a_rows, a_cols, a_ld, a_sb0, a_sb1; int32_t a_mn;
@@ -201,7 +201,7 @@ typedef struct spk_gemm_desc {
 } spk_gemm_desc;
 int spk_gemm(const spk_gemm_desc* desc, void* stream);
 
-/* fp32 [n] -> split-bf16 planes (hi at dst, lo at dst + plane_stride elements). */
+/* fp32 [n] -> split-fp16 planes (hi at dst, lo at dst + plane_stride elements). */
 int spk_split_pack(const float* src, void* dst, int64_t plane_stride, int planes, int64_t n, void* stream);
 
 int spk_device_info(int* sm_count, int* cc_major, int* cc_minor);

@@ -199,7 +199,7 @@ def ptr(t):
 
 
 # ---------------------------------------------------------------------------------------------
-# helpers shared by tests and bench: split-bf16 planes <-> fp32
+# helpers shared by tests and bench: split-fp16 planes <-> fp32
 
 def split_pack(x, planes):
     """fp32 CUDA tensor -> fp16 tensor [planes, *x.shape] (hi, lo) via the library's kernel."""

@@ -1,4 +1,4 @@
-// Fused attention forward for inference (one bf16 plane, no dropout, T <= 256 frames):
+// Fused attention forward for inference (one fp16 plane, no dropout, T <= 256 frames):
 //
 //     O = softmax(Q K^T / 8) V     per (slice, head, 128-query tile), scores never leave the SM.
 //
@@ -7,10 +7,10 @@
 //             arrive as zeros)
 //   tcgen05   S = Q K^T  -> TMEM columns [0, 256)    (UMMA 128 x Tk16 x 16, both operands K-major)
 //   4 warps   thread <-> query row: row max / exp / sum straight from TMEM (tcgen05.ld), unnormalised
-//             probabilities written as bf16 into shared memory in the 128-byte-swizzled K-major layout
+//             probabilities written as fp16 into shared memory in the 128-byte-swizzled K-major layout
 //             the tensor core reads (the same layout TMA produces), keys >= T as zeros
 //   tcgen05   O = P V    -> TMEM columns [256, 320)  (V read MN-major: no transpose)
-//   4 warps   O * (1 / row sum) -> bf16 -> out[(b*T + q) * 256 + h*64 ...]
+//   4 warps   O * (1 / row sum) -> fp16 -> out[(b*T + q) * 256 + h*64 ...]
 //
 // Replaces the QK^T GEMM + softmax kernel + PV GEMM of the dense layers in the inference path (the
 // training path keeps multi-plane operands and materialised probabilities for the backward pass).
@@ -19,7 +19,7 @@
 
 namespace spk {
 
-__device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2: ~2 ulp, plenty for bf16 probabilities
+__device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2: ~2 ulp, plenty for fp16 probabilities
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256, 1) attn_fused_fwd_kernel(const __grid_con
         for (int i = 0; i < 32; ++i)
           if (c * 32 + i < a.T) mx = fmaxf(mx, __uint_as_float(sreg[i]));
       }
-      // pass 2: unnormalised probabilities -> bf16 -> swizzled shared memory; row sum in fp32
+      // pass 2: unnormalised probabilities -> fp16 -> swizzled shared memory; row sum in fp32
       const float mxs = mx * sc;
       float sum = 0.f;
       for (int c = 0; c * 32 < a.Tk64; ++c) {

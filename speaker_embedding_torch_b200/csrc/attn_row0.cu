@@ -7,7 +7,7 @@
 // the score / softmax / PV contraction is 2 x T x 64 MACs -- a bandwidth-bound sweep over K and V that
 // is done here in fp32 by one warp per (slice, head), forward and backward.
 //
-// Layouts: q0 [B, 256] and kv [B*T, 512] (K | V, head h at columns h*64) are split-bf16 tensors;
+// Layouts: q0 [B, 256] and kv [B*T, 512] (K | V, head h at columns h*64) are split-fp16 tensors;
 // probabilities p / p*keep are kept in fp32 [B*H, Tp] for the backward pass.
 #include "rowops.h"
 
@@ -45,6 +45,33 @@ __device__ __forceinline__ float keep_of(const DropCfg& d, uint32_t site, uint64
 __device__ __forceinline__ void load8f(const elem_t* base, int64_t ps, int planes, int64_t off, float (&v)[8]) {
   load8_split(base, ps, planes, off, v);
 }
+// Four rows (one per unrolled key step) of a PL-plane tensor: all 4 x PL 16-byte loads are issued before any is decoded,
+// so a warp keeps 4 x PL x 512 B in flight (the plane loop of load8_split has a run-time bound and serialised them:
+// ncu r02 showed one key step in flight per warp and 30 % of the DRAM peak).
+template <int PL>
+__device__ __forceinline__ void load_rows4(const elem_t* __restrict__ base, int64_t ps, const int64_t (&off)[4],
+                                           float (&v)[4][8]) {
+  uint4 raw[4][PL];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+#pragma unroll
+    for (int p = 0; p < PL; ++p) raw[u][p] = __ldg(reinterpret_cast<const uint4*>(base + p * ps + off[u]));
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+#pragma unroll
+    for (int p = 0; p < PL; ++p) {
+      const uint32_t w[4] = {raw[u][p].x, raw[u][p].y, raw[u][p].z, raw[u][p].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[u][2 * i] += lo_to_f(w[i]);
+        v[u][2 * i + 1] += hi_to_f(w[i]);
+      }
+    }
+  }
+}
 __device__ __forceinline__ float group8_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -52,6 +79,7 @@ __device__ __forceinline__ float group8_sum(float v) {
   return v;
 }
 
+template <int PL>
 __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
     const elem_t* __restrict__ q0, int64_t q_ps, const elem_t* __restrict__ kv, int64_t kv_ps, int planes,
     elem_t* __restrict__ att0, int64_t a_ps, float* __restrict__ p0, float* __restrict__ pd0, DropCfg drop,
@@ -66,17 +94,21 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
   float q[8];
   load8f(q0, q_ps, planes, static_cast<int64_t>(b) * 256 + h * 64 + d8 * 8, q);
   const int64_t kv_row0 = static_cast<int64_t>(b) * T * 512 + h * 64 + d8 * 8;
-  // scores
-#pragma unroll 4
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    const int t = min(t0 + g, T - 1);
-    float k[8];
-    load8f(kv, kv_ps, planes, kv_row0 + static_cast<int64_t>(t) * 512, k);
-    float s = 0.f;
+  // scores: 16 keys per round (four key steps of four groups)
+  for (int t0 = 0; t0 < T; t0 += 16) {
+    int64_t off[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s = fmaf(q[i], k[i], s);
-    s = group8_sum(s);
-    if (d8 == 0 && t0 + g < T) sc[t0 + g] = s * 0.125f;
+    for (int u = 0; u < 4; ++u) off[u] = kv_row0 + static_cast<int64_t>(min(t0 + 4 * u + g, T - 1)) * 512;
+    float k[4][8];
+    load_rows4<PL>(kv, kv_ps, off, k);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(q[i], k[u][i], s);
+      s = group8_sum(s);
+      if (d8 == 0 && t0 + 4 * u + g < T) sc[t0 + 4 * u + g] = s * 0.125f;
+    }
   }
   __syncwarp();
   float mx = -INFINITY;
@@ -104,15 +136,18 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
   __syncwarp();
   // o = sum_t pd_t V_t : each key group accumulates its keys, then the four groups are combined
   float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    const int t = t0 + g;
-    if (t < T) {
-      float v[8];
-      load8f(kv, kv_ps, planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512, v);
-      const float pd = sc[t];
+  for (int t0 = 0; t0 < T; t0 += 16) {
+    int64_t off[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf(pd, v[i], o[i]);
+    for (int u = 0; u < 4; ++u) off[u] = kv_row0 + 256 + static_cast<int64_t>(min(t0 + 4 * u + g, T - 1)) * 512;
+    float v[4][8];
+    load_rows4<PL>(kv, kv_ps, off, v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + 4 * u + g;
+      const float pd = t < T ? sc[t] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(pd, v[u][i], o[i]);
     }
   }
 #pragma unroll
@@ -128,15 +163,29 @@ int attn_row0_fwd(const void* q0, int64_t q_ps, const void* kv, int64_t kv_ps, i
   SPK_CHECK(H == R0_WARPS, "attn_row0: %d heads unsupported", H);
   ProfScope prof("attn_row0_fwd", 4.0 * B * H * T * 64, 2.0 * B * T * 512 * planes, st);
   const int blocks = (B * H + R0_WARPS - 1) / R0_WARPS;
-  attn_row0_fwd_kernel<<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
+  if (planes == 1) {
+    constexpr int PLV = 1;
+    attn_row0_fwd_kernel<PLV><<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
       reinterpret_cast<const elem_t*>(q0), q_ps, reinterpret_cast<const elem_t*>(kv), kv_ps, planes,
       reinterpret_cast<elem_t*>(att0), a_ps, p0, pd0, drop, site, B, H, T, Tp);
+  } else if (planes == 2) {
+    constexpr int PLV = 2;
+    attn_row0_fwd_kernel<PLV><<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
+      reinterpret_cast<const elem_t*>(q0), q_ps, reinterpret_cast<const elem_t*>(kv), kv_ps, planes,
+      reinterpret_cast<elem_t*>(att0), a_ps, p0, pd0, drop, site, B, H, T, Tp);
+  } else {
+    constexpr int PLV = 3;
+    attn_row0_fwd_kernel<PLV><<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
+      reinterpret_cast<const elem_t*>(q0), q_ps, reinterpret_cast<const elem_t*>(kv), kv_ps, planes,
+      reinterpret_cast<elem_t*>(att0), a_ps, p0, pd0, drop, site, B, H, T, Tp);
+  }
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
 
 // Backward: given d(att0), produces dq0 [B,256], dense dK | dV rows [B*T, 512] and the three in-proj bias
 // gradient slices.  p*dp' = pd*dp (pd = p*keep), so the saved p / pd pair is all the dropout state needed.
+template <int PL>
 __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
     const elem_t* __restrict__ datt0, int64_t da_ps, int g_planes, const elem_t* __restrict__ q0,
     int64_t q_ps, const elem_t* __restrict__ kv, int64_t kv_ps, int planes, const float* __restrict__ p0,
@@ -159,24 +208,32 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
   const float* pd = pd0 + bh * Tp;
   // dV rows and dp_t = dO . V_t
   float pd_sum = 0.f;
-#pragma unroll 4
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    const int t = t0 + g;
-    const int tc = min(t, T - 1);
-    float v[8];
-    load8f(kv, kv_ps, planes, kv_row0 + 256 + static_cast<int64_t>(tc) * 512, v);
-    float dp = 0.f;
+  for (int t0 = 0; t0 < T; t0 += 16) {
+    int64_t off[4];
+    float pdt[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dp = fmaf(dout[i], v[i], dp);
-    dp = group8_sum(dp);
-    if (t < T) {
-      const float pdt = pd[t];
-      if (d8 == 0) ds[t] = dp;
-      pd_sum += pdt;
-      float w[8];
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + 4 * u + g;
+      off[u] = kv_row0 + 256 + static_cast<int64_t>(min(t, T - 1)) * 512;
+      pdt[u] = t < T ? __ldg(pd + t) : 0.f;
+    }
+    float v[4][8];
+    load_rows4<PL>(kv, kv_ps, off, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = pdt * dout[i];
-      store8_split(dkv, dkv_ps, g_planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512, w);
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + 4 * u + g;
+      float dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dp = fmaf(dout[i], v[u][i], dp);
+      dp = group8_sum(dp);
+      if (t < T) {
+        if (d8 == 0) ds[t] = dp;
+        pd_sum += pdt[u];
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pdt[u] * dout[i];
+        store8_split(dkv, dkv_ps, g_planes, kv_row0 + 256 + static_cast<int64_t>(t) * 512, w);
+      }
     }
   }
   // pd_sum currently holds this key group's share: combine the four groups
@@ -195,16 +252,22 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
   ds_sum = warp_sum(ds_sum);
   __syncwarp();
   float dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    const int t = t0 + g;
-    if (t < T) {
-      float k[8], w[8];
-      load8f(kv, kv_ps, planes, kv_row0 + static_cast<int64_t>(t) * 512, k);
-      const float d = ds[t];
+  for (int t0 = 0; t0 < T; t0 += 16) {
+    int64_t off[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { dq[i] = fmaf(d, k[i], dq[i]); w[i] = d * q[i]; }
-      store8_split(dkv, dkv_ps, g_planes, kv_row0 + static_cast<int64_t>(t) * 512, w);
+    for (int u = 0; u < 4; ++u) off[u] = kv_row0 + static_cast<int64_t>(min(t0 + 4 * u + g, T - 1)) * 512;
+    float k[4][8];
+    load_rows4<PL>(kv, kv_ps, off, k);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + 4 * u + g;
+      if (t < T) {
+        float w[8];
+        const float d = ds[t];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dq[i] = fmaf(d, k[u][i], dq[i]); w[i] = d * q[i]; }
+        store8_split(dkv, dkv_ps, g_planes, kv_row0 + static_cast<int64_t>(t) * 512, w);
+      }
     }
   }
 #pragma unroll
@@ -230,10 +293,25 @@ int attn_row0_bwd(const void* datt0, int64_t da_ps, int g_planes, const void* q0
   SPK_CHECK(H == R0_WARPS, "attn_row0: %d heads unsupported", H);
   ProfScope prof("attn_row0_bwd", 8.0 * B * H * T * 64, 2.0 * B * T * 512 * (planes + g_planes), st);
   const int blocks = (B * H + R0_WARPS - 1) / R0_WARPS;
-  attn_row0_bwd_kernel<<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
+  if (planes == 1) {
+    constexpr int PLV = 1;
+    attn_row0_bwd_kernel<PLV><<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
       reinterpret_cast<const elem_t*>(datt0), da_ps, g_planes, reinterpret_cast<const elem_t*>(q0), q_ps,
       reinterpret_cast<const elem_t*>(kv), kv_ps, planes, p0, pd0, reinterpret_cast<elem_t*>(dq0), dq_ps,
       reinterpret_cast<elem_t*>(dkv), dkv_ps, dbias, gscale, B, H, T, Tp);
+  } else if (planes == 2) {
+    constexpr int PLV = 2;
+    attn_row0_bwd_kernel<PLV><<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
+      reinterpret_cast<const elem_t*>(datt0), da_ps, g_planes, reinterpret_cast<const elem_t*>(q0), q_ps,
+      reinterpret_cast<const elem_t*>(kv), kv_ps, planes, p0, pd0, reinterpret_cast<elem_t*>(dq0), dq_ps,
+      reinterpret_cast<elem_t*>(dkv), dkv_ps, dbias, gscale, B, H, T, Tp);
+  } else {
+    constexpr int PLV = 3;
+    attn_row0_bwd_kernel<PLV><<<blocks, 32 * R0_WARPS, R0_WARPS * Tp * sizeof(float), st>>>(
+      reinterpret_cast<const elem_t*>(datt0), da_ps, g_planes, reinterpret_cast<const elem_t*>(q0), q_ps,
+      reinterpret_cast<const elem_t*>(kv), kv_ps, planes, p0, pd0, reinterpret_cast<elem_t*>(dq0), dq_ps,
+      reinterpret_cast<elem_t*>(dkv), dkv_ps, dbias, gscale, B, H, T, Tp);
+  }
   SPK_CUDA(cudaGetLastError());
   return 0;
 }

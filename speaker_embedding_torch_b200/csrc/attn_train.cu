@@ -1,4 +1,4 @@
-// Fused attention for the TRAINING path (multi-plane split-bf16 operands, dropout on the probabilities, a backward
+// Fused attention for the TRAINING path (multi-plane split-fp16 operands, dropout on the probabilities, a backward
 // pass that recomputes instead of reading stored probabilities).  Replaces, per dense layer, the QK^T GEMM + softmax
 // kernel + PV GEMM of the forward and the dV / dP GEMMs + softmax-backward kernel + dQ / dK GEMMs of the backward
 // (8 launches over a materialised [B*H, T, T] score tensor in 2-3 planes) by two kernels whose scores never leave the
@@ -14,13 +14,13 @@
 //   TMA       Q tile, K, V (PL planes each) out of the packed qkv buffer [B*T, 768]
 //   tcgen05   S = Q K^T into TMEM (6 plane products for PL = 3, 3 for PL = 2), fp32
 //   8 warps   thread <-> query row (two warps per TMEM lane quarter, alternating 32-key chunks): row max, exp2, row
-//             sum, Philox keep mask, split into bf16 planes and written BACK INTO TMEM over the scores they came from
+//             sum, Philox keep mask, split into fp16 planes and written BACK INTO TMEM over the scores they came from
 //             (tcgen05.st): the probabilities are the A operand of the next MMA straight from tensor memory
 //   tcgen05   O = P_drop V  (A from TMEM, V read MN-major from shared memory)
-//   8 warps   O * (1 / ((1 - p) * row sum)) -> PL bf16 planes -> att[(b*T + q) * 256 + h*64 ...]
+//   8 warps   O * (1 / ((1 - p) * row sum)) -> PL fp16 planes -> att[(b*T + q) * 256 + h*64 ...]
 //   kept for the backward: (row max * log2e / 8, row sum) per query and one keep BIT per probability.
 //
-// TMEM plane layout of P for key step t (16 keys = one MMA K step = 8 columns of packed bf16 pairs, even key in the low
+// TMEM plane layout of P for key step t (16 keys = one MMA K step = 8 columns of packed fp16 pairs, even key in the low
 // half -- tools/probe/ts_probe.cu): plane 0 at S columns [16t, 16t+8), plane 1 at [16t+8, 16t+16), plane 2 (PL = 3)
 // at P_LO + [8t, 8t+8); i.e. planes 0 and 1 overwrite exactly the 16 score columns they were computed from.
 #include "gemm.h"
@@ -58,7 +58,7 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem] * B[smem]: A is [128 lanes x K] packed bf16 pairs in tensor memory (K-major by construction)
+// D[tmem] (+)= A[tmem] * B[smem]: A is [128 lanes x K] packed fp16 pairs in tensor memory (K-major by construction)
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -406,14 +406,14 @@ int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64
   a.stats = reinterpret_cast<float2*>(stats);
   a.mbits = drop.thresh != 0 ? reinterpret_cast<uint16_t*>(mbits) : nullptr;
   a.drop = drop; a.site = site;
-  // algorithmic work: QK^T and PV (bf16 dense count); bytes: Q, K, V in, O out
+  // algorithmic work: QK^T and PV (16-bit dense count); bytes: Q, K, V in, O out
   ProfScope prof("attn_train_fwd", 4.0 * B * H * T * T * 64, 4.0 * B * T * 64 * H * 2.0 * planes, st);
   if (planes == 3) return attn_train_fwd_launch<3>(a, reinterpret_cast<const elem_t*>(qkv), qkv_ps, st);
   return attn_train_fwd_launch<2>(a, reinterpret_cast<const elem_t*>(qkv), qkv_ps, st);
 }
 
 // =====================================================================================================================
-// Backward.  Two bf16 planes everywhere (gradients are smooth in their inputs, DESIGN.md "precision").  Per (slice,
+// Backward.  Two fp16 planes everywhere (gradients are smooth in their inputs, DESIGN.md "precision").  Per (slice,
 // head) the keys are walked in tiles i, the queries in tiles j of `rpt` rows each (rpt = the frames split evenly over
 // ceil(T / 128) tiles, rounded up to 16: 160 frames -> 2 x 80, so that every (i, j) unit is the same size and keeps
 // three of the four lane quarters busy); everything is computed TRANSPOSED (keys on the TMEM lanes) so that the two
@@ -422,7 +422,7 @@ int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64
 //   tcgen05   S^T  = K_i Q_j^T ,  dP^T = V_i dO_j^T                    -> TMEM (fp32)
 //   16 warps  thread <-> key row: P^T = exp2(S^T * c - m_q) / l_q (row statistics saved by the forward), keep bit from
 //             the forward's bit mask (32 x 32 bit transpose by warp shuffles), dS^T = P^T (keep dP^T/(1-p) - delta_q) / 8;
-//             P_drop^T and dS^T go back into TMEM over S^T / dP^T as bf16 planes; dS^T also into shared memory in the
+//             P_drop^T and dS^T go back into TMEM over S^T / dP^T as fp16 planes; dS^T also into shared memory in the
 //             MN-major operand layout (probe: tools/probe/ts_probe.cu)
 //   tcgen05   dV_i += P_drop^T dO_j  and  dK_i += dS^T Q_j   (A from TMEM, B MN-major from shared memory)
 //             dQ_j += dS K_i                                  (A = dS from shared memory, MN-major)
@@ -498,7 +498,7 @@ __device__ __forceinline__ float column_sums16(float (&v)[16], int lane) {
   }
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
-// 16 fp32 values -> two bf16 planes at dst / dst + ps (16-byte stores)
+// 16 fp32 values -> two fp16 planes at dst / dst + ps (16-byte stores)
 __device__ __forceinline__ void store16_two_planes(elem_t* dst, int64_t ps, const float (&v)[16]) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
@@ -514,7 +514,7 @@ __device__ __forceinline__ void store16_two_planes(elem_t* dst, int64_t ps, cons
   }
 }
 
-// 16 fp32 values -> two bf16 planes, 2 x 16 bytes each, into shared-memory staging chunks
+// 16 fp32 values -> two fp16 planes, 2 x 16 bytes each, into shared-memory staging chunks
 __device__ __forceinline__ void stage16_two_planes(uint32_t hi0, uint32_t hi1, uint32_t lo0, uint32_t lo1, const float (&v)[16]) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
           mbar_arrive(bar_p);
         }
         // ---- dV_i, dK_i complete (last query tile's MMAs retired; the dS tile in shared memory is free): every warp
-        //      takes 16 of the 64 columns of each out of TMEM, stages them as bf16 planes, then the quarter's four warps
+        //      takes 16 of the 64 columns of each out of TMEM, stages them as fp16 planes, then the quarter's four warps
         //      write one (tensor, plane) each with full 128-byte rows
         mbar_wait(bar_tile, kt & 1u, 0x721u);
         tc_fence_after();

@@ -1,4 +1,4 @@
-// Shared host/device helpers: error reporting, split-bf16 tensors, Philox dropout masks.
+// Shared host/device helpers: error reporting, split-fp16 tensors, Philox dropout masks.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>

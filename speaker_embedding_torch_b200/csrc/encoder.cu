@@ -3,7 +3,7 @@
 // post-LN torch.nn.TransformerEncoderLayer built at Modules.py:25-36; math: SURVEY.md Appendix B.
 //
 // Data layout in HBM (all token-major, tokens = slices * frames):
-//   split tensors  [planes][rows][cols] bf16   activations and gradients that feed tensor-core GEMMs
+//   split tensors  [planes][rows][cols] fp16   activations and gradients that feed tensor-core GEMMs
 //   fp32           LayerNorm statistics, head vectors, parameters and parameter gradients
 // Dense contractions run in gemm_tc.cu (tcgen05/TMEM/TMA); everything else is a coalesced row kernel.
 #include "encoder.h"

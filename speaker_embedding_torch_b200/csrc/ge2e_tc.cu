@@ -3,7 +3,7 @@
 // the threshold the loss is composed from the tcgen05 GEMM of gemm_tc.cu and three row kernels instead of
 // the single fp32 SIMT kernel of ge2e.cu:
 //
-//   prep    (block / speaker)  row norms, centroids; Ehat, Chat as split-bf16 planes (+ fp32 Chat)
+//   prep    (block / speaker)  row norms, centroids; Ehat, Chat as split-fp16 planes (+ fp32 Chat)
 //   GEMM    S = Ehat Chat^T    3 planes (fp32-equivalent), fp32 output [NM, Np]
 //   rows    (warp / row)       z = w S - b, log-sum-exp, loss, dw, db, G = (w/NM)(softmax - onehot) -> 2 planes
 //   GEMM    dEhat = G Chat     (Chat read MN-major), fp32 output

@@ -1,4 +1,4 @@
-// Host-side description of one (batched, optionally split-K) tensor-core GEMM on split-bf16 operands.
+// Host-side description of one (batched, optionally split-K) tensor-core GEMM on split-fp16 operands.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -7,11 +7,11 @@
 
 namespace spk {
 
-// A row-major matrix (cols contiguous) stored as 1 or 2 bf16 planes, optionally batched over two
+// A row-major matrix (cols contiguous) stored as 1 or 2 fp16 planes, optionally batched over two
 // outer indices.  As a GEMM operand it is "K-major" when cols is the contraction dim and
 // "MN-major" when rows is the contraction dim (A^T / B^T reads, no transposed copy is ever made).
 struct SplitMat {
-  const void* base = nullptr;   // bf16
+  const void* base = nullptr;   // fp16
   int64_t plane_stride = 0;     // elements from the hi plane to the lo plane
   int64_t rows = 0, cols = 0;   // per-batch extents as stored
   int64_t ld = 0;               // elements between consecutive rows
@@ -82,7 +82,7 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream);
 int device_sm_count();
 void gemm_set_cta_pairs(int on);   // route eligible multi-plane GEMMs through the cta_group::2 kernel
 
-// bf16 4-D tiled tensor map {dims[0] (contiguous), dims[1], dims[2], dims[3]} with element strides for dims 1..3,
+// fp16 4-D tiled tensor map {dims[0] (contiguous), dims[1], dims[2], dims[3]} with element strides for dims 1..3,
 // box {64, box_rows, 1, 1}, 128-byte swizzle, out-of-bounds elements read as zero.
 int encode_map_4d(CUtensorMap* map, const void* base, const int64_t dims[4], const int64_t strides[3], int box_rows);
 

@@ -1,11 +1,11 @@
-// Persistent, warp-specialised tcgen05 GEMM for sm_100a on split-bf16 operands.
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a on split-fp16 operands.
 //
 //   D[M,N] = epilogue( alpha * A[M,K] * B[N,K]^T )          (per batch, optional split-K)
 //
 // * operands are fetched by TMA (cp.async.bulk.tensor.4d, 128-byte swizzle) into a multi-stage
 //   shared-memory ring; each operand may be K-major or MN-major (transposed reads for dgrad /
 //   wgrad / P*V come from the descriptor, never from a transposed copy);
-// * one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16 in, fp32 accumulate in
+// * one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, fp16 in, fp32 accumulate in
 //   TMEM); with two planes it issues Ah*Bh + Ah*Bl + Al*Bh into the same accumulator, with three
 //   planes the six products down to 2^-16 (fp32-equivalent operands);
 // * the accumulator is double-buffered in TMEM so the 8 epilogue warps (tcgen05.ld -> registers
@@ -26,13 +26,13 @@
 namespace spk {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;              // 64 bf16 = one 128-byte swizzle row
+constexpr int BLOCK_K = 64;              // 64 fp16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in limit per CTA
 constexpr int BAR_BYTES = 256;
 constexpr int NUM_EPI_WARPS = 12;        // three warps per TMEM lane quarter, round-robin over the 32-column chunks
 constexpr int EPI_CG = NUM_EPI_WARPS / 4;  // column groups
-constexpr int EPI_STAGE_BYTES = 2176;    // per warp: bf16 tile 32 x 32 (2 KB) or fp32 tile 32 x 17
+constexpr int EPI_STAGE_BYTES = 2176;    // per warp: fp16 tile 32 x 32 (2 KB) or fp32 tile 32 x 17
 constexpr int EPI_BIAS_BYTES = 512;      // per warp: the bias of its (up to four) 32-column chunks of the current tile
 constexpr int EPI_SMEM = NUM_EPI_WARPS * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
 // setmaxnreg: the CTA's register pool is its launch allocation, 512 x 128 >= 128 x 40 + 384 x 152 (a larger request
@@ -910,7 +910,7 @@ int device_sm_count() {
   return sms[dev];
 }
 
-// 4-D map {cols, rows, nb0, nb1}; box = {64, box_rows, 1, 1}; bf16; 128-byte swizzle; OOB -> zeros.
+// 4-D map {cols, rows, nb0, nb1}; box = {64, box_rows, 1, 1}; fp16; 128-byte swizzle; OOB -> zeros.
 static int make_map(CUtensorMap* map, const SplitMat& m, int plane, int nb0, int nb1, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   SPK_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
