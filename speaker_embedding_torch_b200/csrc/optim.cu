@@ -13,13 +13,26 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const __grid_constant_
                                                           float* __restrict__ partial) {
   __shared__ float red[8];
   float acc = 0.f;
-  for (int i = 0; i < t.count; ++i) {
-    const float* g = t.grad[i];
+  // Block b owns the elements [b * per, (b + 1) * per) of the concatenation of the table's tensors: it touches one or two
+  // tensors instead of walking all of them (43 dependent round trips to memory per block: 33 us for 9.8 MB).  The
+  // mapping is fixed, so the partial sums -- and the norm -- stay bit-reproducible.
+  int64_t total = 0;
+  for (int i = 0; i < t.count; ++i) total += t.numel[i];
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * per, hi = lo + per < total ? lo + per : total;
+  int64_t base = 0;
+  for (int i = 0; i < t.count && base < hi; ++i) {
     const int64_t n = t.numel[i];
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-      const float v = g[j] * gs;
-      acc = fmaf(v, v, acc);
+    const int64_t a = (lo > base ? lo : base) - base, b = (hi < base + n ? hi : base + n) - base;
+    if (a < b) {
+      const float* g = t.grad[i];
+#pragma unroll 4
+      for (int64_t j = a + threadIdx.x; j < b; j += blockDim.x) {
+        const float v = g[j] * gs;
+        acc = fmaf(v, v, acc);
+      }
     }
+    base += n;
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -59,13 +72,22 @@ __global__ void __launch_bounds__(256) optim_update_kernel(const __grid_constant
     __syncthreads();
     coef *= fminf(1.f, s.max_norm / (sqrtf(total_s) + 1e-6f));
   }
-  for (int i = 0; i < t.count; ++i) {
+  int64_t total = 0;
+  for (int i = 0; i < t.count; ++i) total += t.numel[i];
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * per, hi = lo + per < total ? lo + per : total;
+  int64_t base = 0;
+  for (int i = 0; i < t.count && base < hi; ++i) {
+    const int64_t n = t.numel[i];
+    const int64_t a = (lo > base ? lo : base) - base, b = (hi < base + n ? hi : base + n) - base;
+    base += n;
+    if (a >= b) continue;
     float* p = t.param[i];
     const float* g = t.grad[i];
     float* m = t.exp_avg[i];
     float* v = t.exp_avg_sq[i];
-    const int64_t n = t.numel[i];
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll 4
+    for (int64_t j = a + threadIdx.x; j < b; j += blockDim.x) {
       const float gj = g[j] * coef;
       float pj = p[j];
       const float vj = s.beta2 * v[j] + (1.f - s.beta2) * gj * gj;
