@@ -280,149 +280,231 @@ __global__ void __launch_bounds__(1024) grad_scale_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 // d-vector head (Modules.py:54-57): final LayerNorm of the t = 0 token of every slice, mean over the
 // `samples` slices of an utterance, 256x256 projection (fp32), L2 normalisation.
+// Eight utterances per block, one warp each: the 256 KB projection matrix is read once per block (the first version
+// ran one utterance per block and moved 960 x 256 KB through L2 per call: 45 us for 2 MB of real work).
+constexpr int HEAD_UPB = 8;
 __global__ void __launch_bounds__(256) head_fwd_kernel(const elem_t* __restrict__ h, int64_t ps, int planes,
                                                        int T, int S, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ wp,
                                                        const float* __restrict__ bp, float* __restrict__ hn,
                                                        float2* __restrict__ hst, float* __restrict__ emean,
-                                                       float* __restrict__ epre, float* __restrict__ dvec) {
-  __shared__ float red[8];
-  __shared__ float em[256];
+                                                       float* __restrict__ epre, float* __restrict__ dvec, int64_t U) {
+  __shared__ __align__(16) float em[HEAD_UPB][256];
+  __shared__ float wt[256][33];                      // projection rows n0 .. n0+31, transposed: wt[k][n - n0]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t u = blockIdx.x;
-  auto bsum = [&](float v) {
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    float s = 0.f;
+  const int64_t u = static_cast<int64_t>(blockIdx.x) * HEAD_UPB + warp;
+  const bool valid = u < U;
+  // ---- final LayerNorm of the t = 0 token of each slice, mean over the slices (lane owns columns lane*8 .. +7)
+  float acc[8];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w];
-    return s;
-  };
-  float acc = 0.f;
-  const float g = __ldg(gamma + tid), b = __ldg(beta + tid);
-  for (int s = 0; s < S; ++s) {
-    const int64_t slice = u * S + s;
-    const float x = load1_split(h, ps, planes, slice * T * 256 + tid);   // token t = 0
-    const float mean = bsum(x) * (1.f / 256.f);
-    const float xc = x - mean;
-    const float rstd = rsqrtf(bsum(xc * xc) * (1.f / 256.f) + 1e-5f);
-    const float y = xc * rstd * g + b;
-    hn[slice * 256 + tid] = y;
-    if (tid == 0) hst[slice] = make_float2(mean, rstd);
-    acc += y;
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (valid) {
+    float g[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = __ldg(gamma + lane * 8 + i); b[i] = __ldg(beta + lane * 8 + i); }
+    for (int s = 0; s < S; ++s) {
+      const int64_t slice = u * S + s;
+      float v[8];
+      load8_split(h, ps, planes, slice * T * 256 + lane * 8, v);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += v[i];
+      const float mean = warp_sum(sum) * (1.f / 256.f);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+      const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + 1e-5f);
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { y[i] = v[i] * rstd * g[i] + b[i]; acc[i] += y[i]; }
+      float4* dst = reinterpret_cast<float4*>(hn + slice * 256 + lane * 8);
+      dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+      dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+      if (lane == 0) hst[slice] = make_float2(mean, rstd);
+    }
+    const float inv_s = 1.f / static_cast<float>(S);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv_s;
+    float4* dst = reinterpret_cast<float4*>(emean + u * 256 + lane * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
-  acc *= 1.f / static_cast<float>(S);
-  emean[u * 256 + tid] = acc;
-  em[tid] = acc;
-  __syncthreads();
-  // projection: warp w computes outputs w*32 .. w*32+31, lanes split the 256-long dot product
-  __shared__ float eo[256];
-  for (int j = 0; j < 32; ++j) {
-    const int n = warp * 32 + j;
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + n * 256 + lane * 8));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + n * 256 + lane * 8 + 4));
-    const float* e8 = em + lane * 8;
-    float d = w0.x * e8[0] + w0.y * e8[1] + w0.z * e8[2] + w0.w * e8[3] + w1.x * e8[4] + w1.y * e8[5] +
-              w1.z * e8[6] + w1.w * e8[7];
-    d = warp_sum(d);
-    if (lane == 0) eo[n] = d + __ldg(bp + n);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) em[warp][lane * 8 + i] = acc[i];
+  // ---- projection: 32 outputs per round; lane = output within the round, warp = utterance
+  float eo[8];
+#pragma unroll 1
+  for (int t = 0; t < 8; ++t) {
+    __syncthreads();                                 // em is written / the previous round's tile has been consumed
+#pragma unroll 8
+    for (int it = 0; it < 32; ++it) wt[tid][it] = __ldg(wp + static_cast<int64_t>(t * 32 + it) * 256 + tid);
+    __syncthreads();
+    float d = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 256; k += 4) {
+      const float4 e4 = *reinterpret_cast<const float4*>(&em[warp][k]);
+      d = fmaf(wt[k][lane], e4.x, d);
+      d = fmaf(wt[k + 1][lane], e4.y, d);
+      d = fmaf(wt[k + 2][lane], e4.z, d);
+      d = fmaf(wt[k + 3][lane], e4.w, d);
+    }
+    eo[t] = d + __ldg(bp + t * 32 + lane);
   }
-  __syncthreads();
-  const float e = eo[tid];
-  epre[u * 256 + tid] = e;
-  const float nrm = fmaxf(sqrtf(bsum(e * e)), 1e-12f);
-  dvec[u * 256 + tid] = e / nrm;
+  if (valid) {
+    float ss = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) ss += eo[t] * eo[t];
+    const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      epre[u * 256 + t * 32 + lane] = eo[t];
+      dvec[u * 256 + t * 32 + lane] = eo[t] / nrm;
+    }
+  }
 }
 
-// Backward of the head for one utterance: d_dvec -> de (pre-normalisation), d_emean, final-LN backward
-// into the t = 0 rows of dH (pre-zeroed), dgamma/dbeta of the final LayerNorm.
+// Backward of the head, eight utterances per block (one warp each): d_dvec -> de (pre-normalisation), d_emean,
+// final-LN backward into the t = 0 rows of dH (pre-zeroed), dgamma / dbeta of the final LayerNorm.
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ g_dvec, const float* __restrict__ epre,
                                                        const float* __restrict__ wp, const elem_t* __restrict__ h,
                                                        int64_t h_ps, int planes, const float2* __restrict__ hst,
                                                        const float* __restrict__ gamma, int T, int S,
                                                        float* __restrict__ de_out, elem_t* __restrict__ dh,
                                                        int64_t dh_ps, float* __restrict__ dgamma,
-                                                       float* __restrict__ dbeta, const float* __restrict__ gscale) {
-  __shared__ float red[8];
-  __shared__ float des[256];
+                                                       float* __restrict__ dbeta, const float* __restrict__ gscale,
+                                                       int64_t U) {
+  __shared__ float des[HEAD_UPB][256];
+  __shared__ float wt[32][256];                      // projection rows n0 .. n0+31 (also the dgamma / dbeta exchange)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t u = blockIdx.x;
-  auto bsum = [&](float v) {
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    float s = 0.f;
+  const int64_t u = static_cast<int64_t>(blockIdx.x) * HEAD_UPB + warp;
+  const bool valid = u < U;
+  // ---- L2-normalisation backward (lane owns outputs lane*8 .. +7)
+  {
+    float e[8], go[8], de[8];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w];
-    return s;
-  };
-  const float e = epre[u * 256 + tid];
-  const float go = g_dvec[u * 256 + tid];
-  const float nrm = sqrtf(bsum(e * e));
-  float de;
-  if (nrm > 1e-12f) {            // block-uniform
-    const float d = e / nrm;
-    const float dot = bsum(go * d);
-    de = (go - dot * d) / nrm;
-  } else {
-    de = go / 1e-12f;
+    for (int i = 0; i < 8; ++i) { e[i] = 0.f; go[i] = 0.f; }
+    if (valid) {
+      const float4* ep = reinterpret_cast<const float4*>(epre + u * 256 + lane * 8);
+      const float4* gp = reinterpret_cast<const float4*>(g_dvec + u * 256 + lane * 8);
+      const float4 e0 = ep[0], e1 = ep[1], g0 = gp[0], g1 = gp[1];
+      e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w; e[4] = e1.x; e[5] = e1.y; e[6] = e1.z; e[7] = e1.w;
+      go[0] = g0.x; go[1] = g0.y; go[2] = g0.z; go[3] = g0.w; go[4] = g1.x; go[5] = g1.y; go[6] = g1.z; go[7] = g1.w;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += e[i] * e[i];
+    const float nrm = sqrtf(warp_sum(ss));
+    if (nrm > 1e-12f) {            // warp-uniform
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { e[i] /= nrm; dot += go[i] * e[i]; }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) de[i] = (go[i] - dot * e[i]) / nrm;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) de[i] = go[i] / 1e-12f;
+    }
+    if (valid) {
+      float4* dst = reinterpret_cast<float4*>(de_out + u * 256 + lane * 8);
+      dst[0] = make_float4(de[0], de[1], de[2], de[3]);
+      dst[1] = make_float4(de[4], de[5], de[6], de[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) des[warp][lane * 8 + i] = valid ? de[i] : 0.f;
   }
-  de_out[u * 256 + tid] = de;
-  des[tid] = de;
-  __syncthreads();
-  // d_emean[k] = sum_n Wp[n][k] * de[n]   (thread k; coalesced over k)
-  float dm = 0.f;
+  // ---- d_emean[k] = sum_n Wp[n][k] * de[n]   (lane owns k = lane + 32 j)
+  float dm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dm[j] = 0.f;
+#pragma unroll 1
+  for (int t = 0; t < 8; ++t) {
+    __syncthreads();
 #pragma unroll 8
-  for (int n = 0; n < 256; ++n) dm = fmaf(__ldg(wp + n * 256 + tid), des[n], dm);
-  dm *= 1.f / static_cast<float>(S);       // gradient of every slice's LayerNorm output
-  const float gam = __ldg(gamma + tid);
-  float ag = 0.f, ab = 0.f;
-  for (int s = 0; s < S; ++s) {
-    const int64_t slice = u * S + s;
-    const int64_t off = slice * T * 256 + tid;
-    const float2 ms = hst[slice];
-    const float xh = (load1_split(h, h_ps, planes, off) - ms.x) * ms.y;
-    ag += dm * xh;
-    ab += dm;
-    const float gd = dm * gam;
-    const float m1 = bsum(gd) * (1.f / 256.f);
-    const float m2 = bsum(gd * xh) * (1.f / 256.f);
-    store1_split(dh, dh_ps, planes, off, ms.y * (gd - m1 - xh * m2) * __ldg(gscale));   // enters the encoder scaled by S
+    for (int it = 0; it < 32; ++it) wt[it][tid] = __ldg(wp + static_cast<int64_t>(t * 32 + it) * 256 + tid);
+    __syncthreads();
+#pragma unroll 4
+    for (int nl = 0; nl < 32; ++nl) {
+      const float dv = des[warp][t * 32 + nl];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dm[j] = fmaf(wt[nl][lane + 32 * j], dv, dm[j]);
+    }
   }
-  atomicAdd(dgamma + tid, ag);
-  atomicAdd(dbeta + tid, ab);
+  const float inv_s = 1.f / static_cast<float>(S);       // gradient of every slice's LayerNorm output
+  float ag[8], ab[8], gam[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { dm[j] *= inv_s; ag[j] = 0.f; ab[j] = 0.f; gam[j] = __ldg(gamma + lane + 32 * j); }
+  if (valid) {
+    const float gsc = __ldg(gscale);                     // the gradient enters the encoder scaled by S
+    for (int s = 0; s < S; ++s) {
+      const int64_t slice = u * S + s;
+      const int64_t off = slice * T * 256 + lane;
+      const float2 ms = hst[slice];
+      float xh[8], gd[8];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[j] = (load1_split(h, h_ps, planes, off + 32 * j) - ms.x) * ms.y;
+        ag[j] += dm[j] * xh[j];
+        ab[j] += dm[j];
+        gd[j] = dm[j] * gam[j];
+        s1 += gd[j];
+        s2 += gd[j] * xh[j];
+      }
+      const float m1 = warp_sum(s1) * (1.f / 256.f);
+      const float m2 = warp_sum(s2) * (1.f / 256.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) store1_split(dh, dh_ps, planes, off + 32 * j, ms.y * (gd[j] - m1 - xh[j] * m2) * gsc);
+    }
+  }
+  // ---- dgamma / dbeta: the block's eight utterances meet in shared memory, one atomic per column and block
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wt[warp][lane + 32 * j] = ag[j]; wt[8 + warp][lane + 32 * j] = ab[j]; }
+  __syncthreads();
+  float sg = 0.f, sb = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { sg += wt[w][tid]; sb += wt[8 + w][tid]; }
+  atomicAdd(dgamma + tid, sg);
+  atomicAdd(dbeta + tid, sb);
 }
 
-// dWp[n][k] += sum_u de[u][n] * emean[u][k] ; dbp[n] += sum_u de[u][n]     (block (n, chunk of u), thread k)
-// The u range is cut into gridDim.y chunks (four independent accumulators each) so the 2 x U dependent loads of the
-// first version (132 us at U = 960) become U / 32 rounds; partial sums meet in fp32 atomics.
+// dWp[n][k] += sum_u de[u][n] * emean[u][k] ; dbp[n] += sum_u de[u][n]
+// Block (32 outputs n, chunk of utterances): thread k keeps 32 accumulators, the chunk's de columns sit in shared memory
+// (broadcast reads); partial sums meet in fp32 atomics.
+constexpr int HEAD_WG_UCH = 64;                      // utterances per block
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ de, const float* __restrict__ emean,
                                                          int64_t U, float* __restrict__ dwp, float* __restrict__ dbp) {
-  const int n = blockIdx.x, k = threadIdx.x;
-  const int64_t per = (U + gridDim.y - 1) / gridDim.y;
-  const int64_t u0 = blockIdx.y * per, u1 = (u0 + per < U) ? u0 + per : U;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-  int64_t u = u0;
-  for (; u + 4 <= u1; u += 4) {
-    const float d0 = __ldg(de + u * 256 + n), d1 = __ldg(de + (u + 1) * 256 + n);
-    const float d2 = __ldg(de + (u + 2) * 256 + n), d3 = __ldg(de + (u + 3) * 256 + n);
-    a0 = fmaf(d0, __ldg(emean + u * 256 + k), a0);
-    a1 = fmaf(d1, __ldg(emean + (u + 1) * 256 + k), a1);
-    a2 = fmaf(d2, __ldg(emean + (u + 2) * 256 + k), a2);
-    a3 = fmaf(d3, __ldg(emean + (u + 3) * 256 + k), a3);
-    b0 += d0; b1 += d1; b2 += d2; b3 += d3;
+  __shared__ __align__(16) float ds[HEAD_WG_UCH][32];
+  const int n0 = blockIdx.x * 32, k = threadIdx.x;
+  const int64_t u0 = static_cast<int64_t>(blockIdx.y) * HEAD_WG_UCH;
+  const int nu = static_cast<int>(U - u0 < HEAD_WG_UCH ? U - u0 : HEAD_WG_UCH);
+  for (int i = threadIdx.x; i < HEAD_WG_UCH * 32; i += 256) {
+    const int uu = i >> 5, nn = i & 31;
+    ds[uu][nn] = uu < nu ? __ldg(de + (u0 + uu) * 256 + n0 + nn) : 0.f;
   }
-  for (; u < u1; ++u) {
-    const float d = __ldg(de + u * 256 + n);
-    a0 = fmaf(d, __ldg(emean + u * 256 + k), a0);
-    b0 += d;
+  __syncthreads();
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int uu = 0; uu < nu; ++uu) {
+    const float e = __ldg(emean + (u0 + uu) * 256 + k);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 d4 = *reinterpret_cast<const float4*>(&ds[uu][4 * q]);
+      acc[4 * q] = fmaf(d4.x, e, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(d4.y, e, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(d4.z, e, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(d4.w, e, acc[4 * q + 3]);
+    }
   }
-  if (u1 > u0) {
-    atomicAdd(dwp + n * 256 + k, (a0 + a1) + (a2 + a3));
-    if (k == 0) atomicAdd(dbp + n, (b0 + b1) + (b2 + b3));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) atomicAdd(dwp + static_cast<int64_t>(n0 + i) * 256 + k, acc[i]);
+  if (k < 32) {
+    float sb = 0.f;
+    for (int uu = 0; uu < nu; ++uu) sb += ds[uu][k];
+    atomicAdd(dbp + n0 + k, sb);
   }
 }
 
@@ -693,9 +775,9 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
   const Split& hl = pl.prune ? pl.last.hout : pl.Lb[pl.L - 1].hout;
   const int head_T = pl.prune ? 1 : T;     // the compact buffer holds one row per slice
   ProfScope prof_head("head_fwd", 2.0 * (B / S) * 256 * 256, 4.0 * B * 256 * 2, st);
-  head_fwd_kernel<<<B / S, 256, 0, st>>>(c.ptr(hl), hl.ps, P, head_T, S, w.norm_w, w.norm_b, w.proj_w, w.proj_b,
-                                         c.f32(pl.hn), reinterpret_cast<float2*>(c.f32(pl.hst)), c.f32(pl.emean),
-                                         c.f32(pl.epre), dvec);
+  head_fwd_kernel<<<(B / S + HEAD_UPB - 1) / HEAD_UPB, 256, 0, st>>>(
+      c.ptr(hl), hl.ps, P, head_T, S, w.norm_w, w.norm_b, w.proj_w, w.proj_b, c.f32(pl.hn),
+      reinterpret_cast<float2*>(c.f32(pl.hst)), c.f32(pl.emean), c.f32(pl.epre), dvec, static_cast<int64_t>(B / S));
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -732,11 +814,12 @@ int encoder_backward(const spk_encoder_config& cfg, const spk_encoder_params& w,
   if (!pl.prune) SPK_CUDA(cudaMemsetAsync(c.ptr(pl.dh_a), 0, static_cast<size_t>(pl.dh_a.ps) * P * 2, st));
   {
   ProfScope prof_hb("head_bwd", 4.0 * (B / S) * 256 * 256, 4.0 * B * 256 * 2, st);
-  head_bwd_kernel<<<B / S, 256, 0, st>>>(d_dvec, c.f32(pl.epre), w.proj_w, c.ptr(hl), hl.ps, P,
-                                         reinterpret_cast<const float2*>(c.f32(pl.hst)), w.norm_w, head_T, S, c.f32(pl.de),
-                                         c.ptr(dhead), dhead.ps, gr.norm_w, gr.norm_b, gs);
+  head_bwd_kernel<<<(B / S + HEAD_UPB - 1) / HEAD_UPB, 256, 0, st>>>(
+      d_dvec, c.f32(pl.epre), w.proj_w, c.ptr(hl), hl.ps, P, reinterpret_cast<const float2*>(c.f32(pl.hst)), w.norm_w,
+      head_T, S, c.f32(pl.de), c.ptr(dhead), dhead.ps, gr.norm_w, gr.norm_b, gs, static_cast<int64_t>(B / S));
   SPK_CUDA(cudaGetLastError());
-  head_wgrad_kernel<<<dim3(256, 8), 256, 0, st>>>(c.f32(pl.de), c.f32(pl.emean), B / S, gr.proj_w, gr.proj_b);
+  head_wgrad_kernel<<<dim3(8, (B / S + HEAD_WG_UCH - 1) / HEAD_WG_UCH), 256, 0, st>>>(c.f32(pl.de), c.f32(pl.emean), B / S,
+                                                                                      gr.proj_w, gr.proj_b);
   SPK_CUDA(cudaGetLastError());
   }
 
