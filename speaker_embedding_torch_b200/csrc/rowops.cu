@@ -11,11 +11,20 @@ namespace spk {
 // fp32 weights -> split-fp16 planes, all matrices in one launch.
 __global__ void pack_weights_kernel(const __grid_constant__ PackTable tab, elem_t* dst, int64_t plane_stride,
                                     int planes) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   for (int s = 0; s < tab.count; ++s) {
     const float* src = tab.seg[s].src;
     const int64_t n = tab.seg[s].n, off = tab.seg[s].dst_off;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-      store1_split(dst, plane_stride, planes, off + i, __ldg(src + i));
+    // eight weights per thread and round (two 16-byte loads, one 16-byte store per plane) when the segment allows it
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (off & 7) == 0;
+    const int64_t n8 = vec ? n / 8 : 0;
+    for (int64_t i = tid; i < n8; i += nth) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      store8_split(dst, plane_stride, planes, off + 8 * i, v);
+    }
+    for (int64_t i = n8 * 8 + tid; i < n; i += nth) store1_split(dst, plane_stride, planes, off + i, __ldg(src + i));
   }
 }
 int pack_weights(const PackTable& tab, void* dst, int64_t plane_stride, int planes, cudaStream_t st) {
