@@ -508,9 +508,9 @@ def run_native(args):
         dist.destroy_process_group()
 
 
-def run_infer_shard(model, gen, dev, world, rank, barrier, dist, utt=4000, reps=5):
+def run_infer_shard(model, gen, dev, world, rank, barrier, dist, utt=4000, reps=25):
     """BASELINE config 3 on this rank's shard: `utt` utterances per step, 5 x 64-frame slices at 32 overlap
-    (Inference.py:95-115), `reps` timed steps; plus the 160-frame single-slice d-vector rate.  Returns rank-0 dict
+    (Inference.py:95-115), `reps` timed steps (25 x 4 000 = the 100 000 utterances of the configuration, per GPU); plus the 160-frame single-slice d-vector rate.  Returns rank-0 dict
     with whole-job numbers (time = max over ranks; utterances are independent, there is no collective)."""
     from speaker_embedding_torch_b200.Prefetch import Device_Prefetcher
     pk = peaks()
@@ -569,7 +569,7 @@ def run_infer_shard(model, gen, dev, world, rank, barrier, dist, utt=4000, reps=
             "dvectors_per_sec_160f": world * batch / (dv_ms * 1e-3), "ms_per_960x160_batch": dv_ms,
             "config3": {"metric": "utterances/sec, multi-slice extraction 5 x 64 frames / 32 overlap",
                         "value": world * reps * utt / (ms * 1e-3), "unit": "utterances/s",
-                        "utterances_per_step_per_gpu": utt, "steps": reps, "ms_per_step": ms / reps, "n_gpus": world,
+                        "utterances_per_step_per_gpu": utt, "utterances_per_gpu": utt * reps, "steps": reps, "ms_per_step": ms / reps, "n_gpus": world,
                         "sharding": "utterance shards, no collective",
                         "e2e": {"value": world * reps * utt / (ms_e2e * 1e-3), "unit": "utterances/s",
                                 "h2d_bytes_per_step": host_windows.numel() * 2, "d2h_bytes_per_step": utt * 256 * 4},
