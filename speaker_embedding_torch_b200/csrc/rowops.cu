@@ -167,8 +167,12 @@ int pe_transpose(const float* pe, float* pe_t, int D, int max_pos, int T, cudaSt
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over D = 256, one warp per row.
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const elem_t* __restrict__ z, int64_t z_ps, int z_planes,
+// LayerNorm over D = 256, one warp per row, NR rows per round: all NR x PL plane loads of a round are issued before any
+// row is reduced (one row per round left a single 512-byte row in flight per warp behind the two dependent shuffle
+// reductions: 45 % of the DRAM peak, ncu r02).  One-plane (inference) tensors move half the bytes per row and take four
+// rows per round.
+template <int PL, int NR>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const elem_t* __restrict__ z, int64_t z_ps,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      elem_t* __restrict__ y, int64_t y_ps, int y_planes,
                                                      float2* __restrict__ stats, int64_t rows, int64_t row_stride_rows,
@@ -179,33 +183,29 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const elem_t* __restrict__ 
   float g[8], b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { g[i] = __ldg(gamma + lane * 8 + i); b[i] = __ldg(beta + lane * 8 + i); }
-  // Two rows per round: both rows' plane loads are issued before either is reduced (one row per round left a single
-  // 512-byte row in flight per warp behind the two dependent shuffle reductions: 45 % of the DRAM peak, ncu r02).
-  for (int64_t r0 = warp; r0 < rows; r0 += 2 * nwarps) {
-    const int64_t r1 = r0 + nwarps;
-    const bool two = r1 < rows;
-    uint4 raw[2][3];
+  for (int64_t r0 = warp; r0 < rows; r0 += NR * nwarps) {
+    uint4 raw[NR][PL];
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      if (p < z_planes) {
-        raw[0][p] = __ldg(reinterpret_cast<const uint4*>(z + p * z_ps + r0 * row_stride_rows * 256 + lane * 8));
-        if (two) raw[1][p] = __ldg(reinterpret_cast<const uint4*>(z + p * z_ps + r1 * row_stride_rows * 256 + lane * 8));
+    for (int u = 0; u < NR; ++u) {
+      const int64_t r = r0 + u * nwarps;
+      if (r < rows) {
+#pragma unroll
+        for (int p = 0; p < PL; ++p)
+          raw[u][p] = __ldg(reinterpret_cast<const uint4*>(z + p * z_ps + r * row_stride_rows * 256 + lane * 8));
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !two) break;
-      const int64_t r = u ? r1 : r0;
+    for (int u = 0; u < NR; ++u) {
+      const int64_t r = r0 + u * nwarps;
+      if (r >= rows) break;
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = 0.f;
 #pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        if (p < z_planes) {
-          const uint32_t w[4] = {raw[u][p].x, raw[u][p].y, raw[u][p].z, raw[u][p].w};
+      for (int p = 0; p < PL; ++p) {
+        const uint32_t w[4] = {raw[u][p].x, raw[u][p].y, raw[u][p].z, raw[u][p].w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { v[2 * i] += lo_to_f(w[i]); v[2 * i + 1] += hi_to_f(w[i]); }
-        }
+        for (int i = 0; i < 4; ++i) { v[2 * i] += lo_to_f(w[i]); v[2 * i + 1] += hi_to_f(w[i]); }
       }
       float s = 0.f;
 #pragma unroll
@@ -226,10 +226,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const elem_t* __restrict__ 
 int ln_fwd(const void* z, int64_t z_ps, int z_planes, int64_t z_row_step, const float* gamma, const float* beta,
            void* y, int64_t y_ps, int y_planes, float* stats, int64_t rows, cudaStream_t st) {
   ProfScope prof("ln_fwd", 0, 512.0 * rows * (z_planes + y_planes), st);
+  SPK_CHECK(z_planes >= 1 && z_planes <= 3, "ln_fwd: planes");
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
-  ln_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const elem_t*>(z), z_ps, z_planes, gamma, beta,
-                                        reinterpret_cast<elem_t*>(y), y_ps, y_planes,
-                                        reinterpret_cast<float2*>(stats), rows, z_row_step, 1e-5f);
+  const elem_t* zp = reinterpret_cast<const elem_t*>(z);
+  elem_t* yp = reinterpret_cast<elem_t*>(y);
+  float2* sp = reinterpret_cast<float2*>(stats);
+  if (z_planes == 1) ln_fwd_kernel<1, 4><<<blocks, 256, 0, st>>>(zp, z_ps, gamma, beta, yp, y_ps, y_planes, sp, rows, z_row_step, 1e-5f);
+  else if (z_planes == 2) ln_fwd_kernel<2, 2><<<blocks, 256, 0, st>>>(zp, z_ps, gamma, beta, yp, y_ps, y_planes, sp, rows, z_row_step, 1e-5f);
+  else ln_fwd_kernel<3, 2><<<blocks, 256, 0, st>>>(zp, z_ps, gamma, beta, yp, y_ps, y_planes, sp, rows, z_row_step, 1e-5f);
   SPK_CUDA(cudaGetLastError());
   return 0;
 }
