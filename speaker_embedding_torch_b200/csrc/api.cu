@@ -133,6 +133,7 @@ int spk_set_option(const char* name, int value) {
   SPK_CHECK(name != nullptr, "spk_set_option: null name");
   if (strcmp(name, "prune_last_layer") == 0) { encoder_set_prune(value != 0); return 0; }
   if (strcmp(name, "fused_inference_attention") == 0) { encoder_set_fused_attn(value != 0); return 0; }
+  if (strcmp(name, "inference_attention_two_ctas") == 0) { encoder_set_infer_attn_two(value); return 0; }
   if (strcmp(name, "fused_training_attention") == 0) { encoder_set_fused_train_attn(value != 0); return 0; }
   if (strcmp(name, "grad_scale_log2") == 0) { encoder_set_grad_scale_log2(value); return 0; }
   if (strcmp(name, "gemm_cta_pairs") == 0) { gemm_set_cta_pairs(value != 0); return 0; }

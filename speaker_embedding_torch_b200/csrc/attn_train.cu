@@ -413,6 +413,222 @@ int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64
 }
 
 // =====================================================================================================================
+// Inference variant (one fp16 plane, no dropout, nothing kept), T <= 192: the same structure with 8 compute warps,
+// 85 KB of shared memory and 256 TMEM columns, so that TWO CTAs share an SM and one item's softmax runs under the other
+// item's loads and MMAs (each item on its own is a serial chain TMA -> QK^T -> softmax -> PV -> store of ~8 us).
+constexpr int ATI_CW = 8, ATI_THREADS = 128 + 32 * ATI_CW, ATI_KV_ROWS = 192;
+constexpr int ATI_OFF_K = 16384, ATI_OFF_V = ATI_OFF_K + ATI_KV_ROWS * 128, ATI_OFF_X = ATI_OFF_V + ATI_KV_ROWS * 128;
+constexpr int ATI_OFF_STG = ATI_OFF_X + 2048, ATI_OFF_BAR = ATI_OFF_STG + 16384, ATI_SMEM = ATI_OFF_BAR + 128;
+constexpr int ATI_TMEM_O = 192;
+
+__device__ __forceinline__ void half_quarter_sync(int quarter) {   // the two warps that share a TMEM lane quarter
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+}
+
+__global__ void __launch_bounds__(ATI_THREADS, 2) attn_infer_fwd_kernel(const __grid_constant__ AttnTrainFwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t sQ = sbase, sK = sbase + ATI_OFF_K, sV = sbase + ATI_OFF_V;
+  float* xch = reinterpret_cast<float*>(smem_raw + ATI_OFF_X);   // [0..255] max parts, [256..511] sum parts
+  const uint32_t bar_kv = sbase + ATI_OFF_BAR, bar_q = bar_kv + 8, bar_s = bar_kv + 16, bar_p = bar_kv + 24,
+                 bar_o = bar_kv + 32, bar_oe = bar_kv + 40, bar_kvfree = bar_kv + 48, tmem_slot = bar_kv + 56;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sbase & 1023u) != 0) __trap();
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&a.q_map[0]); tma_prefetch_desc(&a.k_map[0]); tma_prefetch_desc(&a.v_map[0]); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 32 * ATI_CW); mbar_init(bar_o, 1);
+    mbar_init(bar_oe, 32 * ATI_CW); mbar_init(bar_kvfree, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tO = tmem_base + ATI_TMEM_O;
+  const int items = a.B * a.H;
+  const int kv_plane = a.Tk64 * 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t u = 0, it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int h = item % a.H, b = item / a.H;
+        if (it > 0) mbar_wait(bar_kvfree, (it - 1) & 1u, 0x640u);
+        mbar_arrive_expect_tx(bar_kv, 2u * kv_plane);
+        tma_load_4d(sK, &a.k_map[0], bar_kv, 0, 0, h, b);
+        tma_load_4d(sV, &a.v_map[0], bar_kv, 0, 0, h, b);
+        for (int mt = 0; mt < a.mtiles; ++mt, ++u) {
+          if (u > 0) mbar_wait(bar_s, (u - 1) & 1u, 0x641u);
+          mbar_arrive_expect_tx(bar_q, 16384);
+          tma_load_4d(sQ, &a.q_map[0], bar_q, 0, mt * 128, h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = umma_idesc_f16(128, a.Tk16, false, false);
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);
+    const uint64_t dQ0 = umma_smem_desc(sQ, 16, 1024), dK0 = umma_smem_desc(sK, 16, 1024);
+    const uint64_t dV0 = umma_smem_desc(sV, 8192, 1024);
+    const int ksteps = a.Tk16 / 16;
+    uint32_t u = 0, it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      for (int mt = 0; mt < a.mtiles; ++mt, ++u) {
+        mbar_wait(bar_q, u & 1u, 0x650u);
+        if (mt == 0) mbar_wait(bar_kv, it & 1u, 0x651u);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tS, desc_add(dQ0, k * 32), desc_add(dK0, k * 32), idesc_s, k ? 1u : 0u);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
+        mbar_wait(bar_p, u & 1u, 0x652u);
+        if (u > 0) mbar_wait(bar_oe, (u - 1) & 1u, 0x653u);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int t = 0; t < ksteps; ++t)
+            umma_f16_ts(tO, tS + 16 * t, desc_add(dV0, (t >> 2) * 8192 + (t & 3) * 2048), idesc_o, t ? 1u : 0u);
+          umma_commit(bar_o);
+          if (mt == a.mtiles - 1) umma_commit(bar_kvfree);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    const int w = (warp - 4) & 3, part = (warp - 4) >> 2;          // lane quarter, column part (0..1)
+    const int r = w * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(w * 32) << 16;
+    const int nchunks = a.Tk16 / 16;
+    uint32_t u = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int h = item % a.H, b = item / a.H;
+      for (int mt = 0; mt < a.mtiles; ++mt, ++u) {
+        const uint32_t ph = u & 1u;
+        const bool active = mt * 128 + w * 32 < a.T;              // warp-uniform
+        mbar_wait(bar_s, ph, 0x660u);
+        tc_fence_after();
+        uint32_t sreg[16];
+        float mx = -INFINITY;
+        if (active) {
+          for (int c = part; c * 16 < a.T; c += 2) {
+            tmem_ld_32x16(tS + t_lane + c * 16, sreg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c * 16 + i < a.T) mx = fmaxf(mx, __uint_as_float(sreg[i]));
+          }
+        }
+        xch[part * 128 + r] = mx;
+        half_quarter_sync(w);
+        mx = fmaxf(xch[r], xch[128 + r]);
+        const float mxs = mx * ATF_SC;
+        float sum = 0.f;
+        if (active) {
+          for (int c = part; c < nchunks; c += 2) {
+            tmem_ld_32x16(tS + t_lane + c * 16, sreg);
+            tmem_ld_wait();
+            uint32_t o8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int key = c * 16 + 2 * j;
+              const float e0 = key < a.T ? at_exp2(__uint_as_float(sreg[2 * j]) * ATF_SC - mxs) : 0.f;
+              const float e1 = key + 1 < a.T ? at_exp2(__uint_as_float(sreg[2 * j + 1]) * ATF_SC - mxs) : 0.f;
+              sum += e0 + e1;
+              o8[j] = pack2(e0, e1);                                      // columns 16c + j: the A operand of key step c
+            }
+            tmem_st_32x8(tS + t_lane + c * 16, o8);
+          }
+          tmem_st_wait();
+        }
+        xch[256 + part * 128 + r] = sum;
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        half_quarter_sync(w);
+        sum = xch[256 + r] + xch[384 + r];
+        mbar_wait(bar_o, ph, 0x661u);
+        tc_fence_after();
+        float v[32];
+        if (active) {
+          uint32_t oreg[16];
+          const float sc = 1.f / sum;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            tmem_ld_32x16(tO + t_lane + part * 32 + hlf * 16, oreg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[hlf * 16 + i] = __uint_as_float(oreg[i]) * sc;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_oe);
+        if (active) {                                             // uniform over the quarter's two warps
+          const uint32_t stg = sbase + ATI_OFF_STG;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {                           // this warp's 32 columns = 16-byte chunks 4 part .. 4 part + 3
+            uint32_t wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) wv[i] = pack2(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + r * 128 + (((4 * part + g) ^ (r & 7)) << 4)),
+                         "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
+          }
+          half_quarter_sync(w);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {                        // 16 of the quarter's 32 rows per warp, 4 rows per instruction
+            const int row = w * 32 + part * 16 + it * 4 + (lane >> 3);
+            uint4 val;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(stg + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) : "memory");
+            const int qq = mt * 128 + row;
+            if (qq < a.T)
+              *reinterpret_cast<uint4*>(a.out + (static_cast<int64_t>(b) * a.T + qq) * a.out_ld + h * 64 + (lane & 7) * 8) = val;
+          }
+          half_quarter_sync(w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// qkv: [B*T, 768] one plane; out: [B*T, out_ld] one plane (head h at column h*64).  T <= 192.
+int attn_infer_fwd(const void* qkv, void* out, int64_t out_ld, int B, int H, int T, cudaStream_t st) {
+  SPK_CHECK(T >= 1 && T <= ATI_KV_ROWS && H >= 1, "attn_infer_fwd: T=%d outside [1, %d]", T, ATI_KV_ROWS);
+  AttnTrainFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.H = H; a.T = T; a.Tp = (T + 7) / 8 * 8;
+  a.Tk16 = (T + 15) / 16 * 16;
+  a.Tk64 = (T + 63) / 64 * 64;
+  a.mtiles = (T + 127) / 128;
+  a.out = reinterpret_cast<elem_t*>(out);
+  a.out_ld = out_ld;
+  const int64_t ld = 3 * 64 * H;
+  const int64_t dims[4] = {64, T, H, B};
+  const int64_t strides[3] = {ld, 64, static_cast<int64_t>(T) * ld};
+  const elem_t* base = reinterpret_cast<const elem_t*>(qkv);
+  SPK_TRY(encode_map_4d(&a.q_map[0], base, dims, strides, 128));
+  SPK_TRY(encode_map_4d(&a.k_map[0], base + 64 * H, dims, strides, a.Tk64));
+  SPK_TRY(encode_map_4d(&a.v_map[0], base + 2 * 64 * H, dims, strides, a.Tk64));
+  static PerDeviceOnce once;
+  SPK_TRY(once.run([]() -> int {
+    SPK_CUDA(cudaFuncSetAttribute(attn_infer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATI_SMEM));
+    return 0;
+  }));
+  const int items = B * H;
+  const int grid = items < 2 * device_sm_count() ? items : 2 * device_sm_count();
+  ProfScope prof("attn_fused_fwd", 4.0 * B * H * T * T * 64, 4.0 * B * T * 64 * H * 2.0, st);
+  attn_infer_fwd_kernel<<<grid, ATI_THREADS, ATI_SMEM, st>>>(a);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =====================================================================================================================
 // Backward.  Two fp16 planes everywhere (gradients are smooth in their inputs, DESIGN.md "precision").  Per (slice,
 // head) the keys are walked in tiles i, the queries in tiles j of `rpt` rows each (rpt = the frames split evenly over
 // ceil(T / 128) tiles, rounded up to 16: 160 frames -> 2 x 80, so that every (i, j) unit is the same size and keeps

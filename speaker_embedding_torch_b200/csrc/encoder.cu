@@ -18,6 +18,7 @@ int attn_row0_bwd(const void* datt0, int64_t da_ps, int g_planes, const void* q0
                   int64_t kv_ps, int planes, const float* p0, const float* pd0, void* dq0, int64_t dq_ps, void* dkv,
                   int64_t dkv_ps, float* dbias, const float* gscale, int B, int H, int T, int Tp, cudaStream_t st);
 int attn_fused_fwd(const void* qkv, void* out, int64_t out_ld, int B, int H, int T, cudaStream_t st);
+int attn_infer_fwd(const void* qkv, void* out, int64_t out_ld, int B, int H, int T, cudaStream_t st);
 int attn_train_max_frames(int planes);
 int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64_t out_ps, int64_t out_ld, float* stats,
                    uint32_t* mbits, DropCfg drop, uint32_t site, int B, int H, int T, int Tp, cudaStream_t st);
@@ -83,6 +84,8 @@ static size_t take_f32(size_t& cur, int64_t elems) {
 static bool g_prune_last = true;   // spk_set_option("prune_last_layer", 0/1)
 void encoder_set_prune(bool on) { g_prune_last = on; }
 static bool g_fused_attn = true;   // spk_set_option("fused_inference_attention", 0/1)
+static bool g_infer_attn_two = true;   // spk_set_option("inference_attention_two_ctas", 0/1)
+void encoder_set_infer_attn_two(int on) { g_infer_attn_two = on != 0; }
 void encoder_set_fused_attn(bool on) { g_fused_attn = on; }
 static bool g_fused_train_attn = true;   // spk_set_option("fused_training_attention", 0/1)
 void encoder_set_fused_train_attn(bool on) { g_fused_train_attn = on; }
@@ -635,7 +638,9 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     }
     // inference (one plane, nothing kept for a backward pass): scores, softmax and PV in one tcgen05 kernel
     const bool fused_attn = (P == 1) && !keep && !training && T <= 256 && pl.fused_infer;
-    if (fused_attn) {
+    if (fused_attn && T <= 192 && g_infer_attn_two) {      // two CTAs per SM (attn_train.cu, inference variant)
+      SPK_TRY(attn_infer_fwd(c.ptr(b.qkv), c.ptr(b.att), D, B, H, T, st));
+    } else if (fused_attn) {
       SPK_TRY(attn_fused_fwd(c.ptr(b.qkv), c.ptr(b.att), D, B, H, T, st));
     } else if (pl.attn_tr) {
       SPK_TRY(attn_train_fwd(c.ptr(b.qkv), b.qkv.ps, P, c.ptr(b.att), b.att.ps, D, c.f32(b.astat),
