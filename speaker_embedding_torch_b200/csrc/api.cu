@@ -134,6 +134,7 @@ int spk_set_option(const char* name, int value) {
   if (strcmp(name, "prune_last_layer") == 0) { encoder_set_prune(value != 0); return 0; }
   if (strcmp(name, "fused_inference_attention") == 0) { encoder_set_fused_attn(value != 0); return 0; }
   if (strcmp(name, "inference_attention_two_ctas") == 0) { encoder_set_infer_attn_two(value); return 0; }
+  if (strcmp(name, "fused_layernorm") == 0) { encoder_set_fuse_ln(value); return 0; }
   if (strcmp(name, "fused_training_attention") == 0) { encoder_set_fused_train_attn(value != 0); return 0; }
   if (strcmp(name, "grad_scale_log2") == 0) { encoder_set_grad_scale_log2(value); return 0; }
   if (strcmp(name, "gemm_cta_pairs") == 0) { gemm_set_cta_pairs(value != 0); return 0; }

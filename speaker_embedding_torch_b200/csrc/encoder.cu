@@ -85,6 +85,8 @@ static bool g_prune_last = true;   // spk_set_option("prune_last_layer", 0/1)
 void encoder_set_prune(bool on) { g_prune_last = on; }
 static bool g_fused_attn = true;   // spk_set_option("fused_inference_attention", 0/1)
 static bool g_infer_attn_two = true;   // spk_set_option("inference_attention_two_ctas", 0/1)
+static bool g_fuse_ln = true;          // spk_set_option("fused_layernorm", 0/1)
+void encoder_set_fuse_ln(int on) { g_fuse_ln = on != 0; }
 void encoder_set_infer_attn_two(int on) { g_infer_attn_two = on != 0; }
 void encoder_set_fused_attn(bool on) { g_fused_attn = on; }
 static bool g_fused_train_attn = true;   // spk_set_option("fused_training_attention", 0/1)
@@ -622,6 +624,9 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     SPK_TRY(gemm_run(g, st));
   }
   const int dense_layers = pl.prune ? pl.L - 1 : pl.L;
+  // inference (nothing kept for a backward pass): both LayerNorms of the dense layers run inside the out-proj / FFN2
+  // epilogues (EPI_LN); training keeps the separate pass because the backward needs z and the row statistics
+  const bool fuse_ln = !keep && g_fuse_ln;
   for (int l = 0; l < dense_layers; ++l) {
     const LayerBufs& b = pl.Lb[l];
     const Split& hin = (l == 0) ? pl.h0 : pl.Lb[l - 1].hout;
@@ -680,10 +685,16 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       g.epi.flags = EPI_BIAS | EPI_RES | (drop.thresh ? EPI_DROPOUT : 0);
       g.epi.bias = lw.out_proj_b; g.epi.drop = drop; g.epi.drop_site = 2 + 4 * l;
       c.res(g.epi, hin, D);
-      c.out(g.epi, b.z1, 0, D);
+      if (fuse_ln) {   // inference: LayerNorm1 inside the epilogue (the tile owns whole rows), z1 never leaves the SM
+        g.epi.flags |= EPI_LN; g.epi.ln_gamma = lw.norm1_w; g.epi.ln_beta = lw.norm1_b;
+        c.out(g.epi, b.h1, 0, D);
+      } else {
+        c.out(g.epi, b.z1, 0, D);
+      }
       SPK_TRY(gemm_run(g, st));
     }
-    SPK_TRY(ln_fwd(c.ptr(b.z1), b.z1.ps, P, 1, lw.norm1_w, lw.norm1_b, c.ptr(b.h1), b.h1.ps, P, c.f32(b.st1), Mt, st));
+    if (!fuse_ln)
+      SPK_TRY(ln_fwd(c.ptr(b.z1), b.z1.ps, P, 1, lw.norm1_w, lw.norm1_b, c.ptr(b.h1), b.h1.ps, P, c.f32(b.st1), Mt, st));
     {  // linear1 + ReLU + dropout
       GemmProblem g;
       g.tag = "gemm.ffn1";
@@ -708,10 +719,16 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       g.epi.flags = EPI_BIAS | EPI_RES | (drop.thresh ? EPI_DROPOUT : 0);
       g.epi.bias = lw.linear2_b; g.epi.drop = drop; g.epi.drop_site = 4 + 4 * l;
       c.res(g.epi, b.h1, D);
-      c.out(g.epi, b.z2, 0, D);
+      if (fuse_ln) {
+        g.epi.flags |= EPI_LN; g.epi.ln_gamma = lw.norm2_w; g.epi.ln_beta = lw.norm2_b;
+        c.out(g.epi, b.hout, 0, D);
+      } else {
+        c.out(g.epi, b.z2, 0, D);
+      }
       SPK_TRY(gemm_run(g, st));
     }
-    SPK_TRY(ln_fwd(c.ptr(b.z2), b.z2.ps, P, 1, lw.norm2_w, lw.norm2_b, c.ptr(b.hout), b.hout.ps, P, c.f32(b.st2), Mt, st));
+    if (!fuse_ln)
+      SPK_TRY(ln_fwd(c.ptr(b.z2), b.z2.ps, P, 1, lw.norm2_w, lw.norm2_b, c.ptr(b.hout), b.hout.ps, P, c.f32(b.st2), Mt, st));
   }
   if (pl.prune) {
     // ---- last layer: only the t = 0 query row of every slice is consumed (Modules.py:54)

@@ -17,6 +17,7 @@ int encoder_debug_layout(const spk_encoder_config& c, int B, int T, int S, int P
 void encoder_set_prune(bool on);
 void encoder_set_fused_attn(bool on);
 void encoder_set_infer_attn_two(int on);
+void encoder_set_fuse_ln(int on);
 void encoder_set_fused_train_attn(bool on);
 int encoder_plan_flags();
 void encoder_set_grad_scale_log2(int k);

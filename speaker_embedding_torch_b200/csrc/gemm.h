@@ -31,7 +31,9 @@ enum : uint32_t {
   EPI_OUT_ATOMIC = 1u << 9,  // fp32 atomicAdd (split-K weight gradients)
   EPI_EMIT_BITS = 1u << 10,  // gate_bits[col/32, row]: bit i set iff v[col0 + i] > 0   (forward: ReLU mask for the backward;
                              // with EPI_PE the mask is taken right after the ReLU, otherwise after dropout)
-  EPI_GATE_BITS = 1u << 11   // v = bit ? v * gate_scale : 0 from gate_bits (ReLU backward, 1 bit per element)
+  EPI_GATE_BITS = 1u << 11,  // v = bit ? v * gate_scale : 0 from gate_bits (ReLU backward, 1 bit per element)
+  EPI_LN = 1u << 12          // out = LayerNorm(v) * ln_gamma + ln_beta over the row (after bias / dropout / residual):
+                             // needs N == 256 (one tile owns whole rows), an unbatched problem and split-plane output
 };
 
 struct GemmEpilogue {
@@ -55,6 +57,10 @@ struct GemmEpilogue {
   int gate_planes = 1;
   float gate_scale = 1.f;
   uint32_t* gate_bits = nullptr;   // [N / 32, M] words, chunk-major (N % 32 == 0, unbatched): EPI_EMIT_BITS writes, EPI_GATE_BITS reads
+  // fused LayerNorm over the N = 256 columns of every output row (EPI_LN)
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float ln_eps = 1e-5f;
   // fused column sums (fp32, atomically accumulated); colsum_sb0: elements per batch index i0
   float* colsum = nullptr;
   int64_t colsum_sb0 = 0;

@@ -381,6 +381,107 @@ __device__ __forceinline__ void epilogue32(const GemmEpilogue& e, uint32_t stage
   }
 }
 
+__device__ __forceinline__ void tmem_st_32x32_acc(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+      "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]),
+      "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]),
+      "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+
+// EPI_LN: the tile owns whole rows (N == BLOCK_N == 256).  Pass A: every warp turns its chunks of the accumulator into
+// z = alpha * acc + bias (+ dropout) + residual, keeps the row's partial sum / sum of squares and writes z BACK into
+// tensor memory; the EPI_CG warps of a lane quarter exchange their partial sums through their staging tiles (named
+// barrier per quarter); pass B re-reads z, normalises, applies gamma / beta and stores the planes.  z never reaches
+// global memory and the separate LayerNorm pass over the tensor disappears (inference: 12 % of the forward).
+template <int BLOCK_N>
+__device__ __forceinline__ void ln_epilogue_tile(const GemmEpilogue& e, uint32_t stage_buf, uint32_t bias_buf, int lane,
+                                                 int cgroup, int quarter, uint32_t t_row, int M, int N, int64_t row0,
+                                                 int64_t batch, int64_t out_boff, int64_t res_boff, float alpha) {
+  const CoopIO io_out = make_coop(lane, out_boff, row0, e.out_ld, M, 8);
+  const bool has_res = (e.flags & EPI_RES) != 0;
+  const CoopIO io_res = has_res ? make_coop(lane, res_boff, row0, e.res_ld, M, 8) : io_out;
+  const bool use_drop = (e.flags & EPI_DROPOUT) && e.drop.thresh != 0;
+  const int64_t row = row0 + lane;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+  for (int c = cgroup; c < BLOCK_N / 32; c += EPI_CG) {
+    const int col0 = c * 32;
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c * 32, r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = alpha * __uint_as_float(r[i]);
+    if (e.flags & EPI_BIAS) {
+      const uint32_t bias_s = bias_buf + (c / EPI_CG) * 128;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_s + i * 16));
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    }
+    if (use_drop) {
+      const uint64_t idx = (static_cast<uint64_t>(batch) * M + row) * N + col0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float k8[8];
+        dropout_scale8(e.drop.seed, e.drop_site, (idx >> 3) + q, e.drop.thresh, e.drop.inv_keep, k8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[q * 8 + i] *= k8[i];
+      }
+    }
+    if (has_res) {
+      float rr[32];
+      load_aux_tile(stage_buf, lane, e.res, e.res_plane_stride, e.res_planes, io_res, col0, N, rr);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += rr[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+    tmem_st_32x32_acc(t_row + c * 32, v);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  // the quarter's EPI_CG warps meet: partial sums through the (currently idle) staging tiles
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_buf + lane * 8), "f"(s1), "f"(s2) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(quarter + 1), "r"(32 * EPI_CG) : "memory");
+  float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+  for (int g = 0; g < EPI_CG; ++g) {
+    float a, b;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b)
+                 : "r"(stage_buf + (g - cgroup) * 4 * (EPI_STAGE_BYTES + EPI_BIAS_BYTES) + lane * 8) : "memory");
+    t1 += a; t2 += b;
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(quarter + 1), "r"(32 * EPI_CG) : "memory");   // read before the tiles are reused
+  const float mean = t1 * (1.f / BLOCK_N);
+  const float var = fmaxf(t2 * (1.f / BLOCK_N) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + e.ln_eps);
+#pragma unroll 1
+  for (int c = cgroup; c < BLOCK_N / 32; c += EPI_CG) {
+    const int col0 = c * 32;
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c * 32, r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.ln_gamma + col0 + i));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.ln_beta + col0 + i));
+      v[i] = (__uint_as_float(r[i]) - mean) * rstd * g4.x + b4.x;
+      v[i + 1] = (__uint_as_float(r[i + 1]) - mean) * rstd * g4.y + b4.y;
+      v[i + 2] = (__uint_as_float(r[i + 2]) - mean) * rstd * g4.z + b4.z;
+      v[i + 3] = (__uint_as_float(r[i + 3]) - mean) * rstd * g4.w + b4.w;
+    }
+    store_split_tile(stage_buf, lane, e.out, e.out_plane_stride, e.out_planes, io_out, col0, N, v);
+  }
+}
+
 // All 32-column chunks of one accumulator tile that belong to this warp.
 template <uint32_t CT, int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t stage_buf, uint32_t bias_buf, int lane, int cgroup,
@@ -416,7 +517,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& e, uint32_t st
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
+// LN = true: the instantiation whose ONLY epilogue is the fused LayerNorm (EPI_LN); it is a kernel of its own so that the
+// extra code and registers do not touch the other epilogues (built into the common kernel it cost them 2 %).
+template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N, bool LN = false>
 __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(const __grid_constant__ GemmKernelArgs args) {
   using Cfg = TileCfg<PLANES, BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
@@ -594,6 +697,11 @@ __global__ void __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1) gemm_tc_kernel(co
       const int64_t res_boff = i0 * e.res_sb0 + i1 * e.res_sb1;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BLOCK_N;
       const int64_t cs_boff = i0 * e.colsum_sb0;
+      if constexpr (LN) {
+        if (row0 < args.M)
+          ln_epilogue_tile<BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, w, t_row, args.M, args.N, row0, t, out_boff, res_boff,
+                                    alpha);
+      } else
       if (row0 < args.M) {   // warp-uniform
         constexpr uint32_t CT_LEAN = EPI_BIAS | EPI_RELU | EPI_OUT_F32;
         // the bit-mask classes only exist in the multi-plane kernels: the one-plane (inference) kernels stay small
@@ -996,6 +1104,23 @@ static int configure_all() {
   });
 }
 
+template <int PLANES>
+static int launch_ln(const GemmKernelArgs& args, int grid, cudaStream_t stream) {
+  using Cfg = TileCfg<PLANES, 256>;
+  auto kern = gemm_tc_kernel<false, false, PLANES, 256, true>;
+  static PerDeviceOnce once;
+  SPK_TRY(once.run([&]() -> int {
+    SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cudaFuncAttributes fa;
+    SPK_CUDA(cudaFuncGetAttributes(&fa, kern));
+    SPK_CHECK(fa.numRegs == LAUNCH_REGS, "gemm LN kernel was built with %d registers/thread, expected %d", fa.numRegs, LAUNCH_REGS);
+    return 0;
+  }));
+  kern<<<grid, 128 + 32 * NUM_EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(args);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <bool A_MN, bool B_MN, int PLANES, int BLOCK_N>
 static int launch(const GemmKernelArgs& args, int grid, cudaStream_t stream) {
   using Cfg = TileCfg<PLANES, BLOCK_N>;
@@ -1071,10 +1196,17 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
 
   SPK_TRY(configure_all());
 
+  if (p.epi.flags & EPI_LN)
+    SPK_CHECK(p.N == 256 && p.nb0 * p.nb1 == 1 && p.ksplit <= 1 && p.epi.ln_gamma != nullptr && p.epi.ln_beta != nullptr &&
+                  !p.a_mn && !p.b_mn && p.planes <= 2 &&
+                  !(p.epi.flags & (EPI_OUT_F32 | EPI_OUT_ATOMIC | EPI_RELU | EPI_PE | EPI_COLSUM | EPI_GATE_BITS |
+                                   EPI_GATE_POS | EPI_EMIT_BITS | EPI_ACC_GATES_AUX)),
+              "gemm: the fused LayerNorm needs N == 256, an unbatched problem and a bias / dropout / residual epilogue");
   // Problems with few rows (the pruned last layer: M = slices) are latency-bound: 256-wide tiles would put them on 8-32
   // CTAs that each walk the whole K loop; 64-wide single-CTA tiles spread the same work over 4x as many SMs.
   int req_bn = p.block_n;
   if (req_bn == 0 && !p.a_mn && p.ksplit <= 1 && p.nb0 * p.nb1 == 1 && p.M <= 2048 && p.N >= 128) req_bn = 64;
+  if (p.epi.flags & EPI_LN) req_bn = 256;      // the fused LayerNorm runs in its own single-CTA instantiation
 
   // CTA-pair path: K-major A, two or three planes, no split-K, 256-wide N tiles
   if (g_cta_pairs && !p.a_mn && p.planes >= 2 && p.ksplit <= 1 && req_bn == 0 && p.N % 128 == 0 && p.M >= 256) {
@@ -1146,6 +1278,7 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
   if (p.epi.flags & (EPI_RES | EPI_ACC_GATES_AUX)) bytes += nb * p.M * p.N * 2.0 * p.epi.res_planes;
   if (p.epi.flags & EPI_GATE_POS) bytes += nb * p.M * p.N * 2.0 * p.epi.gate_planes;
   ProfScope prof(p.tag, 2.0 * nb * p.M * p.N * p.K, bytes, stream);
+  if (p.epi.flags & EPI_LN) return p.planes == 1 ? launch_ln<1>(a, grid, stream) : launch_ln<2>(a, grid, stream);
   if (p.planes == 1) return launch_major<1>(p.a_mn, p.b_mn, bn, a, grid, stream);
   if (p.planes == 2) return launch_major<2>(p.a_mn, p.b_mn, bn, a, grid, stream);
   return launch_major<3>(p.a_mn, p.b_mn, bn, a, grid, stream);
