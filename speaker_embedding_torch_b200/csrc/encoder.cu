@@ -85,8 +85,9 @@ static bool g_prune_last = true;   // spk_set_option("prune_last_layer", 0/1)
 void encoder_set_prune(bool on) { g_prune_last = on; }
 static bool g_fused_attn = true;   // spk_set_option("fused_inference_attention", 0/1)
 static bool g_infer_attn_two = true;   // spk_set_option("inference_attention_two_ctas", 0/1)
-static bool g_fuse_ln = true;          // spk_set_option("fused_layernorm", 0/1)
-void encoder_set_fuse_ln(int on) { g_fuse_ln = on != 0; }
+static bool g_fuse_ln = true;          // spk_set_option("fused_layernorm", 0 | 1 | 2): 0 off, 1 inference only,
+static bool g_fuse_ln_train = true;    // 2 (default) the two-plane training forward as well
+void encoder_set_fuse_ln(int on) { g_fuse_ln = on != 0; g_fuse_ln_train = on >= 2; }
 void encoder_set_infer_attn_two(int on) { g_infer_attn_two = on != 0; }
 void encoder_set_fused_attn(bool on) { g_fused_attn = on; }
 static bool g_fused_train_attn = true;   // spk_set_option("fused_training_attention", 0/1)
@@ -624,9 +625,9 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
     SPK_TRY(gemm_run(g, st));
   }
   const int dense_layers = pl.prune ? pl.L - 1 : pl.L;
-  // inference (nothing kept for a backward pass): both LayerNorms of the dense layers run inside the out-proj / FFN2
-  // epilogues (EPI_LN); training keeps the separate pass because the backward needs z and the row statistics
-  const bool fuse_ln = !keep && g_fuse_ln;
+  // both LayerNorms of the dense layers run inside the out-proj / FFN2 epilogues (EPI_LN); a training forward also
+  // stores the pre-normalisation rows and the row statistics the backward needs
+  const bool fuse_ln = g_fuse_ln && (!keep || (g_fuse_ln_train && P == 2));
   for (int l = 0; l < dense_layers; ++l) {
     const LayerBufs& b = pl.Lb[l];
     const Split& hin = (l == 0) ? pl.h0 : pl.Lb[l - 1].hout;
@@ -688,6 +689,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       if (fuse_ln) {   // inference: LayerNorm1 inside the epilogue (the tile owns whole rows), z1 never leaves the SM
         g.epi.flags |= EPI_LN; g.epi.ln_gamma = lw.norm1_w; g.epi.ln_beta = lw.norm1_b;
         c.out(g.epi, b.h1, 0, D);
+        if (keep) { g.epi.ln_z = c.ptr(b.z1); g.epi.ln_z_plane_stride = b.z1.ps; g.epi.ln_stats = c.f32(b.st1); }
       } else {
         c.out(g.epi, b.z1, 0, D);
       }
@@ -722,6 +724,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
       if (fuse_ln) {
         g.epi.flags |= EPI_LN; g.epi.ln_gamma = lw.norm2_w; g.epi.ln_beta = lw.norm2_b;
         c.out(g.epi, b.hout, 0, D);
+        if (keep) { g.epi.ln_z = c.ptr(b.z2); g.epi.ln_z_plane_stride = b.z2.ps; g.epi.ln_stats = c.f32(b.st2); }
       } else {
         c.out(g.epi, b.z2, 0, D);
       }

@@ -61,6 +61,9 @@ struct GemmEpilogue {
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   float ln_eps = 1e-5f;
+  void* ln_z = nullptr;            // optional: the pre-normalisation rows (split planes, laid out like `out`) for a backward pass
+  int64_t ln_z_plane_stride = 0;
+  float* ln_stats = nullptr;       // optional: (mean, rstd) per row, [M] float2
   // fused column sums (fp32, atomically accumulated); colsum_sb0: elements per batch index i0
   float* colsum = nullptr;
   int64_t colsum_sb0 = 0;

@@ -445,6 +445,8 @@ __device__ __forceinline__ void ln_epilogue_tile(const GemmEpilogue& e, uint32_t
 #pragma unroll
     for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
     tmem_st_32x32_acc(t_row + c * 32, v);
+    if (e.ln_z != nullptr)      // training: the backward pass needs the pre-normalisation rows (v is consumed by the split)
+      store_split_tile(stage_buf, lane, e.ln_z, e.ln_z_plane_stride, e.out_planes, io_out, col0, N, v);
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   // the quarter's EPI_CG warps meet: partial sums through the (currently idle) staging tiles
@@ -462,6 +464,7 @@ __device__ __forceinline__ void ln_epilogue_tile(const GemmEpilogue& e, uint32_t
   const float mean = t1 * (1.f / BLOCK_N);
   const float var = fmaxf(t2 * (1.f / BLOCK_N) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + e.ln_eps);
+  if (e.ln_stats != nullptr && cgroup == 0 && row < M) reinterpret_cast<float2*>(e.ln_stats)[row] = make_float2(mean, rstd);
 #pragma unroll 1
   for (int c = cgroup; c < BLOCK_N / 32; c += EPI_CG) {
     const int col0 = c * 32;
@@ -760,7 +763,7 @@ struct PairCfg {
   static_assert(2 * BLOCK_N <= 512 && BLOCK_N % 128 == 0, "pair tile N");
 };
 
-template <bool B_MN, int PLANES, int BLOCK_N>
+template <bool B_MN, int PLANES, int BLOCK_N, bool LN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_WARPS, 1)
     gemm_pair_kernel(const __grid_constant__ GemmKernelArgs args) {
   using Cfg = PairCfg<PLANES, BLOCK_N>;
@@ -954,6 +957,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NUM_EPI_W
       const int64_t res_boff = i0 * e.res_sb0 + i1 * e.res_sb1;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BLOCK_N;
       const int64_t cs_boff = i0 * e.colsum_sb0;
+      if constexpr (LN) {
+        if (row0 < args.M)
+          ln_epilogue_tile<BLOCK_N>(e, stage_buf, bias_buf, lane, cgroup, w, t_row, args.M, args.N, row0, t, out_boff, res_boff,
+                                    alpha);
+      } else
       if (row0 < args.M) {   // warp-uniform
         constexpr uint32_t CT_LEAN = EPI_BIAS | EPI_RELU | EPI_OUT_F32;
         // the bit-mask classes only exist in the multi-plane kernels: the one-plane (inference) kernels stay small
@@ -1133,10 +1141,10 @@ static int launch(const GemmKernelArgs& args, int grid, cudaStream_t stream) {
 static int g_cta_pairs = 1;            // spk_set_option("gemm_cta_pairs", 0/1)
 void gemm_set_cta_pairs(int on) { g_cta_pairs = on; }
 
-template <bool B_MN, int PLANES, int BLOCK_N>
+template <bool B_MN, int PLANES, int BLOCK_N, bool LN = false>
 static int launch_pair(const GemmKernelArgs& args, int pairs, cudaStream_t stream) {
   using Cfg = PairCfg<PLANES, BLOCK_N>;
-  auto kern = gemm_pair_kernel<B_MN, PLANES, BLOCK_N>;
+  auto kern = gemm_pair_kernel<B_MN, PLANES, BLOCK_N, LN>;
   static PerDeviceOnce once;
   SPK_TRY(once.run([&]() -> int {
     SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -1206,7 +1214,8 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
   // CTAs that each walk the whole K loop; 64-wide single-CTA tiles spread the same work over 4x as many SMs.
   int req_bn = p.block_n;
   if (req_bn == 0 && !p.a_mn && p.ksplit <= 1 && p.nb0 * p.nb1 == 1 && p.M <= 2048 && p.N >= 128) req_bn = 64;
-  if (p.epi.flags & EPI_LN) req_bn = 256;      // the fused LayerNorm runs in its own single-CTA instantiation
+  const bool ln_pair = (p.epi.flags & EPI_LN) && p.planes == 2 && p.M > 2048 && g_cta_pairs;
+  if ((p.epi.flags & EPI_LN) && !ln_pair) req_bn = 256;      // the fused LayerNorm runs in its own instantiations
 
   // CTA-pair path: K-major A, two or three planes, no split-K, 256-wide N tiles
   if (g_cta_pairs && !p.a_mn && p.planes >= 2 && p.ksplit <= 1 && req_bn == 0 && p.N % 128 == 0 && p.M >= 256) {
@@ -1236,6 +1245,7 @@ int gemm_run(const GemmProblem& p, cudaStream_t stream) {
     if (p.epi.flags & (EPI_RES | EPI_ACC_GATES_AUX)) bytes += nb * p.M * p.N * 2.0 * p.epi.res_planes;
     if (p.epi.flags & EPI_GATE_POS) bytes += nb * p.M * p.N * 2.0 * p.epi.gate_planes;
     ProfScope prof(p.tag, 2.0 * nb * p.M * p.N * p.K, bytes, stream);
+    if (p.epi.flags & EPI_LN) return launch_pair<false, 2, BN, true>(a, pairs, stream);
     if (p.planes == 3) {
       if (p.b_mn) return launch_pair<true, 3, BN>(a, pairs, stream);
       return launch_pair<false, 3, BN>(a, pairs, stream);
