@@ -627,7 +627,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
   const int dense_layers = pl.prune ? pl.L - 1 : pl.L;
   // both LayerNorms of the dense layers run inside the out-proj / FFN2 epilogues (EPI_LN); a training forward also
   // stores the pre-normalisation rows and the row statistics the backward needs
-  const bool fuse_ln = g_fuse_ln && (!keep || (g_fuse_ln_train && P == 2));
+  const bool fuse_ln = g_fuse_ln && P <= 2 && (!keep || (g_fuse_ln_train && P == 2));   // EPI_LN kernels exist for 1 and 2 planes
   for (int l = 0; l < dense_layers; ++l) {
     const LayerBufs& b = pl.Lb[l];
     const Split& hin = (l == 0) ? pl.h0 : pl.Lb[l - 1].hout;

@@ -383,3 +383,28 @@ def test_device_collation_equals_the_host_collated_forward(golden_dir, case):
     assert float((grads[0][1] - grads[1][1]).norm() / grads[1][1].norm()) < 1e-5     # fp32 atomics reorder only
     with pytest.raises(RuntimeError):
         m(ragged)                                                        # host tensors: no CPU path
+
+
+@pytest.mark.parametrize("precision,min_cos", [(1, 0.9999), (2, 1 - 1e-9), (3, 1 - 1e-9)])
+def test_inference_at_every_precision_against_the_oracle(precision, min_cos):
+    """eval_precision 1 / 2 run the fused-LayerNorm GEMM instantiations (one / two planes), 3 the separate LayerNorm pass;
+    all against the fp64 oracle, and the fused path against the unfused one."""
+    from speaker_embedding_torch_b200 import _native
+    m, state = _model(5)
+    m.eval()
+    m.eval_precision = precision
+    mel = synth.make_mel(77, 24, 150)
+    st = {k: torch.as_tensor(v).double() for k, v in state.items()}
+    ref = O.encoder_forward(st, torch.as_tensor(mel).double()).numpy()
+    out = {}
+    try:
+        for fused in (1, 0):
+            _native.set_option("fused_layernorm", 2 * fused)
+            with torch.no_grad():
+                out[fused] = m(torch.as_tensor(mel).cuda()).double().cpu().numpy()
+    finally:
+        _native.set_option("fused_layernorm", 2)
+    for d in out.values():
+        cos = (d * ref).sum(1) / (np.linalg.norm(d, axis=1) * np.linalg.norm(ref, axis=1))
+        assert cos.min() >= min_cos, cos.min()
+    assert np.abs(out[1] - out[0]).max() <= (5e-4 if precision == 1 else 2e-6)
