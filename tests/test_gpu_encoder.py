@@ -408,3 +408,30 @@ def test_inference_at_every_precision_against_the_oracle(precision, min_cos):
         cos = (d * ref).sum(1) / (np.linalg.norm(d, axis=1) * np.linalg.norm(ref, axis=1))
         assert cos.min() >= min_cos, cos.min()
     assert np.abs(out[1] - out[0]).max() <= (5e-4 if precision == 1 else 2e-6)
+
+
+@pytest.mark.parametrize("train", [False, True])
+@pytest.mark.parametrize("frames", [24, 160])
+def test_fused_layernorm_training_forward_matches_the_separate_pass(frames, train):
+    """EPI_LN in the training forward (z planes and row statistics written by the GEMM epilogue) against GEMM + ln_fwd:
+    same d-vectors, same gradients (the backward reads the stashed z / statistics of either path)."""
+    from speaker_embedding_torch_b200 import GE2E_Loss, _native
+    nspk, utt = 3, 2
+    mel = torch.as_tensor(synth.make_mel(900 + frames, nspk * utt, frames)).cuda()
+    res = {}
+    try:
+        for level in (2, 1):
+            _native.set_option("fused_layernorm", level)
+            m, _ = _model(46)
+            m.train(train)
+            crit = GE2E_Loss().cuda()
+            torch.manual_seed(78)
+            d = m(mel)
+            crit(d, utt).backward()
+            torch.cuda.synchronize()
+            res[level] = (d.detach().clone(), torch.cat([p.grad.flatten() for p in m.parameters()]).clone())
+    finally:
+        _native.set_option("fused_layernorm", 2)
+    torch.testing.assert_close(res[2][0], res[1][0], atol=3e-6, rtol=0)
+    rel = float((res[2][1] - res[1][1]).double().norm() / res[1][1].double().norm())
+    assert rel <= 2e-3, rel       # typically ~1e-5; the bound leaves room for one ReLU gate (see the fused-attention test)
