@@ -11,6 +11,7 @@ using namespace spk;
 
 namespace spk {
 void attn_train_set_timeline(void* buf, size_t bytes);   // attn_train.cu
+void attn_train_set_fwd_two(int on);                        // attn_train.cu
 }
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -132,6 +133,7 @@ int spk_split_pack(const float* src, void* dst, int64_t plane_stride, int planes
 int spk_set_option(const char* name, int value) {
   SPK_CHECK(name != nullptr, "spk_set_option: null name");
   if (strcmp(name, "prune_last_layer") == 0) { encoder_set_prune(value != 0); return 0; }
+  if (strcmp(name, "training_attention_two_ctas") == 0) { attn_train_set_fwd_two(value); return 0; }
   if (strcmp(name, "fused_inference_attention") == 0) { encoder_set_fused_attn(value != 0); return 0; }
   if (strcmp(name, "inference_attention_two_ctas") == 0) { encoder_set_infer_attn_two(value); return 0; }
   if (strcmp(name, "fused_layernorm") == 0) { encoder_set_fuse_ln(value); return 0; }

@@ -361,6 +361,12 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __
   }
 }
 
+// two-CTAs-per-SM variant of the two-plane forward (defined below)
+constexpr int ATW_KV_ROWS = 192;
+static int g_attn_fwd_two = 1;     // spk_set_option("training_attention_two_ctas", 0/1)
+void attn_train_set_fwd_two(int on) { g_attn_fwd_two = on; }
+static int attn_train_fwd2_launch(AttnTrainFwdArgs& a, const elem_t* qkv, int64_t qkv_ps, cudaStream_t st);
+
 int attn_train_max_frames(int planes) { return planes == 3 ? AtfCfg<3>::KV_ROWS : AtfCfg<2>::KV_ROWS; }
 
 template <int PL>
@@ -409,7 +415,261 @@ int attn_train_fwd(const void* qkv, int64_t qkv_ps, int planes, void* out, int64
   // algorithmic work: QK^T and PV (16-bit dense count); bytes: Q, K, V in, O out
   ProfScope prof("attn_train_fwd", 4.0 * B * H * T * T * 64, 4.0 * B * T * 64 * H * 2.0 * planes, st);
   if (planes == 3) return attn_train_fwd_launch<3>(a, reinterpret_cast<const elem_t*>(qkv), qkv_ps, st);
+  if (g_attn_fwd_two && T <= ATW_KV_ROWS) return attn_train_fwd2_launch(a, reinterpret_cast<const elem_t*>(qkv), qkv_ps, st);
   return attn_train_fwd_launch<2>(a, reinterpret_cast<const elem_t*>(qkv), qkv_ps, st);
+}
+
+// =====================================================================================================================
+// Two-CTAs-per-SM variant of the training forward (two planes, T <= 192).  Same arithmetic as attn_train_fwd_kernel<2>;
+// what changes is the footprint: 8 compute warps, 256 TMEM columns (S | P in place at 0, O at 192) and ONE operand buffer
+// that holds K for the score MMAs and is then reloaded with V for the PV MMAs (K and V are needed at different times),
+// so a CTA fits in 99 KB and two of them share an SM: one item's softmax runs under the other item's loads and MMAs.
+// K is fetched again for the second query tile of an item (an L2 hit).
+__device__ __forceinline__ void half_quarter_sync(int quarter) {   // the two warps that share a TMEM lane quarter
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+}
+constexpr int ATW_CW = 8, ATW_THREADS = 128 + 32 * ATW_CW;
+constexpr int ATW_Q_BYTES = 16384, ATW_KV_BYTES = ATW_KV_ROWS * 128;
+constexpr int ATW_OFF_KV = 2 * ATW_Q_BYTES, ATW_OFF_X = ATW_OFF_KV + 2 * ATW_KV_BYTES, ATW_OFF_STG = ATW_OFF_X + 2048;
+constexpr int ATW_OFF_BAR = ATW_OFF_STG + 16384, ATW_SMEM = ATW_OFF_BAR + 128;
+constexpr int ATW_TMEM_O = 192;
+
+__global__ void __launch_bounds__(ATW_THREADS, 2) attn_train_fwd2_kernel(const __grid_constant__ AttnTrainFwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t sQ = sbase, sKV = sbase + ATW_OFF_KV;
+  float* xch = reinterpret_cast<float*>(smem_raw + ATW_OFF_X);   // [0..255] max parts, [256..511] sum parts
+  const uint32_t bar_qk = sbase + ATW_OFF_BAR, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_p = bar_qk + 24,
+                 bar_o = bar_qk + 32, bar_oe = bar_qk + 40, tmem_slot = bar_qk + 56;
+  // every barrier completes exactly once per (item, query tile) unit and every waiter waits once per unit
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sbase & 1023u) != 0) __trap();
+  if (warp == 0 && lane == 0) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) { tma_prefetch_desc(&a.q_map[p]); tma_prefetch_desc(&a.k_map[p]); tma_prefetch_desc(&a.v_map[p]); }
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 32 * ATW_CW); mbar_init(bar_o, 1);
+    mbar_init(bar_oe, 32 * ATW_CW);
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tO = tmem_base + ATW_TMEM_O;
+  const int items = a.B * a.H;
+  const int kv_plane = a.Tk64 * 128;      // bytes actually loaded per K / V plane
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t u = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int h = item % a.H, b = item / a.H;
+        for (int mt = 0; mt < a.mtiles; ++mt, ++u) {
+          if (u > 0) mbar_wait(bar_o, (u - 1) & 1u, 0x670u);      // previous PV retired: the operand buffer (V) and Q are free
+          mbar_arrive_expect_tx(bar_qk, 2u * ATW_Q_BYTES + 2u * kv_plane);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            tma_load_4d(sQ + p * ATW_Q_BYTES, &a.q_map[p], bar_qk, 0, mt * 128, h, b);
+            tma_load_4d(sKV + p * ATW_KV_BYTES, &a.k_map[p], bar_qk, 0, 0, h, b);
+          }
+          mbar_wait(bar_s, u & 1u, 0x671u);                        // score MMAs retired: K is dead, V takes its place
+          mbar_arrive_expect_tx(bar_v, 2u * kv_plane);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) tma_load_4d(sKV + p * ATW_KV_BYTES, &a.v_map[p], bar_v, 0, 0, h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = umma_idesc_f16(128, a.Tk16, false, false);
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);
+    constexpr int PA2[3] = {1, 0, 0}, PB2[3] = {0, 1, 0};         // lo*hi, hi*lo, hi*hi
+    const uint64_t dQ0 = umma_smem_desc(sQ, 16, 1024), dK0 = umma_smem_desc(sKV, 16, 1024);
+    const uint64_t dV0 = umma_smem_desc(sKV, 8192, 1024);
+    const int ksteps = a.Tk16 / 16;
+    uint32_t u = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int mt = 0; mt < a.mtiles; ++mt, ++u) {
+        mbar_wait(bar_qk, u & 1u, 0x680u);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tS, desc_add(dQ0, PA2[cb] * ATW_Q_BYTES + k * 32), desc_add(dK0, PB2[cb] * ATW_KV_BYTES + k * 32), idesc_s,
+                        (cb | k) ? 1u : 0u);
+          }
+          umma_commit(bar_s);
+        }
+        __syncwarp();
+        mbar_wait(bar_p, u & 1u, 0x681u);                          // probabilities are in TMEM
+        mbar_wait(bar_v, u & 1u, 0x682u);                          // V is in the operand buffer
+        if (u > 0) mbar_wait(bar_oe, (u - 1) & 1u, 0x683u);        // previous output tile drained
+        tc_fence_after();
+        if (elect_one()) {
+          for (int t = 0; t < ksteps; ++t) {
+            const uint32_t voff = (t >> 2) * 8192 + (t & 3) * 2048;
+#pragma unroll
+            for (int cb = 0; cb < 3; ++cb)
+              umma_f16_ts(tO, tS + 16 * t + 8 * PA2[cb], desc_add(dV0, PB2[cb] * ATW_KV_BYTES + voff), idesc_o, (t | cb) ? 1u : 0u);
+          }
+          umma_commit(bar_o);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    const int w = (warp - 4) & 3, part = (warp - 4) >> 2;          // lane quarter, column part (0..1)
+    const int r = w * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(w * 32) << 16;
+    const bool use_drop = a.drop.thresh != 0;
+    const float inv_keep = use_drop ? a.drop.inv_keep : 1.f;
+    const int nchunks = a.Tk16 / 16;
+    uint32_t u = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int h = item % a.H, b = item / a.H;
+      for (int mt = 0; mt < a.mtiles; ++mt, ++u) {
+        const uint32_t ph = u & 1u;
+        const int q = mt * 128 + r;
+        const bool active = mt * 128 + w * 32 < a.T;              // warp-uniform
+        mbar_wait(bar_s, ph, 0x690u);
+        tc_fence_after();
+        uint32_t sreg[16];
+        float mx = -INFINITY;
+        if (active) {
+          for (int c = part; c * 16 < a.T; c += 2) {
+            tmem_ld_32x16(tS + t_lane + c * 16, sreg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c * 16 + i < a.T) mx = fmaxf(mx, __uint_as_float(sreg[i]));
+          }
+        }
+        xch[part * 128 + r] = mx;
+        half_quarter_sync(w);
+        mx = fmaxf(xch[r], xch[128 + r]);
+        const float mxs = mx * ATF_SC;
+        float sum = 0.f;
+        if (active) {
+          const uint64_t row_idx8 = ((static_cast<uint64_t>(item) * a.T + q) * a.Tp) >> 3;   // Tp % 8 == 0
+          for (int c = part; c < nchunks; c += 2) {
+            tmem_ld_32x16(tS + t_lane + c * 16, sreg);
+            uint32_t keep = 0xFFFFu;
+            if (use_drop)
+              keep = dropout_keep8(a.drop.seed, a.site, row_idx8 + 2 * c, a.drop.thresh) |
+                     (dropout_keep8(a.drop.seed, a.site, row_idx8 + 2 * c + 1, a.drop.thresh) << 8);
+            tmem_ld_wait();
+            uint32_t o01[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int key = c * 16 + 2 * j;
+              float e0 = key < a.T ? at_exp2(__uint_as_float(sreg[2 * j]) * ATF_SC - mxs) : 0.f;
+              float e1 = key + 1 < a.T ? at_exp2(__uint_as_float(sreg[2 * j + 1]) * ATF_SC - mxs) : 0.f;
+              sum += e0 + e1;
+              e0 = ((keep >> (2 * j)) & 1u) ? e0 : 0.f;
+              e1 = ((keep >> (2 * j + 1)) & 1u) ? e1 : 0.f;
+              const uint32_t hi = pack2(e0, e1);
+              o01[j] = hi;                                                // plane 0 at columns 16c + j
+              e0 -= lo_to_f(hi);
+              e1 -= hi_to_f(hi);
+              o01[8 + j] = pack2(e0, e1);                                 // plane 1 at columns 16c + 8 + j
+            }
+            tmem_st_32x16(tS + t_lane + c * 16, o01);
+            if (a.mbits != nullptr && q < a.T)
+              a.mbits[(static_cast<int64_t>(item) * a.nC + c) * a.T + q] = static_cast<uint16_t>(keep);
+          }
+          tmem_st_wait();
+        }
+        xch[256 + part * 128 + r] = sum;
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        half_quarter_sync(w);
+        sum = xch[256 + r] + xch[384 + r];
+        mbar_wait(bar_o, ph, 0x691u);
+        tc_fence_after();
+        float v[32];
+        if (active) {
+          uint32_t oreg[16];
+          const float sc = inv_keep / sum;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            tmem_ld_32x16(tO + t_lane + part * 32 + hlf * 16, oreg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[hlf * 16 + i] = __uint_as_float(oreg[i]) * sc;
+          }
+          if (part == 0 && q < a.T && a.stats != nullptr) a.stats[static_cast<int64_t>(item) * a.T + q] = make_float2(mxs, sum);
+        }
+        tc_fence_before();
+        mbar_arrive(bar_oe);                                      // the accumulator is free for the next tile's PV
+        if (active) {                                             // uniform over the quarter's two warps
+          const uint32_t stg = sbase + ATW_OFF_STG;
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {                         // this warp's 32 columns = 16-byte chunks 4 part .. 4 part + 3
+              uint32_t wv[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                wv[i] = pack2(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
+                if (p == 0) {
+                  v[g * 8 + 2 * i] -= lo_to_f(wv[i]);
+                  v[g * 8 + 2 * i + 1] -= hi_to_f(wv[i]);
+                }
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + r * 128 + (((4 * part + g) ^ (r & 7)) << 4)),
+                           "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
+            }
+            half_quarter_sync(w);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {                      // 16 of the quarter's 32 rows per warp, 4 rows per instruction
+              const int row = w * 32 + part * 16 + it * 4 + (lane >> 3);
+              uint4 val;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                           : "r"(stg + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) : "memory");
+              const int qq = mt * 128 + row;
+              if (qq < a.T)
+                *reinterpret_cast<uint4*>(a.out + p * a.out_ps + (static_cast<int64_t>(b) * a.T + qq) * a.out_ld + h * 64 +
+                                          (lane & 7) * 8) = val;
+            }
+            half_quarter_sync(w);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int attn_train_fwd2_launch(AttnTrainFwdArgs& a, const elem_t* qkv, int64_t qkv_ps, cudaStream_t st) {
+  const int64_t ld = 3 * 64 * a.H;
+  const int64_t dims[4] = {64, a.T, a.H, a.B};
+  const int64_t strides[3] = {ld, 64, static_cast<int64_t>(a.T) * ld};
+  for (int p = 0; p < 2; ++p) {
+    const elem_t* base = qkv + p * qkv_ps;
+    SPK_TRY(encode_map_4d(&a.q_map[p], base, dims, strides, 128));
+    SPK_TRY(encode_map_4d(&a.k_map[p], base + 64 * a.H, dims, strides, a.Tk64));
+    SPK_TRY(encode_map_4d(&a.v_map[p], base + 2 * 64 * a.H, dims, strides, a.Tk64));
+  }
+  static PerDeviceOnce once;
+  SPK_TRY(once.run([]() -> int {
+    SPK_CUDA(cudaFuncSetAttribute(attn_train_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATW_SMEM));
+    return 0;
+  }));
+  const int items = a.B * a.H;
+  const int grid = items < 2 * device_sm_count() ? items : 2 * device_sm_count();
+  attn_train_fwd2_kernel<<<grid, ATW_THREADS, ATW_SMEM, st>>>(a);
+  SPK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // =====================================================================================================================
@@ -420,10 +680,6 @@ constexpr int ATI_CW = 8, ATI_THREADS = 128 + 32 * ATI_CW, ATI_KV_ROWS = 192;
 constexpr int ATI_OFF_K = 16384, ATI_OFF_V = ATI_OFF_K + ATI_KV_ROWS * 128, ATI_OFF_X = ATI_OFF_V + ATI_KV_ROWS * 128;
 constexpr int ATI_OFF_STG = ATI_OFF_X + 2048, ATI_OFF_BAR = ATI_OFF_STG + 16384, ATI_SMEM = ATI_OFF_BAR + 128;
 constexpr int ATI_TMEM_O = 192;
-
-__device__ __forceinline__ void half_quarter_sync(int quarter) {   // the two warps that share a TMEM lane quarter
-  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
-}
 
 __global__ void __launch_bounds__(ATI_THREADS, 2) attn_infer_fwd_kernel(const __grid_constant__ AttnTrainFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
