@@ -240,8 +240,9 @@ int ln_fwd(const void* z, int64_t z_ps, int z_planes, int64_t z_row_step, const 
 
 // dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma ; dgamma += dy * xhat ; dbeta += dy
 // Optionally also writes dz_drop = dz * keep(site) (the gradient that enters the sub-layer's GEMMs).
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const elem_t* __restrict__ dy, int64_t dy_ps, int dy_planes,
-                                                     const elem_t* __restrict__ z, int64_t z_ps, int z_planes,
+template <int PL>
+__global__ void __launch_bounds__(256, 3) ln_bwd_kernel(const elem_t* __restrict__ dy, int64_t dy_ps, int dy_planes_rt,
+                                                        const elem_t* __restrict__ z, int64_t z_ps, int z_planes_rt,
                                                      const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                      elem_t* __restrict__ dz, int64_t dz_ps, int dz_planes,
                                                      elem_t* __restrict__ dz_drop, DropCfg drop, uint32_t site,
@@ -249,6 +250,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const elem_t* __restrict__ 
                                                      float* __restrict__ dbias, int64_t rows,
                                                      const float* __restrict__ gscale) {
   __shared__ float red[3][8][256];
+  // PL > 0: both inputs have PL planes (compile-time: fewer registers, three blocks per SM); PL == 0: run-time counts
+  const int dy_planes = PL > 0 ? PL : dy_planes_rt, z_planes = PL > 0 ? PL : z_planes_rt;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -331,7 +334,8 @@ int ln_bwd(const void* dy, int64_t dy_ps, int dy_planes, const void* z, int64_t 
            float* dgamma, float* dbeta, float* dbias, int64_t rows, const float* gscale, cudaStream_t st) {
   ProfScope prof("ln_bwd", 0, 512.0 * rows * (dy_planes + z_planes + dz_planes * (drop.thresh ? 2 : 1)), st);
   const int blocks = static_cast<int>(std::min<int64_t>((rows + 7) / 8, 148 * 6));
-  ln_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const elem_t*>(dy), dy_ps, dy_planes,
+  auto kern = (dy_planes == 2 && z_planes == 2) ? ln_bwd_kernel<2> : ln_bwd_kernel<0>;
+  kern<<<blocks, 256, 0, st>>>(reinterpret_cast<const elem_t*>(dy), dy_ps, dy_planes,
                                         reinterpret_cast<const elem_t*>(z), z_ps, z_planes,
                                         reinterpret_cast<const float2*>(stats), gamma,
                                         reinterpret_cast<elem_t*>(dz), dz_ps, dz_planes,
