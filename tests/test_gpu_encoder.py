@@ -435,3 +435,54 @@ def test_fused_layernorm_training_forward_matches_the_separate_pass(frames, trai
     torch.testing.assert_close(res[2][0], res[1][0], atol=3e-6, rtol=0)
     rel = float((res[2][1] - res[1][1]).double().norm() / res[1][1].double().norm())
     assert rel <= 2e-3, rel       # typically ~1e-5; the bound leaves room for one ReLU gate (see the fused-attention test)
+
+
+@pytest.mark.parametrize("frames", [1, 15, 16, 17, 100, 128, 129, 160, 191, 192])
+def test_two_cta_inference_attention_matches_the_one_cta_kernel(frames):
+    """attn_infer_fwd_kernel (two CTAs per SM, T <= 192) against attn_fused_fwd_kernel on the same input, and both
+    against the fp64 oracle (one fp16 plane: cosine >= 0.9999)."""
+    from speaker_embedding_torch_b200 import _native
+    m, state = _model(9)
+    m.eval()
+    mel = synth.make_mel(300 + frames, 7, frames)
+    st = {k: torch.as_tensor(v).double() for k, v in state.items()}
+    ref = O.encoder_forward(st, torch.as_tensor(mel).double()).numpy()
+    out = {}
+    try:
+        for two in (1, 0):
+            _native.set_option("inference_attention_two_ctas", two)
+            with torch.no_grad():
+                out[two] = m(torch.as_tensor(mel).cuda()).double().cpu().numpy()
+    finally:
+        _native.set_option("inference_attention_two_ctas", 1)
+    for d in out.values():
+        cos = (d * ref).sum(1) / (np.linalg.norm(d, axis=1) * np.linalg.norm(ref, axis=1))
+        assert cos.min() >= 0.9999, cos.min()
+    assert np.abs(out[1] - out[0]).max() <= 5e-4
+
+
+@pytest.mark.parametrize("frames", [1, 16, 100, 129, 160, 192])
+@pytest.mark.parametrize("train", [False, True])
+def test_two_cta_training_attention_forward_matches_the_one_cta_kernel(frames, train):
+    """attn_train_fwd2_kernel (two CTAs per SM, one operand buffer for K then V) against attn_train_fwd_kernel<2>: same
+    d-vectors, same saved statistics / keep bits (checked through the gradients of the shared backward)."""
+    from speaker_embedding_torch_b200 import GE2E_Loss, _native
+    nspk, utt = 3, 2
+    mel = torch.as_tensor(synth.make_mel(500 + frames, nspk * utt, frames)).cuda()
+    res = {}
+    try:
+        for two in (1, 0):
+            _native.set_option("training_attention_two_ctas", two)
+            m, _ = _model(47)
+            m.train(train)
+            crit = GE2E_Loss().cuda()
+            torch.manual_seed(79)
+            d = m(mel)
+            crit(d, utt).backward()
+            torch.cuda.synchronize()
+            res[two] = (d.detach().clone(), torch.cat([p.grad.flatten() for p in m.parameters()]).clone())
+    finally:
+        _native.set_option("training_attention_two_ctas", 1)
+    torch.testing.assert_close(res[1][0], res[0][0], atol=3e-6, rtol=0)
+    rel = float((res[1][1] - res[0][1]).double().norm() / res[0][1].double().norm())
+    assert rel <= 2e-3, rel
