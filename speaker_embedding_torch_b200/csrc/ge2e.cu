@@ -15,6 +15,7 @@
 // D is fixed at 256 (= Embedding_Size of the reference hyper-parameters): thread <-> column.
 #include "common.cuh"
 #include "ge2e.h"
+#include "ptx.cuh"
 
 namespace spk {
 
@@ -286,6 +287,229 @@ ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------ row-tile stage, v2
+// Same mathematics as phase 2 above, re-tiled for the shared-memory pipe (ncu of the first version: L1/shared 64 % busy on
+// the 60 SMs it used, 20 us of the 32 us call at N = 64):
+//   * 8 rows per block instead of 16 -> 120 blocks at the training size (148 SMs), two blocks per SM;
+//   * the centroid tile arrives by bulk copy (cp.async.bulk -> mbarrier), one 1 KB row per copy, while the block
+//     normalises its rows;
+//   * S tile: 2 x 2 outputs per thread, the warp covers 8 rows x 16 centroids, K split over the two warp halves of the
+//     block: 4 shared-memory wavefronts per 16 FMA instructions (was 9);
+//   * whole logit rows stay in shared memory (N < 256), warp <-> row for the log-sum-exp and G;
+//   * one sweep over the centroids feeds both dEhat (8 row accumulators, thread <-> column) and dChat (row values of the
+//     column in registers, one RED per centroid): 3 wavefronts per 16 FMA instructions (was 5 + 5).
+constexpr int RT = 8;            // rows per tile
+constexpr int EPAD = GD + 4;     // padded row: the four rows a warp reads at one d land in different banks
+constexpr int NCAP = 256;        // this path serves N < GE2E_TC_MIN_SPEAKERS
+
+struct Ge2eTileSmem {
+  float c[TC][CPAD];             // normalised centroid tile (bulk-copy destination)
+  float e[RT][EPAD];             // normalised rows
+  float s[RT][NCAP];             // cosine similarities of the whole row
+  float gt[NCAP][RT];            // G^T: the 8 row values of one centroid are two 16-byte broadcasts
+  float part[RT][TC];            // upper K half of the S tile
+  float red[8][RT];
+  float scal[3][8];
+  float rowv[RT];
+  float einv[RT];
+  unsigned long long bar;
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __restrict__ w_ptr,
+                      const float* __restrict__ b_ptr, float* __restrict__ loss, float* __restrict__ dE,
+                      float* __restrict__ dw, float* __restrict__ db, const float* __restrict__ chat,
+                      const float* __restrict__ einv, float* __restrict__ dchat, int need_grad) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Ge2eTileSmem& sm = *reinterpret_cast<Ge2eTileSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t NM = static_cast<int64_t>(N) * M;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * RT;
+  const int col_tiles = (N + TC - 1) / TC;
+  const float w = __ldg(w_ptr), b = __ldg(b_ptr);
+  const float inv_nm = 1.f / static_cast<float>(NM);
+  const uint32_t bar = smem_u32(&sm.bar);
+  uint32_t parity = 0;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // warp 0 requests centroid tile `ct`; every thread of the block has finished reading the previous tile (caller syncs)
+  auto request_tile = [&](int ct) {
+    if (warp == 0) {
+      const int c0 = ct * TC;
+      const int rows = min(TC, N - c0);
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar, static_cast<uint32_t>(rows) * GD * 4u);
+      }
+      __syncwarp();
+      for (int r = lane; r < rows; r += 32)
+        bulk_g2s(smem_u32(&sm.c[r][0]), chat + static_cast<int64_t>(c0 + r) * GD, GD * 4u, bar);
+    }
+  };
+  request_tile(0);
+
+  {  // this block's rows, normalised: warp <-> row
+    const int64_t gi = row0 + warp;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    float sc = 0.f;
+    if (gi < NM) {
+      sc = __ldg(einv + gi);
+      a0 = __ldg(reinterpret_cast<const float4*>(E + gi * GD + lane * 8));
+      a1 = __ldg(reinterpret_cast<const float4*>(E + gi * GD + lane * 8 + 4));
+    }
+    a0.x *= sc; a0.y *= sc; a0.z *= sc; a0.w *= sc;
+    a1.x *= sc; a1.y *= sc; a1.z *= sc; a1.w *= sc;
+    *reinterpret_cast<float4*>(&sm.e[warp][lane * 8]) = a0;
+    *reinterpret_cast<float4*>(&sm.e[warp][lane * 8 + 4]) = a1;
+    if (lane == 0) sm.einv[warp] = sc;
+  }
+  __syncthreads();
+
+  // ---- pass A: S = Ehat Chat^T for the whole rows
+  const int khalf = warp >> 2, wq = warp & 3, lr = lane >> 3, lc = lane & 7;
+  const int ra = lr, rb = lr + 4, ca = 16 * wq + lc, cb = ca + 8;
+  for (int ct = 0; ct < col_tiles; ++ct) {
+    mbar_wait(bar, parity, 0x6e01);
+    parity ^= 1;
+    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+    const int d0 = khalf * (GD / 2);
+#pragma unroll 8
+    for (int d = d0; d < d0 + GD / 2; d += 4) {
+      const float4 ea = *reinterpret_cast<const float4*>(&sm.e[ra][d]);
+      const float4 eb = *reinterpret_cast<const float4*>(&sm.e[rb][d]);
+      const float4 va = *reinterpret_cast<const float4*>(&sm.c[ca][d]);
+      const float4 vb = *reinterpret_cast<const float4*>(&sm.c[cb][d]);
+      s00 = fmaf(ea.x, va.x, s00); s00 = fmaf(ea.y, va.y, s00); s00 = fmaf(ea.z, va.z, s00); s00 = fmaf(ea.w, va.w, s00);
+      s01 = fmaf(ea.x, vb.x, s01); s01 = fmaf(ea.y, vb.y, s01); s01 = fmaf(ea.z, vb.z, s01); s01 = fmaf(ea.w, vb.w, s01);
+      s10 = fmaf(eb.x, va.x, s10); s10 = fmaf(eb.y, va.y, s10); s10 = fmaf(eb.z, va.z, s10); s10 = fmaf(eb.w, va.w, s10);
+      s11 = fmaf(eb.x, vb.x, s11); s11 = fmaf(eb.y, vb.y, s11); s11 = fmaf(eb.z, vb.z, s11); s11 = fmaf(eb.w, vb.w, s11);
+    }
+    if (khalf == 1) {
+      sm.part[ra][ca] = s00; sm.part[ra][cb] = s01; sm.part[rb][ca] = s10; sm.part[rb][cb] = s11;
+    }
+    __syncthreads();          // every read of this centroid tile is done; partial sums visible
+    if (ct + 1 < col_tiles) request_tile(ct + 1);
+    if (khalf == 0) {
+      const int c0 = ct * TC;
+      sm.s[ra][c0 + ca] = s00 + sm.part[ra][ca];
+      sm.s[ra][c0 + cb] = s01 + sm.part[ra][cb];
+      sm.s[rb][c0 + ca] = s10 + sm.part[rb][ca];
+      sm.s[rb][c0 + cb] = s11 + sm.part[rb][cb];
+    }
+    __syncthreads();          // part may be rewritten by the next tile; s complete after the last one
+  }
+  // the centroid tile needed first by pass B: tile 0 (still resident when there is only one)
+  if (need_grad && col_tiles > 1) request_tile(0);
+
+  // ---- log-sum-exp, loss, dw, db, G: warp <-> row
+  {
+    const int64_t gi = row0 + warp;
+    const bool live = gi < NM;
+    const int label = live ? static_cast<int>(gi / M) : -1;
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, w * sm.s[warp][j] - b);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) sum += expf(w * sm.s[warp][j] - b - mx);
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    float lrow = 0.f, dw_part = 0.f, db_part = 0.f;
+    if (live && lane == 0) lrow = lse - (w * sm.s[warp][label] - b);
+    if (need_grad) {
+      for (int j = lane; j < N; j += 32) {
+        float gval = 0.f;
+        if (live) {
+          const float sv = sm.s[warp][j];
+          const float p = expf(w * sv - b - lse);
+          const float pm = (p - (j == label ? 1.f : 0.f)) * inv_nm;
+          dw_part += pm * sv;
+          db_part -= pm;
+          gval = w * pm;
+        }
+        sm.gt[j][warp] = gval;
+      }
+      dw_part = warp_sum(dw_part);
+      db_part = warp_sum(db_part);
+    }
+    if (lane == 0) { sm.scal[0][warp] = lrow; sm.scal[1][warp] = dw_part; sm.scal[2][warp] = db_part; }
+  }
+  __syncthreads();
+  if (tid < 3 && (tid == 0 || need_grad)) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += sm.scal[tid][i];
+    atomicAdd(tid == 0 ? loss : (tid == 1 ? dw : db), tid == 0 ? a * inv_nm : a);
+  }
+  if (!need_grad) return;
+
+  // ---- pass B: dEhat = G Chat (registers, thread <-> column) and dChat += G^T Ehat (RED per centroid)
+  float er[RT], dacc[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) { er[r] = sm.e[r][tid]; dacc[r] = 0.f; }
+  for (int ct = 0; ct < col_tiles; ++ct) {
+    const int c0 = ct * TC;
+    const int cols = min(TC, N - c0);
+    if (col_tiles > 1) {
+      mbar_wait(bar, parity, 0x6e02);
+      parity ^= 1;
+    }
+    // every block starts its sweep at another centroid: the REDs of the 120 blocks then land on different lines (and
+    // L2 slices) at any one time instead of queueing on the same 1 KB row
+    const int rot = static_cast<int>(blockIdx.x % static_cast<unsigned>(cols));
+#pragma unroll 4
+    for (int i = 0; i < cols; ++i) {
+      const int c = (i + rot >= cols) ? i + rot - cols : i + rot;
+      const float4 g0 = *reinterpret_cast<const float4*>(&sm.gt[c0 + c][0]);
+      const float4 g1 = *reinterpret_cast<const float4*>(&sm.gt[c0 + c][4]);
+      const float cv = sm.c[c][tid];
+      dacc[0] = fmaf(g0.x, cv, dacc[0]); dacc[1] = fmaf(g0.y, cv, dacc[1]);
+      dacc[2] = fmaf(g0.z, cv, dacc[2]); dacc[3] = fmaf(g0.w, cv, dacc[3]);
+      dacc[4] = fmaf(g1.x, cv, dacc[4]); dacc[5] = fmaf(g1.y, cv, dacc[5]);
+      dacc[6] = fmaf(g1.z, cv, dacc[6]); dacc[7] = fmaf(g1.w, cv, dacc[7]);
+      float a = g0.x * er[0];
+      a = fmaf(g0.y, er[1], a); a = fmaf(g0.z, er[2], a); a = fmaf(g0.w, er[3], a);
+      a = fmaf(g1.x, er[4], a); a = fmaf(g1.y, er[5], a); a = fmaf(g1.z, er[6], a); a = fmaf(g1.w, er[7], a);
+      atomicAdd(dchat + static_cast<int64_t>(c0 + c) * GD + tid, a);
+    }
+    if (ct + 1 < col_tiles) {
+      __syncthreads();
+      request_tile(ct + 1);
+    }
+  }
+  // project out the radial component, write the row part of dE
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    const float dot = warp_sum(dacc[r] * er[r]);
+    if (lane == 0) sm.red[warp][r] = dot;
+  }
+  __syncthreads();
+  if (tid < RT) {
+    float a = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) a += sm.red[wv][tid];
+    sm.rowv[tid] = a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    const int64_t gi = row0 + r;
+    if (gi < NM) dE[gi * GD + tid] = (dacc[r] - sm.rowv[r] * er[r]) * sm.einv[r];
+  }
+}
+
+static int g_ge2e_tile_v2 = 1;     // spk_set_option("ge2e_row_tile_v2", 0/1): 0 = the first 16-row stage (A/B, tests)
+void ge2e_set_tile_v2(int on) { g_ge2e_tile_v2 = on != 0; }
+
 static size_t ge2e_simt_workspace_bytes(int N, int M) {
   const size_t NM = static_cast<size_t>(N) * M;
   return (2 * static_cast<size_t>(N) * GD + N + NM) * sizeof(float) + 256;
@@ -313,8 +537,10 @@ int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float*
 
   static PerDeviceOnce once;
   const int smem = static_cast<int>(sizeof(Ge2eSmem));
+  const int smem2 = static_cast<int>(sizeof(Ge2eTileSmem));
   SPK_TRY(once.run([&]() -> int {
     SPK_CUDA(cudaFuncSetAttribute(ge2e_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SPK_CUDA(cudaFuncSetAttribute(ge2e_rows_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
     return 0;
   }));
   const long long NM = 1LL * N * M;
@@ -325,7 +551,12 @@ int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float*
   // three launches in stream order: centroids | row tiles (loss, dE row part, dC) | centroid part of dE
   ge2e_fused_kernel<<<N, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 1);
   SPK_CUDA(cudaGetLastError());
-  ge2e_fused_kernel<<<row_tiles, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 2);
+  if (g_ge2e_tile_v2) {
+    const int tiles8 = static_cast<int>((NM + RT - 1) / RT);
+    ge2e_rows_tile_kernel<<<tiles8, 256, smem2, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, einv, dchat, need_grad);
+  } else {
+    ge2e_fused_kernel<<<row_tiles, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 2);
+  }
   SPK_CUDA(cudaGetLastError());
   if (need_grad) {
     ge2e_fused_kernel<<<N, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 3);

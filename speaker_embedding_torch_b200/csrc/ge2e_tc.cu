@@ -121,29 +121,38 @@ __global__ void __launch_bounds__(256) ge2e_rows_kernel(const float* __restrict_
   for (int64_t r = warp; r < NM; r += nwarps) {
     const float* srow = S + r * Np;
     const int label = static_cast<int>(r / M);
-    float mx = -INFINITY;
+    // one sweep for the maximum and the sum (per-lane running pair, rescaled when the maximum moves): the logits are
+    // read twice per call (here and for G) instead of three times
+    float mx = -INFINITY, sum = 0.f;
     for (int c0 = lane * 8; c0 < Np; c0 += 256) {
       const float4 a0 = *reinterpret_cast<const float4*>(srow + c0);
       const float4 a1 = *reinterpret_cast<const float4*>(srow + c0 + 4);
       const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float z[8], cm = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (c0 + i < N) mx = fmaxf(mx, w * v[i] - b);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int c0 = lane * 8; c0 < Np; c0 += 256) {
-      const float4 a0 = *reinterpret_cast<const float4*>(srow + c0);
-      const float4 a1 = *reinterpret_cast<const float4*>(srow + c0 + 4);
-      const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      for (int i = 0; i < 8; ++i) {
+        z[i] = (c0 + i < N) ? w * v[i] - b : -INFINITY;
+        cm = fmaxf(cm, z[i]);
+      }
+      if (cm > -INFINITY) {
+        const float nm = fmaxf(mx, cm);
+        float part = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (c0 + i < N) sum += expf(w * v[i] - b - mx);
+        for (int i = 0; i < 8; ++i) part += expf(z[i] - nm);      // exp(-inf) = 0 for the padding columns
+        sum = sum * expf(mx - nm) + part;                          // exp(-inf - nm) = 0 on the first chunk
+        mx = nm;
+      }
     }
-    sum = warp_sum(sum);
+    {
+      const float all = warp_max(mx);
+      sum = warp_sum(mx > -INFINITY ? sum * expf(mx - all) : 0.f);
+      mx = all;
+    }
     const float lse = mx + logf(sum);
     if (lane == 0) loss_acc += lse - (w * srow[label] - b);
     if (need_grad) {
+      // (keeping the row in shared memory for this sweep was measured: 8 warps x 16 KB leaves one block per SM at
+      // N = 4096 and the kernel ran 1.8x slower than re-reading the row, most of which L2 still holds)
       for (int c0 = lane * 8; c0 < Np; c0 += 256) {
         const float4 a0 = *reinterpret_cast<const float4*>(srow + c0);
         const float4 a1 = *reinterpret_cast<const float4*>(srow + c0 + 4);
@@ -247,8 +256,8 @@ int ge2e_tc(const float* E, int N, int M, const float* w, const float* b, float*
     SPK_TRY(gemm_run(g, st));
   }
   {
-    ProfScope prof("ge2e_tc.rows", 0, (need_grad ? 3.0 : 2.0) * NM * pl.Np * 4.0 + (need_grad ? 4.0 * NM * pl.Np : 0.0), st);
-    const int blocks = static_cast<int>(std::min<int64_t>((NM + 7) / 8, 148 * 8));
+    ProfScope prof("ge2e_tc.rows", 0, (need_grad ? 2.0 : 1.0) * NM * pl.Np * 4.0 + (need_grad ? 4.0 * NM * pl.Np : 0.0), st);
+    const int blocks = static_cast<int>(std::min<int64_t>((NM + 7) / 8, static_cast<int64_t>(device_sm_count()) * 8));
     ge2e_rows_kernel<<<blocks, 256, 0, st>>>(fp(pl.s), NM, N, static_cast<int>(pl.Np), M, w, b, bf(pl.g), pl.g_ps, scal3,
                                              need_grad);
     SPK_CUDA(cudaGetLastError());
