@@ -66,11 +66,17 @@ __global__ void __launch_bounds__(256) ge2e_prep_kernel(const float* __restrict_
                                                         elem_t* __restrict__ ehat, int64_t e_ps,
                                                         elem_t* __restrict__ chat, int64_t c_ps,
                                                         float* __restrict__ chat32, float* __restrict__ einv,
-                                                        float* __restrict__ cinv, float* __restrict__ scal, float eps) {
+                                                        float* __restrict__ cinv, float* __restrict__ loss,
+                                                        float* __restrict__ dw, float* __restrict__ db,
+                                                        float* __restrict__ dchat, float eps) {
   __shared__ float part[8][TD];
   __shared__ float red[8];
   const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (k == 0 && tid < 3) scal[tid] = 0.f;   // loss, dw, db accumulators
+  if (k == 0 && tid == 0) {                  // the accumulators of the row kernel: the caller's own scalars
+    loss[0] = 0.f;
+    if (dw != nullptr) { dw[0] = 0.f; db[0] = 0.f; }
+  }
+  if (dchat != nullptr) dchat[static_cast<int64_t>(k) * TD + tid] = 0.f;   // split-K target of the dChat GEMM
   float cp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int m = warp; m < M; m += 8) {
     const int64_t row = static_cast<int64_t>(k) * M + m;
@@ -110,7 +116,8 @@ __global__ void __launch_bounds__(256) ge2e_prep_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) ge2e_rows_kernel(const float* __restrict__ S, int64_t NM, int N, int Np, int M,
                                                         const float* __restrict__ w_ptr, const float* __restrict__ b_ptr,
                                                         elem_t* __restrict__ G, int64_t g_ps,
-                                                        float* __restrict__ scal, int need_grad) {
+                                                        float* __restrict__ loss, float* __restrict__ dw,
+                                                        float* __restrict__ db, int need_grad) {
   __shared__ float red[3][8];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -179,10 +186,10 @@ __global__ void __launch_bounds__(256) ge2e_rows_kernel(const float* __restrict_
   db_acc = warp_sum(db_acc);
   if (lane == 0) { red[0][wib] = loss_acc; red[1][wib] = dw_acc; red[2][wib] = db_acc; }
   __syncthreads();
-  if (threadIdx.x < 3) {
+  if (threadIdx.x == 0 || (threadIdx.x < 3 && need_grad)) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += red[threadIdx.x][i];
-    atomicAdd(scal + threadIdx.x, threadIdx.x == 0 ? s * inv_nm : s);
+    atomicAdd(threadIdx.x == 0 ? loss : (threadIdx.x == 1 ? dw : db), threadIdx.x == 0 ? s * inv_nm : s);
   }
 }
 
@@ -238,11 +245,11 @@ int ge2e_tc(const float* E, int N, int M, const float* w, const float* b, float*
   auto fp = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   const int need_grad = dE != nullptr;
   const int64_t NM = pl.NM;
-  float* scal3 = fp(pl.scal);   // loss, dw, db accumulators (zeroed by the prep kernel)
   {
     ProfScope prof("ge2e_tc.prep", 0, 4.0 * NM * TD + 6.0 * NM * TD, st);
     ge2e_prep_kernel<<<N, 256, 0, st>>>(E, N, M, bf(pl.ehat), pl.ehat_ps, bf(pl.chat), pl.chat_ps, fp(pl.chat32),
-                                        fp(pl.einv), fp(pl.cinv), scal3, 1e-8f);
+                                        fp(pl.einv), fp(pl.cinv), loss, need_grad ? dw : nullptr, need_grad ? db : nullptr,
+                                        need_grad ? fp(pl.dchat) : nullptr, 1e-8f);
     SPK_CUDA(cudaGetLastError());
   }
   {  // S = Ehat Chat^T
@@ -258,7 +265,7 @@ int ge2e_tc(const float* E, int N, int M, const float* w, const float* b, float*
   {
     ProfScope prof("ge2e_tc.rows", 0, (need_grad ? 2.0 : 1.0) * NM * pl.Np * 4.0 + (need_grad ? 4.0 * NM * pl.Np : 0.0), st);
     const int blocks = static_cast<int>(std::min<int64_t>((NM + 7) / 8, static_cast<int64_t>(device_sm_count()) * 8));
-    ge2e_rows_kernel<<<blocks, 256, 0, st>>>(fp(pl.s), NM, N, static_cast<int>(pl.Np), M, w, b, bf(pl.g), pl.g_ps, scal3,
+    ge2e_rows_kernel<<<blocks, 256, 0, st>>>(fp(pl.s), NM, N, static_cast<int>(pl.Np), M, w, b, bf(pl.g), pl.g_ps, loss, dw, db,
                                              need_grad);
     SPK_CUDA(cudaGetLastError());
   }
@@ -275,7 +282,6 @@ int ge2e_tc(const float* E, int N, int M, const float* w, const float* b, float*
       g.epi.out = fp(pl.dehat); g.epi.out_ld = TD;
       SPK_TRY(gemm_run(g, st));
     }
-    SPK_CUDA(cudaMemsetAsync(fp(pl.dchat), 0, static_cast<size_t>(N) * TD * 4, st));
     {  // dChat = G^T Ehat
       GemmProblem g;
       g.tag = "ge2e_tc.gemm_dchat";
@@ -299,12 +305,6 @@ int ge2e_tc(const float* E, int N, int M, const float* w, const float* b, float*
                                                  dE, NM, M);
       SPK_CUDA(cudaGetLastError());
     }
-  }
-  // scalars out (device -> device, stream ordered)
-  SPK_CUDA(cudaMemcpyAsync(loss, scal3, sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (need_grad) {
-    SPK_CUDA(cudaMemcpyAsync(dw, scal3 + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    SPK_CUDA(cudaMemcpyAsync(db, scal3 + 2, sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   return 0;
 }
