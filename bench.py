@@ -753,6 +753,13 @@ def run_ge2e(args):
         launches = sum(v["launches"] for k, v in rep.items() if k.startswith("ge2e")) // iters
         us_graph = _ge2e_graph_us(e.detach(), crit, N, M, D, reps=20 if N <= 1024 else 4)
         us = us_graph if us_graph is not None else us_stages
+        us_no_pdl = None
+        if N < 256 and us_graph is not None:                   # A/B of the programmatic dependent launch of stages 2, 3
+            _native.set_option("ge2e_dependent_launch", 0)
+            try:
+                us_no_pdl = _ge2e_graph_us(e.detach(), crit, N, M, D, reps=20)
+            finally:
+                _native.set_option("ge2e_dependent_launch", 1)
         nbytes, flops = 2.0 * N * M * D * 4, 6.0 * N * M * N * D
         t_hbm, t_tc = nbytes / (pk["hbm"] * 1e9), flops / (pk["tf_burst"] * 1e12)
         bound = "hbm" if t_hbm > t_tc else "tensor"
@@ -760,6 +767,7 @@ def run_ge2e(args):
         peak = pk["hbm"] if bound == "hbm" else pk["tf_burst"]
         rows.append({"N": N, "M": M, "us": round(us, 1), "us_sum_of_stage_events": round(us_stages, 1),
                      "timing": "graph replay" if us_graph is not None else "stage events",
+                     "us_without_dependent_launch": None if us_no_pdl is None else round(us_no_pdl, 1),
                      "stage_events_us": {k: round(v["ms"] / iters * 1e3, 1) for k, v in sorted(rep.items())
                                          if k.startswith("ge2e")},
                      "launches": launches, "loss": round(loss.item(), 5),

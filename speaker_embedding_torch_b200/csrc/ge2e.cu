@@ -33,6 +33,13 @@ struct Ge2eSmem {
   float rowv[TR];
 };
 
+// Programmatic dependent launch: the three stages are launched back to back with the stream-serialisation attribute, a
+// stage lets its successor start launching as soon as all of its own blocks are resident (pdl_trigger) and touches
+// its predecessor's results only after pdl_wait (= predecessor grid complete and flushed).  Both are no-ops in a
+// launch without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float block_sum_256(float v, float* red8) {
   v = warp_sum(v);
   __syncthreads();
@@ -61,6 +68,7 @@ ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __rest
 
   // ------------------------------------------------------------------ phase 1
   if (phase == 1) {
+  pdl_trigger();
   if (blockIdx.x == 0 && tid == 0) {
     loss[0] = 0.f;
     if (need_grad) { dw[0] = 0.f; db[0] = 0.f; }
@@ -278,6 +286,7 @@ ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __rest
   }
 
   // ------------------------------------------------------------------ phase 3
+  pdl_wait();
   for (int k = blockIdx.x; k < N; k += gridDim.x) {
     const float dc = dchat[static_cast<int64_t>(k) * GD + tid];
     const float ch = chat[static_cast<int64_t>(k) * GD + tid];
@@ -337,11 +346,13 @@ ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __
   const uint32_t bar = smem_u32(&sm.bar);
   uint32_t parity = 0;
 
+  pdl_trigger();
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();               // the centroid stage is complete: chat, einv, zeroed accumulators
   // warp 0 requests centroid tile `ct`; every thread of the block has finished reading the previous tile (caller syncs)
   auto request_tile = [&](int ct) {
     if (warp == 0) {
@@ -509,6 +520,8 @@ ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __
 
 static int g_ge2e_tile_v2 = 1;     // spk_set_option("ge2e_row_tile_v2", 0/1): 0 = the first 16-row stage (A/B, tests)
 void ge2e_set_tile_v2(int on) { g_ge2e_tile_v2 = on != 0; }
+static int g_ge2e_pdl = 1;         // spk_set_option("ge2e_dependent_launch", 0/1): programmatic dependent launch of stages 2, 3
+void ge2e_set_pdl(int on) { g_ge2e_pdl = on != 0; }
 
 static size_t ge2e_simt_workspace_bytes(int N, int M) {
   const size_t NM = static_cast<size_t>(N) * M;
@@ -551,16 +564,31 @@ int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float*
   // three launches in stream order: centroids | row tiles (loss, dE row part, dC) | centroid part of dE
   ge2e_fused_kernel<<<N, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 1);
   SPK_CUDA(cudaGetLastError());
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cfg.attrs = pdl_attr;
+  const bool pdl = g_ge2e_tile_v2 && g_ge2e_pdl;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const float* chat_c = chat;
+  const float* einv_c = einv;
   if (g_ge2e_tile_v2) {
-    const int tiles8 = static_cast<int>((NM + RT - 1) / RT);
-    ge2e_rows_tile_kernel<<<tiles8, 256, smem2, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, einv, dchat, need_grad);
+    cfg.gridDim = dim3(static_cast<unsigned>((NM + RT - 1) / RT));
+    cfg.dynamicSmemBytes = smem2;
+    SPK_CUDA(cudaLaunchKernelEx(&cfg, ge2e_rows_tile_kernel, E, N, M, w, b, loss, dE, dw, db, chat_c, einv_c, dchat,
+                                need_grad));
   } else {
     ge2e_fused_kernel<<<row_tiles, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 2);
-  }
-  SPK_CUDA(cudaGetLastError());
-  if (need_grad) {
-    ge2e_fused_kernel<<<N, 256, smem, st>>>(E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad, eps, 3);
     SPK_CUDA(cudaGetLastError());
+  }
+  if (need_grad) {
+    cfg.gridDim = dim3(N);
+    cfg.dynamicSmemBytes = smem;
+    SPK_CUDA(cudaLaunchKernelEx(&cfg, ge2e_fused_kernel, E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad,
+                                eps, 3));
   }
   return 0;
 }
