@@ -310,13 +310,14 @@ ge2e_fused_kernel(const float* __restrict__ E, int N, int M, const float* __rest
 constexpr int RT = 8;            // rows per tile
 constexpr int EPAD = GD + 4;     // padded row: the four rows a warp reads at one d land in different banks
 constexpr int NCAP = 256;        // this path serves N < GE2E_TC_MIN_SPEAKERS
+constexpr int TILE_THREADS = 512;
 
 struct Ge2eTileSmem {
   float c[TC][CPAD];             // normalised centroid tile (bulk-copy destination)
   float e[RT][EPAD];             // normalised rows
   float s[RT][NCAP];             // cosine similarities of the whole row
   float gt[NCAP][RT];            // G^T: the 8 row values of one centroid are two 16-byte broadcasts
-  float part[RT][TC];            // upper K half of the S tile
+  float part[3][RT][TC];         // K quarters 1..3 of the S tile
   float red[8][RT];
   float scal[3][8];
   float rowv[RT];
@@ -330,7 +331,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(TILE_THREADS, 2)
 ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __restrict__ w_ptr,
                       const float* __restrict__ b_ptr, float* __restrict__ loss, float* __restrict__ dE,
                       float* __restrict__ dw, float* __restrict__ db, const float* __restrict__ chat,
@@ -369,7 +370,7 @@ ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __
   };
   request_tile(0);
 
-  {  // this block's rows, normalised: warp <-> row
+  if (warp < RT) {  // this block's rows, normalised: warp <-> row (warps 0..7)
     const int64_t gi = row0 + warp;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     float sc = 0.f;
@@ -387,15 +388,15 @@ ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __
   __syncthreads();
 
   // ---- pass A: S = Ehat Chat^T for the whole rows
-  const int khalf = warp >> 2, wq = warp & 3, lr = lane >> 3, lc = lane & 7;
+  const int kq = warp >> 2, wq = warp & 3, lr = lane >> 3, lc = lane & 7;      // kq: K quarter of the 16 warps
   const int ra = lr, rb = lr + 4, ca = 16 * wq + lc, cb = ca + 8;
   for (int ct = 0; ct < col_tiles; ++ct) {
     mbar_wait(bar, parity, 0x6e01);
     parity ^= 1;
     float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
-    const int d0 = khalf * (GD / 2);
+    const int d0 = kq * (GD / 4);
 #pragma unroll 8
-    for (int d = d0; d < d0 + GD / 2; d += 4) {
+    for (int d = d0; d < d0 + GD / 4; d += 4) {
       const float4 ea = *reinterpret_cast<const float4*>(&sm.e[ra][d]);
       const float4 eb = *reinterpret_cast<const float4*>(&sm.e[rb][d]);
       const float4 va = *reinterpret_cast<const float4*>(&sm.c[ca][d]);
@@ -405,25 +406,26 @@ ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __
       s10 = fmaf(eb.x, va.x, s10); s10 = fmaf(eb.y, va.y, s10); s10 = fmaf(eb.z, va.z, s10); s10 = fmaf(eb.w, va.w, s10);
       s11 = fmaf(eb.x, vb.x, s11); s11 = fmaf(eb.y, vb.y, s11); s11 = fmaf(eb.z, vb.z, s11); s11 = fmaf(eb.w, vb.w, s11);
     }
-    if (khalf == 1) {
-      sm.part[ra][ca] = s00; sm.part[ra][cb] = s01; sm.part[rb][ca] = s10; sm.part[rb][cb] = s11;
+    if (kq != 0) {
+      float(*pt)[TC] = sm.part[kq - 1];
+      pt[ra][ca] = s00; pt[ra][cb] = s01; pt[rb][ca] = s10; pt[rb][cb] = s11;
     }
     __syncthreads();          // every read of this centroid tile is done; partial sums visible
     if (ct + 1 < col_tiles) request_tile(ct + 1);
-    if (khalf == 0) {
+    if (kq == 0) {
       const int c0 = ct * TC;
-      sm.s[ra][c0 + ca] = s00 + sm.part[ra][ca];
-      sm.s[ra][c0 + cb] = s01 + sm.part[ra][cb];
-      sm.s[rb][c0 + ca] = s10 + sm.part[rb][ca];
-      sm.s[rb][c0 + cb] = s11 + sm.part[rb][cb];
+      sm.s[ra][c0 + ca] = s00 + (sm.part[0][ra][ca] + sm.part[1][ra][ca] + sm.part[2][ra][ca]);
+      sm.s[ra][c0 + cb] = s01 + (sm.part[0][ra][cb] + sm.part[1][ra][cb] + sm.part[2][ra][cb]);
+      sm.s[rb][c0 + ca] = s10 + (sm.part[0][rb][ca] + sm.part[1][rb][ca] + sm.part[2][rb][ca]);
+      sm.s[rb][c0 + cb] = s11 + (sm.part[0][rb][cb] + sm.part[1][rb][cb] + sm.part[2][rb][cb]);
     }
     __syncthreads();          // part may be rewritten by the next tile; s complete after the last one
   }
   // the centroid tile needed first by pass B: tile 0 (still resident when there is only one)
   if (need_grad && col_tiles > 1) request_tile(0);
 
-  // ---- log-sum-exp, loss, dw, db, G: warp <-> row
-  {
+  // ---- log-sum-exp, loss, dw, db, G: warp <-> row (warps 0..7)
+  if (warp < RT) {
     const int64_t gi = row0 + warp;
     const bool live = gi < NM;
     const int label = live ? static_cast<int>(gi / M) : -1;
@@ -464,9 +466,11 @@ ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __
   if (!need_grad) return;
 
   // ---- pass B: dEhat = G Chat (registers, thread <-> column) and dChat += G^T Ehat (RED per centroid)
+  // the two halves of the block take alternate centroids of the sweep; thread <-> column `col` in both
+  const int half = tid >> 8, col = tid & (GD - 1);
   float er[RT], dacc[RT];
 #pragma unroll
-  for (int r = 0; r < RT; ++r) { er[r] = sm.e[r][tid]; dacc[r] = 0.f; }
+  for (int r = 0; r < RT; ++r) { er[r] = sm.e[r][col]; dacc[r] = 0.f; }
   for (int ct = 0; ct < col_tiles; ++ct) {
     const int c0 = ct * TC;
     const int cols = min(TC, N - c0);
@@ -478,11 +482,11 @@ ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __
     // L2 slices) at any one time instead of queueing on the same 1 KB row
     const int rot = static_cast<int>(blockIdx.x % static_cast<unsigned>(cols));
 #pragma unroll 4
-    for (int i = 0; i < cols; ++i) {
+    for (int i = half; i < cols; i += 2) {
       const int c = (i + rot >= cols) ? i + rot - cols : i + rot;
       const float4 g0 = *reinterpret_cast<const float4*>(&sm.gt[c0 + c][0]);
       const float4 g1 = *reinterpret_cast<const float4*>(&sm.gt[c0 + c][4]);
-      const float cv = sm.c[c][tid];
+      const float cv = sm.c[c][col];
       dacc[0] = fmaf(g0.x, cv, dacc[0]); dacc[1] = fmaf(g0.y, cv, dacc[1]);
       dacc[2] = fmaf(g0.z, cv, dacc[2]); dacc[3] = fmaf(g0.w, cv, dacc[3]);
       dacc[4] = fmaf(g1.x, cv, dacc[4]); dacc[5] = fmaf(g1.y, cv, dacc[5]);
@@ -490,18 +494,27 @@ ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __
       float a = g0.x * er[0];
       a = fmaf(g0.y, er[1], a); a = fmaf(g0.z, er[2], a); a = fmaf(g0.w, er[3], a);
       a = fmaf(g1.x, er[4], a); a = fmaf(g1.y, er[5], a); a = fmaf(g1.z, er[6], a); a = fmaf(g1.w, er[7], a);
-      atomicAdd(dchat + static_cast<int64_t>(c0 + c) * GD + tid, a);
+      atomicAdd(dchat + static_cast<int64_t>(c0 + c) * GD + col, a);
     }
     if (ct + 1 < col_tiles) {
       __syncthreads();
       request_tile(ct + 1);
     }
   }
-  // project out the radial component, write the row part of dE
+  // the upper half hands its accumulators over (S is dead: its buffer carries them)
+  if (half == 1) {
 #pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    const float dot = warp_sum(dacc[r] * er[r]);
-    if (lane == 0) sm.red[warp][r] = dot;
+    for (int r = 0; r < RT; ++r) sm.s[r][col] = dacc[r];
+  }
+  __syncthreads();
+  // project out the radial component, write the row part of dE
+  if (half == 0) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      dacc[r] += sm.s[r][col];
+      const float dot = warp_sum(dacc[r] * er[r]);
+      if (lane == 0) sm.red[warp][r] = dot;
+    }
   }
   __syncthreads();
   if (tid < RT) {
@@ -511,10 +524,12 @@ ge2e_rows_tile_kernel(const float* __restrict__ E, int N, int M, const float* __
     sm.rowv[tid] = a;
   }
   __syncthreads();
+  if (half == 0) {
 #pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    const int64_t gi = row0 + r;
-    if (gi < NM) dE[gi * GD + tid] = (dacc[r] - sm.rowv[r] * er[r]) * sm.einv[r];
+    for (int r = 0; r < RT; ++r) {
+      const int64_t gi = row0 + r;
+      if (gi < NM) dE[gi * GD + col] = (dacc[r] - sm.rowv[r] * er[r]) * sm.einv[r];
+    }
   }
 }
 
@@ -577,6 +592,7 @@ int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float*
   const float* einv_c = einv;
   if (g_ge2e_tile_v2) {
     cfg.gridDim = dim3(static_cast<unsigned>((NM + RT - 1) / RT));
+    cfg.blockDim = dim3(TILE_THREADS);
     cfg.dynamicSmemBytes = smem2;
     SPK_CUDA(cudaLaunchKernelEx(&cfg, ge2e_rows_tile_kernel, E, N, M, w, b, loss, dE, dw, db, chat_c, einv_c, dchat,
                                 need_grad));
@@ -586,6 +602,7 @@ int ge2e_fused(const float* E, int N, int M, int D, const float* w, const float*
   }
   if (need_grad) {
     cfg.gridDim = dim3(N);
+    cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = smem;
     SPK_CUDA(cudaLaunchKernelEx(&cfg, ge2e_fused_kernel, E, N, M, w, b, loss, dE, dw, db, chat, cinv, einv, dchat, need_grad,
                                 eps, 3));
