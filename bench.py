@@ -751,6 +751,8 @@ def run_ge2e(args):
         _native.prof_enable(False)
         us_stages = sum(v["ms"] for k, v in rep.items() if k.startswith("ge2e")) / iters * 1e3
         launches = sum(v["launches"] for k, v in rep.items() if k.startswith("ge2e")) // iters
+        if N < 256:
+            launches = 3          # one profiler scope around the three stage kernels of the small-N path
         us_graph = _ge2e_graph_us(e.detach(), crit, N, M, D, reps=20 if N <= 1024 else 4)
         us = us_graph if us_graph is not None else us_stages
         us_no_pdl = None
