@@ -311,6 +311,7 @@ constexpr int RT = 8;            // rows per tile
 constexpr int EPAD = GD + 4;     // padded row: the four rows a warp reads at one d land in different banks
 constexpr int NCAP = 256;        // this path serves N < GE2E_TC_MIN_SPEAKERS
 constexpr int TILE_THREADS = 512;
+static_assert(NCAP >= GE2E_TC_MIN_SPEAKERS - 1 && NCAP % TC == 0, "the row cache must hold every N of the SIMT path");
 
 struct Ge2eTileSmem {
   float c[TC][CPAD];             // normalised centroid tile (bulk-copy destination)
