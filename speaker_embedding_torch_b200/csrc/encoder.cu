@@ -338,23 +338,32 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const elem_t* __restrict_
 #pragma unroll
   for (int i = 0; i < 8; ++i) em[warp][lane * 8 + i] = acc[i];
   // ---- projection: 32 outputs per round; lane = output within the round, warp = utterance
+  // The next round's 32 weight rows travel from L2 into registers while this round is multiplied (one L2 latency per
+  // round instead of four serialised load batches); four accumulators break the 256-long FMA chain.
   float eo[8];
+  float wv[32];
+#pragma unroll
+  for (int it = 0; it < 32; ++it) wv[it] = __ldg(wp + static_cast<int64_t>(it) * 256 + tid);
 #pragma unroll 1
   for (int t = 0; t < 8; ++t) {
     __syncthreads();                                 // em is written / the previous round's tile has been consumed
-#pragma unroll 8
-    for (int it = 0; it < 32; ++it) wt[tid][it] = __ldg(wp + static_cast<int64_t>(t * 32 + it) * 256 + tid);
+#pragma unroll
+    for (int it = 0; it < 32; ++it) wt[tid][it] = wv[it];
+    if (t + 1 < 8) {
+#pragma unroll
+      for (int it = 0; it < 32; ++it) wv[it] = __ldg(wp + static_cast<int64_t>((t + 1) * 32 + it) * 256 + tid);
+    }
     __syncthreads();
-    float d = 0.f;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll 8
     for (int k = 0; k < 256; k += 4) {
       const float4 e4 = *reinterpret_cast<const float4*>(&em[warp][k]);
-      d = fmaf(wt[k][lane], e4.x, d);
-      d = fmaf(wt[k + 1][lane], e4.y, d);
-      d = fmaf(wt[k + 2][lane], e4.z, d);
-      d = fmaf(wt[k + 3][lane], e4.w, d);
+      d0 = fmaf(wt[k][lane], e4.x, d0);
+      d1 = fmaf(wt[k + 1][lane], e4.y, d1);
+      d2 = fmaf(wt[k + 2][lane], e4.z, d2);
+      d3 = fmaf(wt[k + 3][lane], e4.w, d3);
     }
-    eo[t] = d + __ldg(bp + t * 32 + lane);
+    eo[t] = ((d0 + d1) + (d2 + d3)) + __ldg(bp + t * 32 + lane);
   }
   if (valid) {
     float ss = 0.f;
@@ -423,11 +432,18 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   float dm[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) dm[j] = 0.f;
+  float wv[32];                                      // next round's weight rows in flight while this one is consumed
+#pragma unroll
+  for (int it = 0; it < 32; ++it) wv[it] = __ldg(wp + static_cast<int64_t>(it) * 256 + tid);
 #pragma unroll 1
   for (int t = 0; t < 8; ++t) {
     __syncthreads();
-#pragma unroll 8
-    for (int it = 0; it < 32; ++it) wt[it][tid] = __ldg(wp + static_cast<int64_t>(t * 32 + it) * 256 + tid);
+#pragma unroll
+    for (int it = 0; it < 32; ++it) wt[it][tid] = wv[it];
+    if (t + 1 < 8) {
+#pragma unroll
+      for (int it = 0; it < 32; ++it) wv[it] = __ldg(wp + static_cast<int64_t>((t + 1) * 32 + it) * 256 + tid);
+    }
     __syncthreads();
 #pragma unroll 4
     for (int nl = 0; nl < 32; ++nl) {
