@@ -93,6 +93,9 @@ class _FusedBase(Optimizer):
         for _, _, plist in chunks:            # only after every launch was accepted
             for p in plist:
                 self.state[p]["step"] += 1
+            # the kernels wrote the parameters through raw pointers: tell torch (version counters are what autograd's
+            # saved-tensor checks and the inference weight cache of Modules.py look at)
+            torch.autograd.graph.increment_version(plist)
         return loss
 
     def grad_norm(self):
