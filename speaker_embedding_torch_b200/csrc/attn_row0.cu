@@ -10,6 +10,7 @@
 // Layouts: q0 [B, 256] and kv [B*T, 512] (K | V, head h at columns h*64) are split-fp16 tensors;
 // probabilities p / p*keep are kept in fp32 [B*H, Tp] for the backward pass.
 #include "rowops.h"
+#include "ptx.cuh"
 
 namespace spk {
 
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_fwd_kernel(
     const elem_t* __restrict__ q0, int64_t q_ps, const elem_t* __restrict__ kv, int64_t kv_ps, int planes,
     elem_t* __restrict__ att0, int64_t a_ps, float* __restrict__ p0, float* __restrict__ pd0, DropCfg drop,
     uint32_t site, int B, int H, int T, int Tp) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t bh = static_cast<int64_t>(blockIdx.x) * R0_WARPS + warp;
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(32 * R0_WARPS) attn_row0_bwd_kernel(
     const float* __restrict__ pd0, elem_t* __restrict__ dq0, int64_t dq_ps, elem_t* __restrict__ dkv,
     int64_t dkv_ps, float* __restrict__ dbias /* [768] q | k | v */, const float* __restrict__ gscale, int B, int H,
     int T, int Tp) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t bh = static_cast<int64_t>(blockIdx.x) * R0_WARPS + warp;

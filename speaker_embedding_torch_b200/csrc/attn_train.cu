@@ -126,6 +126,7 @@ struct AttnTrainFwdArgs {
 
 template <int PL>
 __global__ void __launch_bounds__(ATF_THREADS, 1) attn_train_fwd_kernel(const __grid_constant__ AttnTrainFwdArgs a) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   using Cfg = AtfCfg<PL>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
@@ -435,6 +436,7 @@ constexpr int ATW_OFF_BAR = ATW_OFF_STG + 16384, ATW_SMEM = ATW_OFF_BAR + 128;
 constexpr int ATW_TMEM_O = 192;
 
 __global__ void __launch_bounds__(ATW_THREADS, 2) attn_train_fwd2_kernel(const __grid_constant__ AttnTrainFwdArgs a) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sQ = sbase, sKV = sbase + ATW_OFF_KV;
@@ -682,6 +684,7 @@ constexpr int ATI_OFF_STG = ATI_OFF_X + 2048, ATI_OFF_BAR = ATI_OFF_STG + 16384,
 constexpr int ATI_TMEM_O = 192;
 
 __global__ void __launch_bounds__(ATI_THREADS, 2) attn_infer_fwd_kernel(const __grid_constant__ AttnTrainFwdArgs a) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sQ = sbase, sK = sbase + ATI_OFF_K, sV = sbase + ATI_OFF_V;
@@ -1008,6 +1011,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __grid_constant__ AttnTrainBwdArgs a) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sQ = sbase, sdO = sbase + ATB_OFF_DO, sK = sbase + ATB_OFF_K, sV = sbase + ATB_OFF_V, sdS = sbase + ATB_OFF_DS;
@@ -1371,6 +1375,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_train_bwd_kernel(const __
 __global__ void __launch_bounds__(256) attn_delta_kernel(const elem_t* __restrict__ dout, int64_t do_ps,
                                                          const elem_t* __restrict__ out, int64_t o_ps,
                                                          float* __restrict__ delta, int64_t tokens, int T) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;

@@ -612,6 +612,7 @@ int encoder_forward(const spk_encoder_config& cfg, const spk_encoder_params& w, 
   SPK_CHECK((reinterpret_cast<uintptr_t>(ws_v) & 255) == 0, "encoder: workspace must be 256-byte aligned");
   SPK_CHECK(!training || keep, "encoder: training forward needs keep_stash (dropout P buffers live in the stash)");
   Ctx c{pl, reinterpret_cast<char*>(ws_v), st, P};
+  GemmDependentLaunchScope dependent_launch(!keep && !training);   // inference: GEMM prologues under the previous kernel's tail
   const int64_t Mt = pl.Mt, D = pl.D, F = pl.F;
   const int Tp = pl.Tp, H = pl.H;
   const DropCfg drop_pe = make_drop(seed, cfg.pe_dropout, training != 0);

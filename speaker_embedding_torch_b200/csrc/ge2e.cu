@@ -33,13 +33,8 @@ struct Ge2eSmem {
   float rowv[TR];
 };
 
-// Programmatic dependent launch: the three stages are launched back to back with the stream-serialisation attribute, a
-// stage lets its successor start launching as soon as all of its own blocks are resident (pdl_trigger) and touches
-// its predecessor's results only after pdl_wait (= predecessor grid complete and flushed).  Both are no-ops in a
-// launch without the attribute.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
+// Programmatic dependent launch (pdl_trigger / pdl_wait, ptx.cuh): the three stages are launched back to back with the
+// stream-serialisation attribute; a stage touches its predecessor's results only after pdl_wait().
 __device__ __forceinline__ float block_sum_256(float v, float* red8) {
   v = warp_sum(v);
   __syncthreads();

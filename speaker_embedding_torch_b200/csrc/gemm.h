@@ -89,6 +89,16 @@ struct GemmProblem {
 int gemm_run(const GemmProblem& p, cudaStream_t stream);
 
 int device_sm_count();
+void gemm_set_dependent_launch(int mode);   // programmatic dependent launch of the GEMM kernels: 0 off, 1 inference, 2 all
+// While one lives (and the option is 1), the calling thread's GEMM launches carry the dependent-launch attribute.
+struct GemmDependentLaunchScope {
+  explicit GemmDependentLaunchScope(bool on);
+  ~GemmDependentLaunchScope();
+  GemmDependentLaunchScope(const GemmDependentLaunchScope&) = delete;
+  GemmDependentLaunchScope& operator=(const GemmDependentLaunchScope&) = delete;
+ private:
+  bool on_;
+};
 void gemm_set_cta_pairs(int on);   // route eligible multi-plane GEMMs through the cta_group::2 kernel
 
 // fp16 4-D tiled tensor map {dims[0] (contiguous), dims[1], dims[2], dims[3]} with element strides for dims 1..3,

@@ -57,6 +57,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
   }
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled while its predecessor in
+// the stream is still running: pdl_trigger() in the predecessor allows that as soon as all of its CTAs are resident (or
+// done), pdl_wait() in the successor returns once the predecessor grid has completed and its writes are visible.  The
+// successor's prologue (barrier init, tensor-memory allocation, descriptor prefetch) and its launch latency then overlap
+// the predecessor's tail.  Both are no-ops in a launch without the attribute.  Rule: nothing before pdl_wait() may touch
+// global memory that an earlier kernel of the stream writes or reads.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- CTA pairs (clusters of 2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

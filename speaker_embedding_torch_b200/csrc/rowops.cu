@@ -2,6 +2,7 @@
 // column sums (bias gradients).  All are coalesced 16-byte-vector kernels with warp-shuffle
 // reductions; rows of the 256-wide model dimension are handled one warp per row (8 elements / lane).
 #include "rowops.h"
+#include "ptx.cuh"
 
 #include <cuda_fp16.h>
 
@@ -41,6 +42,7 @@ int pack_weights(const PackTable& tab, void* dst, int64_t plane_stride, int plan
 template <int C, typename TIn>
 __global__ void mel_pack_kernel(const TIn* __restrict__ mel, elem_t* __restrict__ out, int64_t plane_stride,
                                 int planes, int T, int L, int hop, int spw) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   __shared__ float tile[C][33];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 32;
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const elem_t* __restrict__ 
                                                      elem_t* __restrict__ y, int64_t y_ps, int y_planes,
                                                      float2* __restrict__ stats, int64_t rows, int64_t row_stride_rows,
                                                      float eps) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_kernel(const elem_t* __restrict
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      float* __restrict__ dbias, int64_t rows,
                                                      const float* __restrict__ gscale) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   __shared__ float red[3][8][256];
   // PL > 0: both inputs have PL planes (compile-time: fewer registers, three blocks per SM); PL == 0: run-time counts
   const int dy_planes = PL > 0 ? PL : dy_planes_rt, z_planes = PL > 0 ? PL : z_planes_rt;
@@ -604,6 +608,7 @@ __global__ void __launch_bounds__(256) prenet_bwd_kernel(const elem_t* __restric
                                                          DropCfg drop, uint32_t site, elem_t* __restrict__ du, int64_t du_ps,
                                                          float* __restrict__ dalpha, float* __restrict__ dbias, int64_t rows,
                                                          int T, const float* __restrict__ gscale) {
+  pdl_trigger();   // the next kernel of the stream may start its prologue (ptx.cuh)
   __shared__ float red[8];
   __shared__ float cs[8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
