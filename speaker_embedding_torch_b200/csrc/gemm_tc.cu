@@ -1117,10 +1117,10 @@ static int configure_all() {
 }
 
 
-// spk_set_option("gemm_dependent_launch", 0 | 1 | 2): 0 off, 1 (default) inside the inference forward, 2 every GEMM.
+// spk_set_option("gemm_dependent_launch", 0 | 1 | 2): 0 off, 1 inside the inference forward only, 2 (default) every GEMM.
 // Measured (same process, alternating): inference 960 x 200 frames 1.904 -> 1.842 ms, 7 x 33 frames 0.246 -> 0.237 ms,
-// identical d-vectors; the power-capped training step showed no gain (8.76 vs 8.83 ms, inside its drift).
-static int g_gemm_pdl = 1;
+// identical d-vectors; training step, drift-balanced order (tools/train_ab_balanced.py): 8.623 (1) -> 8.574 ms (2).
+static int g_gemm_pdl = 2;
 void gemm_set_dependent_launch(int on) { g_gemm_pdl = on; }
 static thread_local int t_gemm_pdl_scope = 0;      // > 0 while an inference forward enqueues its kernels
 GemmDependentLaunchScope::GemmDependentLaunchScope(bool on) : on_(on) { if (on_) ++t_gemm_pdl_scope; }
