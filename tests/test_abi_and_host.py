@@ -47,6 +47,24 @@ def test_workspace_query_is_host_only(native):
     assert L.spk_ge2e_workspace_bytes(64, 15) > 64 * 256 * 8
 
 
+def test_option_switches_are_host_only_and_documented(native):
+    """spk_set_option touches no device: every switch INTEGRATION.md lists is accepted here (and put back to its
+    default), an unknown name is rejected with a message."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    defaults = {"prune_last_layer": 1, "fused_training_attention": 1, "fused_inference_attention": 1,
+                "inference_attention_two_ctas": 1, "training_attention_two_ctas": 1, "fused_layernorm": 2,
+                "gemm_cta_pairs": 1, "gemm_dependent_launch": 2, "ge2e_row_tile_v2": 1, "ge2e_dependent_launch": 1,
+                "grad_scale_log2": 12}
+    flags = native.plan_flags()
+    for name, default in defaults.items():
+        assert "`%s`" % name in text, name
+        native.set_option(name, 0 if name != "grad_scale_log2" else 10)
+        native.set_option(name, default)
+    assert native.plan_flags() == flags
+    with pytest.raises(RuntimeError, match="unknown option"):
+        native.set_option("no_such_option", 1)
+
+
 def _model():
     from speaker_embedding_torch_b200 import GE2E
     from speaker_embedding_torch_b200.Arg_Parser import default_hyper_parameters
